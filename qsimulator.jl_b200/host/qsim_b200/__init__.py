@@ -1,0 +1,18 @@
+"""qsim_b200: host-side mirror of QSimulator.jl's interface for the time-evolution hot path.
+
+Same names and argument meaning as the reference (Julia's `!` suffix dropped):
+systems (systems.jl), operators and drive factories (operators.jl), CompositeQSystem
+assembly (composite_systems.jl) and the four solvers (time_evolution.jl:29-164), which call
+the CUDA shared library through the C ABI of include/qsim_b200.h.  There is no CPU fallback.
+"""
+from .signals import Param, Signal, ComplexSignal, Const, Cos, Sin
+from .systems import (HermitianSpec, ResonatorSpec, TransmonSpec, DuffingSpec, QSystem, LiteralHermitian,
+                      Resonator, DuffingTransmon, PerturbativeTransmon, RotatingFrameSystem, label, dimension,
+                      spec, hamiltonian, duffing_hamiltonian)
+from .transmon_series import (PERTURBATIVE_NUM_TERMS, xi_effective, perturbative_transmon_freq,
+                              perturbative_transmon_anharm)
+from .operators import (raising, lowering, number, X, Y, X_Y, XY, flip_flop, decay, dephasing, dipole_drive,
+                        rwa_dipole, parametric_drive, xy_exchange_drive, ParametricHamiltonian,
+                        ParametricLindblad)
+from .composite import (CompositeQSystem, add_hamiltonian, add_lindblad, embed, embed_indices, embed_add,
+                        find_indices, add_parametric_hamiltonians, lower, ProblemSpec)
