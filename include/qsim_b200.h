@@ -37,6 +37,7 @@
 #ifndef QSIM_B200_H
 #define QSIM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -175,6 +176,10 @@ int qsim_destroy(qsim_ctx *ctx);
 int qsim_device_info(qsim_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                      double *sm_clock_mhz, int64_t *global_mem_bytes);
 int qsim_synchronize(qsim_ctx *ctx);
+/* Page-locked host buffers for params / out: host<->device copies of pinned memory run at full
+ * PCIe rate and asynchronously.  Optional: pageable caller memory works too.  */
+int qsim_alloc_pinned(size_t bytes, void **ptr);
+int qsim_free_pinned(void *ptr);
 
 /* ---- problem: the final term lists of one CompositeQSystem --------------- */
 /* d = dimension(cqs) (composite_systems.jl:19).  Host-only; needs no device.  */

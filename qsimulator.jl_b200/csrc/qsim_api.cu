@@ -1,0 +1,633 @@
+// C ABI of the B200 time-evolution library (include/qsim_b200.h): contexts, problem assembly,
+// kernel dispatch, and the four batched solver entry points replacing
+// unitary_propagator / unitary_state / me_propagator / me_state
+// (/root/reference/src/time_evolution.jl:29-164).  No CPU fallback: solver calls need a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "qsim_registry.h"
+
+namespace qsim {
+void build_generator(const qsim_problem &p, int which, Generator &g);
+void host_eval_generator(const Generator &g, double t, const double *row, cplx *dense);
+const SeriesTables &series_tables();
+}  // namespace qsim
+
+using namespace qsim;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(QSIM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct qsim_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop;
+    SeriesTables *d_tab = nullptr;
+    unsigned long long *d_counter = nullptr;
+    DevBuf params, ts, init, out, stats, scratch;
+    int64_t launches = 0;
+};
+
+struct qsim_problem::DeviceCopy {
+    qsim_ctx *owner = nullptr;
+    uint32_t *ell = nullptr;
+    uint8_t *row_len = nullptr;
+    int32_t *slot_ptr = nullptr, *pair_chan = nullptr;
+    double2 *pair_w = nullptr;
+    EvalDesc *evals = nullptr;
+    void free_all() {
+        cudaFree(ell); cudaFree(row_len); cudaFree(slot_ptr); cudaFree(pair_chan); cudaFree(pair_w); cudaFree(evals);
+        ell = nullptr; row_len = nullptr; slot_ptr = nullptr; pair_chan = nullptr; pair_w = nullptr; evals = nullptr;
+    }
+};
+
+extern "C" {
+
+int qsim_version(void) { return QSIM_ABI_VERSION; }
+const char *qsim_last_error(void) { return g_err.c_str(); }
+
+void qsim_default_opts(qsim_solver_opts *o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->reltol = 1e-6;   // time_evolution.jl:43
+    o->abstol = 1e-8;
+    o->gamma = 0.9;     // OrdinaryDiffEq defaults for Tsit5
+    o->qmin = 0.2;
+    o->qmax = 10.0;
+    o->beta1 = 7.0 / 50.0;
+    o->beta2 = 2.0 / 25.0;
+    o->qoldinit = 1e-4;
+    o->dtmax = 0.0;
+    o->maxiters = 1000000;
+}
+
+// ---------------------------------------------------------------- context
+int qsim_create(int device, qsim_ctx **out) {
+    if (!out) return fail(QSIM_ERR_ARG, "qsim_create: ctx is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(QSIM_ERR_NO_DEVICE, std::string("no usable CUDA device (") +
+                                            (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                            "); this library has no CPU fallback");
+    if (device < 0 || device >= count) return fail(QSIM_ERR_ARG, "qsim_create: device index out of range");
+    CU(cudaSetDevice(device));
+    qsim_ctx *c = new qsim_ctx();
+    c->device = device;
+    CU(cudaGetDeviceProperties(&c->prop, device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->d_tab, sizeof(SeriesTables)));
+    CU(cudaMemcpy(c->d_tab, &series_tables(), sizeof(SeriesTables), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
+    *out = c;
+    return QSIM_OK;
+}
+
+int qsim_destroy(qsim_ctx *c) {
+    if (!c) return QSIM_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->params.release(); c->ts.release(); c->init.release(); c->out.release(); c->stats.release(); c->scratch.release();
+    cudaFree(c->d_tab);
+    cudaFree(c->d_counter);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return QSIM_OK;
+}
+
+int qsim_device_info(qsim_ctx *c, int *sm_count, int *cc_major, int *cc_minor, double *sm_clock_mhz,
+                     int64_t *global_mem_bytes) {
+    if (!c) return fail(QSIM_ERR_ARG, "ctx is NULL");
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (cc_major) *cc_major = c->prop.major;
+    if (cc_minor) *cc_minor = c->prop.minor;
+    if (sm_clock_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+        *sm_clock_mhz = khz / 1000.0;
+    }
+    if (global_mem_bytes) *global_mem_bytes = (int64_t)c->prop.totalGlobalMem;
+    return QSIM_OK;
+}
+
+int qsim_synchronize(qsim_ctx *c) {
+    if (!c) return fail(QSIM_ERR_ARG, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return QSIM_OK;
+}
+
+int64_t qsim_launch_count(qsim_ctx *c) { return c ? c->launches : 0; }
+
+int qsim_alloc_pinned(size_t bytes, void **ptr) {
+    if (!ptr) return fail(QSIM_ERR_ARG, "ptr is NULL");
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return QSIM_OK;
+}
+int qsim_free_pinned(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return QSIM_OK;
+}
+
+// ---------------------------------------------------------------- problem
+int qsim_problem_create(int d, int n_params, qsim_problem **out) {
+    if (!out) return fail(QSIM_ERR_ARG, "prob is NULL");
+    if (d < 1 || d > 255) return fail(QSIM_ERR_ARG, "qsim_problem_create: dimension must be in [1, 255]");
+    if (n_params < 0) return fail(QSIM_ERR_ARG, "qsim_problem_create: n_params < 0");
+    qsim_problem *p = new qsim_problem();
+    p->d = d;
+    p->n_params = n_params;
+    p->h0.assign((size_t)d * d, cplx(0, 0));
+    *out = p;
+    return QSIM_OK;
+}
+
+int qsim_problem_destroy(qsim_problem *p) {
+    if (!p) return QSIM_OK;
+    for (int w = 0; w < 2; w++)
+        if (p->dev[w]) {
+            cudaSetDevice(p->dev[w]->owner->device);
+            p->dev[w]->free_all();
+            delete p->dev[w];
+        }
+    delete p;
+    return QSIM_OK;
+}
+
+static int check_open(qsim_problem *p) {
+    if (!p) return fail(QSIM_ERR_ARG, "prob is NULL");
+    if (p->finalized) return fail(QSIM_ERR_STATE, "problem is already finalized");
+    return QSIM_OK;
+}
+static int check_slot(const qsim_problem *p, const qsim_slot &s, const char *what) {
+    if (s.param >= p->n_params) return fail(QSIM_ERR_ARG, std::string(what) + ": parameter index out of range");
+    return QSIM_OK;
+}
+static int check_signal(const qsim_problem *p, const qsim_signal &s) {
+    if (s.carrier < 0 || s.carrier > 2 || s.envelope < 0 || s.envelope > 2 || s.blend < 0 || s.blend > 1)
+        return fail(QSIM_ERR_ARG, "signal: unknown carrier / envelope / blend");
+    const qsim_slot *sl[8] = {&s.offset, &s.amp, &s.freq, &s.phase, &s.t1, &s.t2, &s.sigma, &s.rest};
+    for (auto q : sl)
+        if (int rc = check_slot(p, *q, "signal")) return rc;
+    return QSIM_OK;
+}
+
+int qsim_problem_set_h0(qsim_problem *p, const double *h0) {
+    if (int rc = check_open(p)) return rc;
+    if (!h0) return fail(QSIM_ERR_ARG, "h0 is NULL");
+    std::memcpy(p->h0.data(), h0, sizeof(double) * 2 * p->d * p->d);
+    return QSIM_OK;
+}
+
+int qsim_problem_add_term(qsim_problem *p, const qsim_term *t, const double *atom_a, const double *atom_b,
+                          const int32_t *levels) {
+    if (int rc = check_open(p)) return rc;
+    if (!t) return fail(QSIM_ERR_ARG, "term is NULL");
+    if (int rc = check_signal(p, t->signal)) return rc;
+    const size_t dd = (size_t)p->d * p->d;
+    qsim_problem::Term term;
+    term.desc = *t;
+    auto copy_atom = [&](const double *src, std::vector<cplx> &dst) {
+        dst.resize(dd);
+        std::memcpy(dst.data(), src, sizeof(double) * 2 * dd);
+    };
+    switch (t->kind) {
+        case QSIM_TERM_SCALAR:
+            if (!atom_a) return fail(QSIM_ERR_ARG, "SCALAR term needs atom_a");
+            copy_atom(atom_a, term.a);
+            break;
+        case QSIM_TERM_ROTATING:
+            if (!atom_a || !atom_b) return fail(QSIM_ERR_ARG, "ROTATING term needs atom_a and atom_b");
+            if (int rc = check_slot(p, t->rate, "rate")) return rc;
+            copy_atom(atom_a, term.a);
+            copy_atom(atom_b, term.b);
+            break;
+        case QSIM_TERM_DUFFING:
+        case QSIM_TERM_TRANSMON:
+            if (!levels) return fail(QSIM_ERR_ARG, "DUFFING/TRANSMON term needs levels");
+            if (int rc = check_slot(p, t->rot, "rot")) return rc;
+            if (t->kind == QSIM_TERM_DUFFING) {
+                if (int rc = check_slot(p, t->anharm, "anharm")) return rc;
+            } else {
+                if (t->num_terms < 1) return fail(QSIM_ERR_ARG, "num_terms < 1");  // perturbative_transmon.jl:225
+                if (int rc = check_slot(p, t->EC, "EC")) return rc;
+                if (int rc = check_slot(p, t->EJ1, "EJ1")) return rc;
+                if (int rc = check_slot(p, t->EJ2, "EJ2")) return rc;
+            }
+            term.levels.assign(levels, levels + p->d);
+            for (int v : term.levels)
+                if (v < 0 || v > 1023) return fail(QSIM_ERR_ARG, "levels out of range");
+            break;
+        default:
+            return fail(QSIM_ERR_ARG, "unknown term kind");
+    }
+    p->terms.push_back(std::move(term));
+    return QSIM_OK;
+}
+
+int qsim_problem_add_lindblad(qsim_problem *p, const double *lind, const qsim_signal *scale) {
+    if (int rc = check_open(p)) return rc;
+    if (!lind) return fail(QSIM_ERR_ARG, "lind is NULL");
+    qsim_problem::Lind l;
+    const size_t dd = (size_t)p->d * p->d;
+    l.op.resize(dd);
+    std::memcpy(l.op.data(), lind, sizeof(double) * 2 * dd);
+    l.has_scale = scale != nullptr;
+    if (scale) {
+        if (int rc = check_signal(p, *scale)) return rc;
+        l.scale = *scale;
+    } else {
+        std::memset(&l.scale, 0, sizeof(l.scale));
+    }
+    p->linds.push_back(std::move(l));
+    return QSIM_OK;
+}
+
+int qsim_problem_finalize(qsim_problem *p) {
+    if (!p) return fail(QSIM_ERR_ARG, "prob is NULL");
+    p->finalized = true;
+    return QSIM_OK;
+}
+
+static int ensure_generator(qsim_problem *p, int w) {
+    if (!p->finalized) return fail(QSIM_ERR_STATE, "problem is not finalized");
+    if (p->gen_built[w]) return QSIM_OK;
+    try {
+        build_generator(*p, w, p->gen[w]);
+    } catch (const std::exception &e) {
+        return fail(QSIM_ERR_UNSUPPORTED, std::string("generator assembly failed: ") + e.what());
+    }
+    p->gen_built[w] = true;
+    return QSIM_OK;
+}
+
+int qsim_problem_eval(qsim_problem *p, int kind, double t, const double *param_row, double *out) {
+    if (!p || !out) return fail(QSIM_ERR_ARG, "NULL argument");
+    if (kind != 0 && kind != 1) return fail(QSIM_ERR_ARG, "kind must be 0 or 1");
+    if (p->n_params > 0 && !param_row) return fail(QSIM_ERR_ARG, "param_row is NULL");
+    if (int rc = ensure_generator(p, kind)) return rc;
+    const Generator &g = p->gen[kind];
+    std::vector<cplx> dense((size_t)g.n * g.n);
+    host_eval_generator(g, t, param_row, dense.data());
+    if (kind == 0) {
+        // A = -2 pi i H  ->  H = A * i / (2 pi)
+        const cplx f(0.0, 1.0 / QSIM_TWO_PI);
+        for (auto &v : dense) v *= f;
+    }
+    std::memcpy(out, dense.data(), sizeof(cplx) * dense.size());
+    return QSIM_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- dispatch
+struct Plan {
+    const KernelVariant *kv = nullptr;
+    int w = 0, ncols = 1, identity = 0;
+    int groups = 1, n_batches = 1, team_warps = 1, teams_per_cta = 1, streamed = 0;
+    int block = 32, grid = 1, nvp = 0, ncp = 0, team_smem_doubles = 0;
+    size_t smem = 0, scratch_per_team = 0;
+};
+
+static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz) {
+    const KernelVariant *(*lists[])(int *) = {variants_r1c1, variants_r1c3, variants_r2c1, variants_r2c2, variants_r3c1};
+    const KernelVariant *best = nullptr;
+    for (auto fn : lists) {
+        int cnt = 0;
+        const KernelVariant *v = fn(&cnt);
+        for (int i = 0; i < cnt; i++)
+            if (v[i].rpl == rpl && v[i].cpl == cpl && v[i].maxnnz >= max_nnz && (!best || v[i].maxnnz < best->maxnnz))
+                best = &v[i];
+    }
+    return best;
+}
+
+// which: 0 unitary_propagator, 1 unitary_state, 2 me_propagator, 3 me_state
+static int make_plan(qsim_problem *p, int which, Plan &pl) {
+    pl.w = which >= 2 ? 1 : 0;
+    if (int rc = ensure_generator(p, pl.w)) return rc;
+    const Generator &g = p->gen[pl.w];
+    const int n = g.n;
+    pl.identity = (which == 0 || which == 2) ? 1 : 0;
+    pl.ncols = pl.identity ? n : 1;
+    int rpl, cpl;
+    if (n <= 16) {
+        rpl = 1;
+        pl.groups = std::min(32 / n, pl.ncols);
+        cpl = (pl.ncols + pl.groups - 1) / pl.groups > 1 ? 3 : 1;
+    } else if (n <= 32) {
+        rpl = 1;
+        cpl = pl.ncols > 1 ? 3 : 1;
+    } else if (n <= 64) {
+        rpl = 2;
+        cpl = pl.ncols > 1 ? 2 : 1;
+    } else if (n <= 96) {
+        rpl = 3;
+        cpl = 1;
+    } else {
+        return fail(QSIM_ERR_UNSUPPORTED, "state vectors longer than 96 entries (e.g. d^2 = 729 Lindblad) have no kernel yet");
+    }
+    pl.kv = find_variant(rpl, cpl, g.max_nnz);
+    if (!pl.kv)
+        return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
+                                              std::to_string(g.max_nnz) + ")");
+    const int cpb = pl.groups * cpl;
+    pl.n_batches = (pl.ncols + cpb - 1) / cpb;
+    if (pl.n_batches <= 9) {
+        pl.streamed = 0;
+        pl.team_warps = pl.n_batches;
+    } else {
+        pl.streamed = 1;
+        pl.team_warps = 9;
+    }
+    pl.teams_per_cta = pl.team_warps == 1 ? 4 : 1;
+    pl.block = pl.team_warps * 32 * pl.teams_per_cta;
+    pl.nvp = g.n_slots + (g.n_slots & 1) + 2;
+    pl.ncp = g.n_chan + (g.n_chan & 1) + 2;
+    pl.team_smem_doubles = 2 * 5 * pl.nvp + 5 * pl.ncp + (pl.team_warps * 4 + 8) + pl.team_warps * 2 * n * cpb * 2;
+    pl.smem = (size_t)pl.team_smem_doubles * sizeof(double) * pl.teams_per_cta;
+    pl.scratch_per_team = pl.streamed ? (size_t)4 * pl.n_batches * cpb * n * sizeof(double2) : 0;
+    if (pl.smem > 220 * 1024) return fail(QSIM_ERR_UNSUPPORTED, "problem needs more shared memory than one SM has");
+    return QSIM_OK;
+}
+
+extern "C" int qsim_problem_kernel_name(qsim_problem *p, int which, char *buf, int buflen) {
+    if (!p || !buf || buflen < 1 || which < 0 || which > 3) return fail(QSIM_ERR_ARG, "bad argument");
+    Plan pl;
+    if (int rc = make_plan(p, which, pl)) return rc;
+    std::snprintf(buf, (size_t)buflen, "%s%s_tw%d", pl.kv->name, pl.streamed ? "_streamed" : "_resident", pl.team_warps);
+    return QSIM_OK;
+}
+
+extern "C" int qsim_problem_flops_per_rhs(qsim_problem *p, int which, double *flops) {
+    if (!p || !flops || which < 0 || which > 3) return fail(QSIM_ERR_ARG, "bad argument");
+    const int w = which >= 2 ? 1 : 0;
+    if (int rc = ensure_generator(p, w)) return rc;
+    const Generator &g = p->gen[w];
+    const double ncols = (which == 0 || which == 2) ? (double)g.n : 1.0;
+    *flops = 8.0 * (double)g.nnz * ncols;
+    return QSIM_OK;
+}
+
+template <typename T>
+static cudaError_t upload(T **dst, const std::vector<T> &src) {
+    const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)dst, bytes);
+    if (e != cudaSuccess) return e;
+    if (!src.empty()) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+static int ensure_device_copy(qsim_ctx *c, qsim_problem *p, int w) {
+    if (p->dev[w] && p->dev[w]->owner == c) return QSIM_OK;
+    if (p->dev[w]) {
+        cudaSetDevice(p->dev[w]->owner->device);
+        p->dev[w]->free_all();
+        delete p->dev[w];
+        p->dev[w] = nullptr;
+        cudaSetDevice(c->device);
+    }
+    const Generator &g = p->gen[w];
+    auto *dc = new qsim_problem::DeviceCopy();
+    dc->owner = c;
+    std::vector<double2> w2(g.pair_w.size());
+    for (size_t i = 0; i < w2.size(); i++) w2[i] = make_double2(g.pair_w[i].real(), g.pair_w[i].imag());
+    CU(upload(&dc->ell, g.ell));
+    CU(upload(&dc->row_len, g.row_len));
+    CU(upload(&dc->slot_ptr, g.slot_ptr));
+    CU(upload(&dc->pair_chan, g.pair_chan));
+    CU(upload(&dc->pair_w, w2));
+    CU(upload(&dc->evals, g.evals));
+    p->dev[w] = dc;
+    return QSIM_OK;
+}
+
+static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj, const double *params,
+                        const double *ts, int n_ts, int64_t ts_stride, const double *init, int64_t init_stride,
+                        const qsim_solver_opts *opts_in, double *out, qsim_traj_stats *stats) {
+    if (!c) return fail(QSIM_ERR_NO_DEVICE, "ctx is NULL: create one with qsim_create (needs a CUDA device; no CPU fallback)");
+    if (!p) return fail(QSIM_ERR_ARG, "prob is NULL");
+    if (n_traj < 0) return fail(QSIM_ERR_ARG, "n_traj < 0");
+    if (n_ts < 1 || !ts) return fail(QSIM_ERR_ARG, "need at least one save time");
+    if (!out) return fail(QSIM_ERR_ARG, "out is NULL");
+    if (p->n_params > 0 && !params) return fail(QSIM_ERR_ARG, "params is NULL but the problem has sweep parameters");
+    if ((which == 1 || which == 3) && !init) return fail(QSIM_ERR_ARG, "initial state is NULL");
+    if (ts_stride != 0 && ts_stride < n_ts) return fail(QSIM_ERR_ARG, "ts_stride must be 0 or >= n_ts");
+    qsim_solver_opts o;
+    if (opts_in)
+        o = *opts_in;
+    else
+        qsim_default_opts(&o);
+    if (!(o.reltol > 0) || !(o.abstol >= 0) || !(o.gamma > 0) || !(o.qmin > 0) || !(o.qmax > 0))
+        return fail(QSIM_ERR_ARG, "solver options out of range");
+    const bool dev_ptrs = (o.flags & QSIM_FLAG_DEVICE_PTRS) != 0;
+    if (!dev_ptrs) {
+        // @assert issorted(ts)   (time_evolution.jl:30,64,97,141)
+        const int64_t ngrids = ts_stride ? n_traj : 1;
+        for (int64_t i = 0; i < ngrids; i++)
+            for (int k = 1; k < n_ts; k++)
+                if (!(ts[i * ts_stride + k - 1] <= ts[i * ts_stride + k]))
+                    return fail(QSIM_ERR_ARG, "ts must be sorted");
+    }
+    if (n_traj == 0) return QSIM_OK;
+    Plan pl;
+    if (int rc = make_plan(p, which, pl)) return rc;
+    CU(cudaSetDevice(c->device));
+    if (int rc = ensure_device_copy(c, p, pl.w)) return rc;
+    const Generator &g = p->gen[pl.w];
+    const qsim_problem::DeviceCopy *dc = p->dev[pl.w];
+    cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : c->stream;
+
+    int ctas_per_sm = 0;
+    CU(pl.kv->occupancy(pl.block, pl.smem, &ctas_per_sm));
+    if (ctas_per_sm < 1) return fail(QSIM_ERR_UNSUPPORTED, "kernel does not fit on an SM with this configuration");
+    const int64_t need = (n_traj + pl.teams_per_cta - 1) / pl.teams_per_cta;
+    pl.grid = (int)std::min<int64_t>((int64_t)ctas_per_sm * c->prop.multiProcessorCount, need);
+
+    const size_t n_state = (size_t)g.n * pl.ncols;
+    const size_t b_params = sizeof(double) * (size_t)std::max(p->n_params, 1) * n_traj;
+    const size_t b_ts = sizeof(double) * (size_t)(ts_stride ? ts_stride * n_traj : n_ts);
+    const size_t b_init = init ? sizeof(double2) * (size_t)(init_stride ? init_stride * n_traj : g.n) : 0;
+    const size_t b_out = sizeof(double2) * n_state * n_ts * n_traj;
+    const size_t b_stats = sizeof(qsim_traj_stats) * n_traj;
+
+    LaunchArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (dev_ptrs) {
+        a.params = params;
+        a.ts = ts;
+        a.init = reinterpret_cast<const double2 *>(init);
+        a.out = reinterpret_cast<double2 *>(out);
+        a.stats = stats;
+    } else {
+        CU(c->params.reserve(b_params));
+        CU(c->ts.reserve(b_ts));
+        CU(c->out.reserve(b_out));
+        CU(c->stats.reserve(b_stats));
+        if (params && p->n_params > 0) CU(cudaMemcpyAsync(c->params.p, params, b_params, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(c->ts.p, ts, b_ts, cudaMemcpyHostToDevice, stream));
+        if (init) {
+            CU(c->init.reserve(b_init));
+            CU(cudaMemcpyAsync(c->init.p, init, b_init, cudaMemcpyHostToDevice, stream));
+        }
+        a.params = (const double *)c->params.p;
+        a.ts = (const double *)c->ts.p;
+        a.init = (const double2 *)c->init.p;
+        a.out = (double2 *)c->out.p;
+        a.stats = (qsim_traj_stats *)c->stats.p;
+    }
+    if (pl.streamed) {
+        CU(c->scratch.reserve(pl.scratch_per_team * (size_t)pl.grid * pl.teams_per_cta));
+        a.scratch = (double2 *)c->scratch.p;
+    }
+    a.g.n = g.n;
+    a.g.max_nnz = g.max_nnz;
+    a.g.n_slots = g.n_slots;
+    a.g.n_dyn_slots = g.n_dyn_slots;
+    a.g.n_chan = g.n_chan;
+    a.g.n_evals = (int)g.evals.size();
+    a.g.ell = dc->ell;
+    a.g.row_len = dc->row_len;
+    a.g.slot_ptr = dc->slot_ptr;
+    a.g.pair_chan = dc->pair_chan;
+    a.g.pair_w = dc->pair_w;
+    a.g.evals = dc->evals;
+    a.g.tab = c->d_tab;
+    a.ncols = pl.ncols;
+    a.identity_init = pl.identity;
+    a.n_params = p->n_params;
+    a.n_ts = n_ts;
+    a.ts_stride = ts_stride;
+    a.init_stride = init_stride;
+    a.n_traj = n_traj;
+    a.work_counter = c->d_counter;
+    a.team_warps = pl.team_warps;
+    a.teams_per_cta = pl.teams_per_cta;
+    a.n_batches = pl.n_batches;
+    a.groups = pl.groups;
+    a.streamed = pl.streamed;
+    a.nvp = pl.nvp;
+    a.ncp = pl.ncp;
+    a.team_smem_doubles = pl.team_smem_doubles;
+    a.reltol = o.reltol; a.abstol = o.abstol; a.gamma = o.gamma; a.qmin = o.qmin; a.qmax = o.qmax;
+    a.beta1 = o.beta1; a.beta2 = o.beta2; a.qoldinit = o.qoldinit; a.dtmax = o.dtmax;
+    a.maxiters = o.maxiters > 0 ? o.maxiters : 1000000;
+
+    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), stream));
+    CU(pl.kv->launch(a, pl.grid, pl.block, pl.smem, stream));
+    c->launches++;
+    if (!dev_ptrs) {
+        CU(cudaMemcpyAsync(out, c->out.p, b_out, cudaMemcpyDeviceToHost, stream));
+        if (stats) CU(cudaMemcpyAsync(stats, c->stats.p, b_stats, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    return QSIM_OK;
+}
+
+extern "C" {
+
+int qsim_unitary_propagator(qsim_ctx *ctx, qsim_problem *prob, int64_t n_traj, const double *params,
+                            const double *ts, int n_ts, int64_t ts_stride, const qsim_solver_opts *opts, double *out,
+                            qsim_traj_stats *stats) {
+    return solve_common(ctx, prob, 0, n_traj, params, ts, n_ts, ts_stride, nullptr, 0, opts, out, stats);
+}
+int qsim_unitary_state(qsim_ctx *ctx, qsim_problem *prob, int64_t n_traj, const double *params, const double *ts,
+                       int n_ts, int64_t ts_stride, const double *psi0, int64_t init_stride,
+                       const qsim_solver_opts *opts, double *out, qsim_traj_stats *stats) {
+    return solve_common(ctx, prob, 1, n_traj, params, ts, n_ts, ts_stride, psi0, init_stride, opts, out, stats);
+}
+int qsim_me_propagator(qsim_ctx *ctx, qsim_problem *prob, int64_t n_traj, const double *params, const double *ts,
+                       int n_ts, int64_t ts_stride, const qsim_solver_opts *opts, double *out,
+                       qsim_traj_stats *stats) {
+    return solve_common(ctx, prob, 2, n_traj, params, ts, n_ts, ts_stride, nullptr, 0, opts, out, stats);
+}
+int qsim_me_state(qsim_ctx *ctx, qsim_problem *prob, int64_t n_traj, const double *params, const double *ts,
+                  int n_ts, int64_t ts_stride, const double *rho0, int64_t init_stride, const qsim_solver_opts *opts,
+                  double *out, qsim_traj_stats *stats) {
+    return solve_common(ctx, prob, 3, n_traj, params, ts, n_ts, ts_stride, rho0, init_stride, opts, out, stats);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- FP64 peak probe
+// 8 independent DFMA chains per thread, 2 flop per FMA.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *sink, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, b = 1e-9;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+extern "C" int qsim_peak_fp64(qsim_ctx *c, double ms_target, double *tflops) {
+    if (!c || !tflops) return fail(QSIM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    double *sink = nullptr;
+    CU(cudaMalloc(&sink, sizeof(double)));
+    const int grid = c->prop.multiProcessorCount * 8, block = 256;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    int iters = 2000;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CU(cudaEventRecord(e0, c->stream));
+        dfma_peak_kernel<<<grid, block, 0, c->stream>>>(sink, iters, 1.0);
+        CU(cudaEventRecord(e1, c->stream));
+        CU(cudaEventSynchronize(e1));
+        c->launches++;
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double)iters * (double)grid * block;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        if (ms < ms_target && rep < 4) iters = (int)std::min<double>(2e8, iters * std::max(1.5, 0.9 * ms_target / std::max(ms, 1e-3f)));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tflops = best;
+    return QSIM_OK;
+}

@@ -16,3 +16,6 @@ from .operators import (raising, lowering, number, X, Y, X_Y, XY, flip_flop, dec
                         ParametricLindblad)
 from .composite import (CompositeQSystem, add_hamiltonian, add_lindblad, embed, embed_indices, embed_add,
                         find_indices, add_parametric_hamiltonians, lower, ProblemSpec)
+from . import _abi
+from ._ffi import Context, Problem, QsimError, PinnedArray, default_context
+from .time_evolution import unitary_propagator, unitary_state, me_propagator, me_state

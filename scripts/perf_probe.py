@@ -1,0 +1,29 @@
+"""Development probe (GPU box): quick timings of the configs through the host-buffer C ABI."""
+import os, sys, time, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "qsimulator.jl_b200", "host")]
+import numpy as np
+from qsim_b200 import Context, Problem, _abi
+from qsim_b200 import workloads as W
+
+ctx = Context(0)
+print("device", ctx.info())
+print("peak fp64 TFLOP/s", ctx.peak_fp64(200.0))
+which = sys.argv[1:] or ["cfg2:256:20", "cfg2:4096:200", "cfg3:256:10", "cfg4:256:2"]
+for item in which:
+    name, n, tf = item.split(":")
+    n, tf = int(n), float(tf)
+    cqs, params, ts, fn = W.config(name)
+    idx = np.linspace(0, len(params) - 1, n).astype(int)
+    pr = np.ascontiguousarray(params[idx])
+    ts = np.arange(0.0, tf + 1.0) if fn == "unitary_propagator" else np.array([0.0, tf])
+    P = Problem(cqs)
+    P.solve(fn, ts[:2], params=pr[:8], ctx=ctx)  # warm-up / upload
+    t0 = time.perf_counter()
+    out, st = P.solve(fn, ts, params=pr, ctx=ctx)
+    dt = time.perf_counter() - t0
+    steps = int(st["n_accept"].sum() + st["n_reject"].sum())
+    flops = P.flops_per_rhs(fn) * 6.0 * steps
+    print(json.dumps({"cfg": name, "n_traj": n, "t_final": tf, "kernel": P.kernel_name(fn), "seconds": dt,
+                      "traj_per_s": n / dt, "steps": steps, "steps_per_s": steps / dt, "rejects": int(st["n_reject"].sum()),
+                      "spmv_tflops": flops / dt / 1e12, "retcodes": np.unique(st["retcode"]).tolist()}))

@@ -1,0 +1,228 @@
+"""GPU parity: the CUDA library (through the C ABI) vs the CPU oracle on identical inputs.
+
+Tolerance: elementwise |a-b| / max(|b|, 1e-3) <= 1e-8 (BASELINE.json north_star: "agree elementwise
+within 1e-8 relative at matched solver tolerances"; denominator floor per SURVEY.md section 8d), with
+identical accepted/rejected step counts -- i.e. the same step sequence as the oracle.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from qsim_b200 import (CompositeQSystem, Cos, DuffingSpec, DuffingTransmon, HermitianSpec, LiteralHermitian, Param,
+                       PerturbativeTransmon, Problem, RotatingFrameSystem, Sin, TransmonSpec, X_Y, _abi,
+                       add_hamiltonian, add_lindblad, decay, dephasing, dipole_drive, me_propagator, me_state,
+                       parametric_drive, rwa_dipole, unitary_propagator, unitary_state, xy_exchange_drive)
+from qsim_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+FLOOR = 1e-3
+
+
+def max_rel_err(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), FLOOR)))
+
+
+def check_parity(cqs, which, ts, params=None, init=None, opts=None, steps_exact=True):
+    P, O = Problem(cqs), co.OracleProblem(cqs)
+    got, gs = P.solve(which, ts, params=params, init=init, opts=opts)
+    want, ws = O.solve(_ffi_which(which), ts, params=params, init=init, opts=opts, n_threads=8)
+    assert got.shape == want.shape
+    assert np.all(gs["retcode"] == 0) and np.all(ws["retcode"] == 0)
+    err = max_rel_err(got, want)
+    assert err <= RTOL, f"max rel err {err:.3e}"
+    if steps_exact:
+        assert np.array_equal(gs["n_accept"], ws["n_accept"])
+        assert np.array_equal(gs["n_reject"], ws["n_reject"])
+        assert np.array_equal(gs["n_rhs"], ws["n_rhs"])
+    assert np.allclose(gs["dt_init"], ws["dt_init"], rtol=1e-12)
+    assert np.array_equal(gs["t_final"], ws["t_final"])
+    return got, gs, err
+
+
+def _ffi_which(name):
+    return {"unitary_propagator": 0, "unitary_state": 1, "me_propagator": 2, "me_state": 3}[name]
+
+
+# ---------------------------------------------------------------- unitary
+def test_cfg1_benchmark_system_short():
+    """benchmarks.jl:125-154 (n=2), first 12 ns, 13 saves."""
+    cqs, params, _, _ = W.config("cfg1")
+    got, st, err = check_parity(cqs, "unitary_propagator", np.arange(0.0, 13.0), params)
+    u = got[0, -1]
+    assert np.abs(u.conj().T @ u - np.eye(9)).max() < 1e-3   # reference tolerances' own unitarity error
+
+
+def test_cfg2_sweep_corners_and_interior():
+    cqs, _, _, _ = W.config("cfg2")
+    params = W.amp_freq_grid(64, 64)[[0, 63, 2017, 4032, 4095]]
+    check_parity(cqs, "unitary_propagator", np.arange(0.0, 9.0), params)
+
+
+def test_cfg3_three_transmons():
+    """d = 27: one trajectory per 9-warp team."""
+    cqs, _, _, _ = W.config("cfg3")
+    params = W.amp_freq_grid(128, 128)[[0, 8191, 16383]]
+    check_parity(cqs, "unitary_propagator", np.arange(0.0, 4.0), params)
+
+
+def test_literal_hermitian_dense_and_states():
+    """test_time_evolution.jl:5-23: dense complex 6x6 H, 100 save points."""
+    from scipy.linalg import block_diag, expm
+    m1 = np.array([[0, 1], [1, 0]], dtype=complex)
+    m2 = np.array([[0, -1j, 0], [1j, .1, 2 - 1j], [0, 2 + 1j, 0]])
+    mat = block_diag(m1, m2, np.array([[3.0]]))
+    lh = LiteralHermitian("label", HermitianSpec(mat))
+    cqs = CompositeQSystem([lh])
+    add_hamiltonian(cqs, lh)
+    ts = np.linspace(0, 10, 100)
+    got, _, _ = check_parity(cqs, "unitary_propagator", ts)
+    for u, t in zip(got[0], ts):
+        assert np.allclose(u, expm(-2j * np.pi * mat * t), atol=1e-4, rtol=0)
+    us = unitary_propagator(cqs, ts)
+    assert us.shape == (100, 6, 6) and np.array_equal(us, got[0])
+    psi = np.arange(1, 7, dtype=complex) / np.linalg.norm(np.arange(1, 7))
+    check_parity(cqs, "unitary_state", ts, init=psi)
+
+
+def _iswap_system():
+    q0 = DuffingTransmon("q0", 3, DuffingSpec(0.0, -0.2))
+    q1 = DuffingTransmon("q1", 3, DuffingSpec(4.0, -0.2))
+    cqs = CompositeQSystem([q0, q1])
+    add_hamiltonian(cqs, q1)
+    add_hamiltonian(cqs, parametric_drive(q0, Cos(amp=0.3, freq=0.3, offset=4.3)), q0)
+    add_hamiltonian(cqs, .5 * 0.01 * X_Y([q0, q1]), [q0, q1])
+    return cqs
+
+
+def test_saveat_independence_bitwise():
+    """test_time_evolution.jl:75-78: unitary_propagator(cqs, t) == us_full[end], bitwise."""
+    cqs = _iswap_system()
+    t_final = 20.0
+    us_full = unitary_propagator(cqs, np.linspace(0, t_final, 3))
+    us_dense = unitary_propagator(cqs, np.linspace(0, t_final, 57))
+    u_end = unitary_propagator(cqs, t_final)
+    assert np.array_equal(u_end, us_full[-1]) and np.array_equal(u_end, us_dense[-1])
+    psi0 = np.zeros(9, dtype=complex)
+    psi0[3] = 1
+    psis = unitary_state(cqs, np.linspace(0, t_final, 3), psi0)
+    assert np.array_equal(unitary_state(cqs, t_final, psi0), psis[-1])
+    pop_state = np.abs(psis[:, 3]) ** 2
+    pop_prop = np.array([abs(np.vdot(psi0, u @ psi0)) ** 2 for u in us_full])
+    assert np.allclose(pop_state, pop_prop, rtol=1e-4)
+
+
+def test_drive_family_kitchen_sink():
+    """Every descriptor kind at once: flux drive in a rotating frame, erf-squared blended frequency drive,
+    gaussian lab-frame dipole with frame rotation, RWA dipole, swept exchange coupling."""
+    q0 = DuffingTransmon("q0", 3, DuffingSpec(3.94015, -0.1807))
+    q1 = RotatingFrameSystem.wrap(PerturbativeTransmon("q1", 3, TransmonSpec(0.172, 12.71, 3.69)), 3.9)
+    q2 = DuffingTransmon("q2", 2, DuffingSpec(4.2, -0.22))
+    cqs = CompositeQSystem([q0, q1, q2])
+    add_hamiltonian(cqs, q0)
+    add_hamiltonian(cqs, parametric_drive(q1, Sin(amp=Param(0), freq=0.12, offset=0.05)), q1)
+    add_hamiltonian(cqs, parametric_drive(q0, Cos(amp=0.3, freq=0.3, offset=4.3).erf_squared(2.0, 9.0, 0.7, rest=4.6)), q0)
+    add_hamiltonian(cqs, dipole_drive(q2, Cos(amp=0.02, freq=4.2).gaussian(5.0, 2.0), 4.0), q2)
+    add_hamiltonian(cqs, rwa_dipole(q2, Cos(amp=0.01, freq=0.01)), q2)
+    add_hamiltonian(cqs, xy_exchange_drive([q2, q0], Param(1), [0.2, 0.0]), [q2, q0])
+    params = np.array([[0.31, 0.004], [0.1, 0.002]])
+    check_parity(cqs, "unitary_propagator", np.linspace(0, 6, 7), params)
+    psi = np.zeros(18, dtype=complex)
+    psi[7] = 1
+    check_parity(cqs, "unitary_state", np.linspace(0, 6, 7), params, init=psi)
+
+
+def test_per_trajectory_save_grids():
+    cqs, _, _, _ = W.config("cfg2")
+    params = W.amp_freq_grid(2, 2)
+    ts = np.stack([np.linspace(0, 2.0 + i, 5) for i in range(4)])
+    got, st, _ = check_parity(cqs, "unitary_propagator", ts, params)
+    assert np.array_equal(st["t_final"], ts[:, -1])
+
+
+def test_edge_cases():
+    cqs, params, _, _ = W.config("cfg1")
+    # single save time / zero-length span: identity (the reference returns u0)
+    u = unitary_propagator(cqs, np.array([0.0]), params=params)
+    assert u.shape == (1, 1, 9, 9) and np.array_equal(u[0, 0], np.eye(9))
+    u = unitary_propagator(cqs, np.array([1.0, 1.0]), params=params)
+    assert np.array_equal(u[0, 0], np.eye(9)) and np.array_equal(u[0, 1], np.eye(9))
+    # start time is ts[0], not 0
+    a = unitary_propagator(cqs, np.array([3.0, 4.0]), params=params)
+    b = unitary_propagator(cqs, np.array([0.0, 1.0]), params=params)
+    assert not np.allclose(a[0, -1], b[0, -1])
+    with pytest.raises(AssertionError):
+        unitary_propagator(cqs, np.array([0.0, 2.0, 1.0]), params=params)
+    # maxiters surfaces as a retcode, unreached saves are NaN
+    P = Problem(cqs)
+    out, st = P.solve("unitary_propagator", np.array([0.0, 5.0]), params=params, opts=_abi.default_opts(maxiters=10))
+    assert st["retcode"][0] == _abi.RET_MAXITERS and np.isnan(out[0, -1]).all() and st["n_accept"][0] <= 10
+    # ragged sweep sizes around the CTA/team granularity
+    for n in (1, 3, 5, 149):
+        pr = np.tile(params, (n, 1))
+        pr[:, 0] = np.linspace(0.2, 0.45, n)
+        got, st = P.solve("unitary_propagator", np.array([0.0, 0.5]), params=pr)
+        want, _ = co.OracleProblem(cqs).solve(0, np.array([0.0, 0.5]), params=pr, n_threads=8)
+        assert max_rel_err(got, want) <= RTOL
+
+
+# ---------------------------------------------------------------- Lindblad
+def _driven_decay_system():
+    q0 = DuffingTransmon("q0", 3, DuffingSpec(5.0, -0.2))
+    cqs = CompositeQSystem([q0])
+    add_hamiltonian(cqs, q0)
+    add_hamiltonian(cqs, dipole_drive(q0, Cos(amp=0.02, freq=5.0)), q0)
+    add_lindblad(cqs, decay(q0, 1 / (2 * np.pi * 50.)), [q0])
+    return cqs
+
+
+def test_me_propagator_and_state_single_transmon():
+    """test_time_evolution.jl:121-153."""
+    cqs = _driven_decay_system()
+    ts = np.linspace(0, 20, 21)
+    rho0 = np.zeros((3, 3), dtype=complex)
+    rho0[0, 0] = 1
+    us, _, _ = check_parity(cqs, "me_propagator", ts)
+    rhos, _, _ = check_parity(cqs, "me_state", ts, init=rho0)
+    for u, rho in zip(us[0], rhos[0]):
+        rp = (u @ rho0.ravel(order="F")).reshape(3, 3, order="F")
+        assert np.linalg.norm(rp - rho) <= 1e-4 * max(np.linalg.norm(rp), np.linalg.norm(rho))
+    assert np.array_equal(me_propagator(cqs, 20.0), us[0, -1])
+    assert np.array_equal(me_state(cqs, 20.0, rho0), rhos[0, -1])
+
+
+def test_decay_and_dephasing_known_answer():
+    """test_time_evolution.jl:155-182."""
+    q0 = DuffingTransmon("q0", 3, DuffingSpec(5.0, -0.2))
+    cqs = CompositeQSystem([q0])
+    add_hamiltonian(cqs, q0)
+    T1, Tphi = 50.0, 200.0
+    T2 = 1 / (.5 / T1 + 1 / Tphi)
+    add_lindblad(cqs, decay(q0, 1 / (2 * np.pi * T1)), [q0])
+    add_lindblad(cqs, dephasing(q0, 1 / (2 * np.pi * Tphi)), [q0])
+    ts = np.linspace(0, 100, 101)
+    psi0 = np.array([1, 1, 0], dtype=complex) / math.sqrt(2)
+    rhos = me_state(cqs, ts, np.outer(psi0, psi0.conj()))
+    assert np.allclose(rhos[:, 1, 1], np.exp(-ts / T1) / 2, rtol=1e-10, atol=0)
+    assert np.allclose(np.abs(rhos[:, 0, 1]), np.exp(-ts / T2) / 2, rtol=1e-2, atol=0)
+    check_parity(cqs, "me_state", ts, init=np.outer(psi0, psi0.conj()))
+
+
+def test_cfg4_lindblad_two_transmons():
+    """d^2 = 81 superoperator propagator, swept T1/Tphi (streamed kernel), 3 ns."""
+    cqs, params, _, _ = W.config("cfg4")
+    pr = params[[0, 4097, 8191]]
+    ts = np.array([0.0, 1.5, 3.0])
+    got, st, err = check_parity(cqs, "me_propagator", ts, pr)
+    vi = np.eye(9).ravel(order="F")
+    for s in got[:, -1]:
+        assert np.abs(vi @ s - vi).max() < 1e-5          # trace preservation
+    rho0 = np.zeros((9, 9), dtype=complex)
+    rho0[3, 3] = 1
+    rhos, _, _ = check_parity(cqs, "me_state", ts, pr, init=rho0)
+    for s, rho in zip(got[:, -1], rhos[:, -1]):
+        rp = (s @ rho0.ravel(order="F")).reshape(9, 9, order="F")
+        assert np.linalg.norm(rp - rho) <= 1e-4
