@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
@@ -322,18 +323,19 @@ struct Plan {
     const KernelVariant *kv = nullptr;
     int w = 0, ncols = 1, identity = 0;
     int groups = 1, n_batches = 1, team_warps = 1, teams_per_cta = 1, streamed = 0;
-    int block = 32, grid = 1, nvp = 0, ncp = 0, team_smem_doubles = 0;
+    int block = 32, grid = 1, nvp = 0, ncp = 0, common_bytes = 0, team_bytes = 0, n_dyn_pairs = 0;
     size_t smem = 0, scratch_per_team = 0;
 };
 
-static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz) {
+static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block) {
     const KernelVariant *(*lists[])(int *) = {variants_r1c1, variants_r1c3, variants_r2c1, variants_r2c2, variants_r3c1};
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
         int cnt = 0;
         const KernelVariant *v = fn(&cnt);
         for (int i = 0; i < cnt; i++)
-            if (v[i].rpl == rpl && v[i].cpl == cpl && v[i].maxnnz >= max_nnz && (!best || v[i].maxnnz < best->maxnnz))
+            if (v[i].rpl == rpl && v[i].cpl == cpl && v[i].maxnnz >= max_nnz && v[i].maxt >= block &&
+                (!best || v[i].maxnnz < best->maxnnz || (v[i].maxnnz == best->maxnnz && v[i].maxt < best->maxt)))
                 best = &v[i];
     }
     return best;
@@ -364,10 +366,6 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     } else {
         return fail(QSIM_ERR_UNSUPPORTED, "state vectors longer than 96 entries (e.g. d^2 = 729 Lindblad) have no kernel yet");
     }
-    pl.kv = find_variant(rpl, cpl, g.max_nnz);
-    if (!pl.kv)
-        return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
-                                              std::to_string(g.max_nnz) + ")");
     const int cpb = pl.groups * cpl;
     pl.n_batches = (pl.ncols + cpb - 1) / cpb;
     if (pl.n_batches <= 9) {
@@ -378,11 +376,25 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.team_warps = 9;
     }
     pl.teams_per_cta = pl.team_warps == 1 ? 4 : 1;
+    if (const char *env = std::getenv("QSIM_TEAMS_PER_CTA")) {  // tuning knob (development)
+        const int v = std::atoi(env);
+        if (v >= 1 && v <= 15 && v * pl.team_warps * 32 <= 288) pl.teams_per_cta = v;
+    }
     pl.block = pl.team_warps * 32 * pl.teams_per_cta;
-    pl.nvp = g.n_slots + (g.n_slots & 1) + 2;
-    pl.ncp = g.n_chan + (g.n_chan & 1) + 2;
-    pl.team_smem_doubles = 2 * 5 * pl.nvp + 5 * pl.ncp + (pl.team_warps * 4 + 8) + pl.team_warps * 2 * n * cpb * 2;
-    pl.smem = (size_t)pl.team_smem_doubles * sizeof(double) * pl.teams_per_cta;
+    pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block);
+    if (!pl.kv)
+        return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
+                                              std::to_string(g.max_nnz) + ")");
+    if (16 * n * cpb > 65535 || g.n_slots > 4094)
+        return fail(QSIM_ERR_UNSUPPORTED, "generator too large for the packed 16-bit row/slot offsets");
+    pl.nvp = (g.n_slots + 1 + 1) & ~1;  // + the zero slot, even
+    pl.ncp = (g.n_chan + 1) & ~1;
+    pl.n_dyn_pairs = g.slot_ptr[g.n_dyn_slots];
+    const int n_ev = std::max<int>((int)g.evals.size(), 1);
+    pl.common_bytes = 512 + ((4 * (g.n_dyn_slots + 1 + pl.n_dyn_pairs) + 15) & ~15) + 16 * std::max(pl.n_dyn_pairs, 1);
+    pl.team_bytes = 16 * 5 * pl.nvp + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 8 * (pl.team_warps * 4 + 8) +
+                    pl.team_warps * 2 * 16 * n * cpb;
+    pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
     pl.scratch_per_team = pl.streamed ? (size_t)4 * pl.n_batches * cpb * n * sizeof(double2) : 0;
     if (pl.smem > 220 * 1024) return fail(QSIM_ERR_UNSUPPORTED, "problem needs more shared memory than one SM has");
     return QSIM_OK;
@@ -523,6 +535,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.g.n_dyn_slots = g.n_dyn_slots;
     a.g.n_chan = g.n_chan;
     a.g.n_evals = (int)g.evals.size();
+    a.g.n_dyn_pairs = pl.n_dyn_pairs;
     a.g.ell = dc->ell;
     a.g.row_len = dc->row_len;
     a.g.slot_ptr = dc->slot_ptr;
@@ -545,7 +558,8 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.streamed = pl.streamed;
     a.nvp = pl.nvp;
     a.ncp = pl.ncp;
-    a.team_smem_doubles = pl.team_smem_doubles;
+    a.common_bytes = pl.common_bytes;
+    a.team_bytes = pl.team_bytes;
     a.reltol = o.reltol; a.abstol = o.abstol; a.gamma = o.gamma; a.qmin = o.qmin; a.qmax = o.qmax;
     a.beta1 = o.beta1; a.beta2 = o.beta2; a.qoldinit = o.qoldinit; a.dtmax = o.dtmax;
     a.maxiters = o.maxiters > 0 ? o.maxiters : 1000000;

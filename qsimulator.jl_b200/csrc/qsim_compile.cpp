@@ -309,7 +309,14 @@ void host_eval_generator(const Generator &g, double t, const double *row, cplx *
     const SeriesTables &tab = series_tables();
     std::vector<double> chan((size_t)g.n_chan, 0.0);
     chan[0] = 1.0;
-    for (const auto &e : g.evals) run_evaluator(e, tab, t, row, chan.data());
+    for (const auto &e : g.evals) {
+        ResolvedEval r;
+        resolve_eval(e, row, r);
+        double o0, o1;
+        run_resolved(r, tab.freq, tab.anh, t, &o0, &o1);
+        chan[r.out_chan] = o0;
+        if (eval_outputs(r.kind) == 2) chan[r.out_chan + 1] = o1;
+    }
     std::vector<cplx> V((size_t)g.n_slots);
     for (int s = 0; s < g.n_slots; s++) {
         cplx v(0, 0);

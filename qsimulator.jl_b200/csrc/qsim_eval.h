@@ -5,8 +5,11 @@
 //   xi_effective                      perturbative_transmon.jl:187-189
 //   Horner with muladd                perturbative_transmon.jl:193-201
 //   perturbative_transmon_freq/anharm perturbative_transmon.jl:222-231, 253-261
-// Compiled for the device (CUDA libm: FP64 sin/cos/erf/exp/sqrt) and for the host, where the
-// introspection entry qsim_problem_eval uses it so the tests can check it without a GPU.
+// An evaluator is first RESOLVED against a trajectory's parameter row (slots -> numbers, the
+// time-independent products 2*pi*freq, 2*EC, EJ1^2+EJ2^2, 2*EJ1*EJ2 formed once, in the same
+// operation order as the reference) and then RUN at each stage time.  Both steps compile for the
+// device (CUDA libm: FP64 sin/cos/erf/exp/sqrt) and for the host, where the introspection entry
+// qsim_problem_eval uses them so the tests can check them without a GPU.
 #pragma once
 #include <math.h>
 
@@ -21,76 +24,112 @@ struct SeriesTables {
     double anh[31];
 };
 
-QSIM_HD double slot_value(const qsim_slot &s, const double *row) { return s.param >= 0 ? row[s.param] : s.value; }
+// One evaluator with its slots resolved for a trajectory (18 doubles; lives in shared memory).
+struct ResolvedEval {
+    int32_t kind, carrier, envelope, blend, num_terms, out_chan, dynamic, _pad;
+    double offset, amp, w, phase, t1, t2, sigma, rest;  // w = 2*pi*freq
+    double rate;                                        // ROTATING
+    double EC, EC2, EJs, EJp;                           // TRANSMON: EC, 2*EC, EJ1^2+EJ2^2, 2*EJ1*EJ2
+    double slot;                                        // SLOT
+};
 
-QSIM_HD double eval_signal(const qsim_signal &s, double t, const double *row) {
-    double car = 1.0, env = 1.0;
-    if (s.carrier != QSIM_CARRIER_NONE) {
-        double arg = (QSIM_TWO_PI * slot_value(s.freq, row)) * t + slot_value(s.phase, row);
-        car = s.carrier == QSIM_CARRIER_COS ? cos(arg) : sin(arg);
-    }
-    if (s.envelope == QSIM_ENV_GAUSSIAN) {
-        double x = (t - slot_value(s.t1, row)) / slot_value(s.sigma, row);
-        env = exp(-0.5 * (x * x));
-    } else if (s.envelope == QSIM_ENV_ERF_SQUARED) {
-        double sg = slot_value(s.sigma, row);
-        env = 0.5 * (erf((t - slot_value(s.t1, row)) / sg) - erf((t - slot_value(s.t2, row)) / sg));
-    }
-    if (s.blend == QSIM_BLEND_NONE) return slot_value(s.offset, row) + slot_value(s.amp, row) * env * car;
-    return env * (slot_value(s.offset, row) + slot_value(s.amp, row) * car) + (1.0 - env) * slot_value(s.rest, row);
-}
+QSIM_HD double slot_value(const qsim_slot &s, const double *row) { return s.param >= 0 ? row[s.param] : s.value; }
 
 QSIM_HD bool signal_is_dynamic(const qsim_signal &s) {
     return s.carrier != QSIM_CARRIER_NONE || s.envelope != QSIM_ENV_NONE;
 }
 
-QSIM_HD double horner(double x, const double *c, int n) {
-    if (n <= 0) return 0.0;
-    double ex = c[n - 1];
-    for (int i = n - 2; i >= 0; i--) ex = fma(x, ex, c[i]);
-    return ex;
+QSIM_HD void resolve_eval(const EvalDesc &e, const double *row, ResolvedEval &r) {
+    r.kind = e.kind;
+    r.carrier = e.sig.carrier;
+    r.envelope = e.sig.envelope;
+    r.blend = e.sig.blend;
+    r.num_terms = e.num_terms;
+    r.out_chan = e.out_chan;
+    r.dynamic = e.dynamic;
+    r._pad = 0;
+    r.offset = slot_value(e.sig.offset, row);
+    r.amp = slot_value(e.sig.amp, row);
+    r.w = QSIM_TWO_PI * slot_value(e.sig.freq, row);
+    r.phase = slot_value(e.sig.phase, row);
+    r.t1 = slot_value(e.sig.t1, row);
+    r.t2 = slot_value(e.sig.t2, row);
+    r.sigma = slot_value(e.sig.sigma, row);
+    r.rest = slot_value(e.sig.rest, row);
+    r.rate = slot_value(e.rate, row);
+    const double EC = slot_value(e.EC, row), EJ1 = slot_value(e.EJ1, row), EJ2 = slot_value(e.EJ2, row);
+    r.EC = EC;
+    r.EC2 = 2.0 * EC;
+    r.EJs = EJ1 * EJ1 + EJ2 * EJ2;
+    r.EJp = 2.0 * EJ1 * EJ2;
+    r.slot = slot_value(e.slot, row);
 }
 
-QSIM_HD void transmon_f_a(const SeriesTables &tab, double EC, double EJ1, double EJ2, double phi, int num_terms,
-                          double *f, double *a) {
-    int t = num_terms < 32 ? num_terms : 32;
-    double xi = sqrt((2.0 * EC) / sqrt((EJ1 * EJ1 + EJ2 * EJ2) + (2.0 * EJ1 * EJ2) * cos(QSIM_TWO_PI * phi)));
-    *f = EC * (4.0 / xi + horner(xi, tab.freq, t - 1));
-    *a = EC * horner(xi, tab.anh, t - 1);
+QSIM_HD double eval_signal(const ResolvedEval &s, double t) {
+    double car = 1.0, env = 1.0;
+    if (s.carrier != QSIM_CARRIER_NONE) {
+        const double arg = s.w * t + s.phase;
+        car = s.carrier == QSIM_CARRIER_COS ? cos(arg) : sin(arg);
+    }
+    if (s.envelope == QSIM_ENV_GAUSSIAN) {
+        const double x = (t - s.t1) / s.sigma;
+        env = exp(-0.5 * (x * x));
+    } else if (s.envelope == QSIM_ENV_ERF_SQUARED) {
+        env = 0.5 * (erf((t - s.t1) / s.sigma) - erf((t - s.t2) / s.sigma));
+    }
+    if (s.blend == QSIM_BLEND_NONE) return s.offset + s.amp * env * car;
+    return env * (s.offset + s.amp * car) + (1.0 - env) * s.rest;
 }
 
-// Evaluate one evaluator at time t into chan[] (indexed by absolute channel number).
-QSIM_HD void run_evaluator(const EvalDesc &e, const SeriesTables &tab, double t, const double *row, double *chan) {
+// Two Horner chains interleaved (frequency and anharmonicity series share xi).
+QSIM_HD void transmon_f_a(const ResolvedEval &r, const double *freq_tab, const double *anh_tab, double phi, double *f,
+                          double *a) {
+    const int nt = (r.num_terms < 32 ? r.num_terms : 32) - 1;
+    const double xi = sqrt(r.EC2 / sqrt(r.EJs + r.EJp * cos(QSIM_TWO_PI * phi)));
+    double pf = 0.0, pa = 0.0;
+    if (nt > 0) {
+        pf = freq_tab[nt - 1];
+        pa = anh_tab[nt - 1];
+        for (int i = nt - 2; i >= 0; i--) {
+            pf = fma(xi, pf, freq_tab[i]);
+            pa = fma(xi, pa, anh_tab[i]);
+        }
+    }
+    *f = r.EC * (4.0 / xi + pf);
+    *a = r.EC * pa;
+}
+
+// Run one resolved evaluator at time t: up to two channel values.
+QSIM_HD void run_resolved(const ResolvedEval &e, const double *freq_tab, const double *anh_tab, double t, double *o0,
+                          double *o1) {
+    *o1 = 0.0;
     switch (e.kind) {
         case EV_SIGNAL:
-            chan[e.out_chan] = eval_signal(e.sig, t, row);
+            *o0 = eval_signal(e, t);
             break;
         case EV_ROTATING: {
-            double s = eval_signal(e.sig, t, row);
-            double th = QSIM_TWO_PI * (slot_value(e.rate, row) * t);
+            const double s = eval_signal(e, t);
+            const double th = QSIM_TWO_PI * (e.rate * t);
             double sn, cs;
             sincos(th, &sn, &cs);
-            chan[e.out_chan] = s * cs;
-            chan[e.out_chan + 1] = s * sn;
+            *o0 = s * cs;
+            *o1 = s * sn;
             break;
         }
-        case EV_TRANSMON: {
-            double f, a;
-            transmon_f_a(tab, slot_value(e.EC, row), slot_value(e.EJ1, row), slot_value(e.EJ2, row),
-                         eval_signal(e.sig, t, row), e.num_terms, &f, &a);
-            chan[e.out_chan] = f;
-            chan[e.out_chan + 1] = a;
+        case EV_TRANSMON:
+            transmon_f_a(e, freq_tab, anh_tab, eval_signal(e, t), o0, o1);
             break;
-        }
         case EV_SQUARE: {
-            double s = eval_signal(e.sig, t, row);
-            chan[e.out_chan] = s * s;
+            const double s = eval_signal(e, t);
+            *o0 = s * s;
             break;
         }
         default:
-            chan[e.out_chan] = slot_value(e.slot, row);
+            *o0 = e.slot;
             break;
     }
 }
+
+QSIM_HD int eval_outputs(int kind) { return (kind == EV_ROTATING || kind == EV_TRANSMON) ? 2 : 1; }
 
 }  // namespace qsim

@@ -13,14 +13,17 @@
 //   * the state is a set of independent columns (columns of U, or of the superoperator propagator)
 //     that share one adaptive step sequence: only the error norm couples them.  A warp owns a
 //     BATCH of columns; during a step the batch (u, k1..k7) lives entirely in registers, the stage
-//     vector is exchanged through shared memory, and A(t) is applied as a sparse row gather whose
-//     (source, value-slot) lists sit in registers for the whole kernel.
+//     vector is exchanged through shared memory (explicit ld/st.shared on 32-bit addresses), and
+//     A(t) is applied as a sparse row gather whose (source offset, value-slot offset) lists sit in
+//     registers for the whole kernel.
 //   * resident mode: one batch per warp, state never leaves registers (unitary d <= 32, me_state).
 //     streamed mode: more batches than warps (me_propagator): u/k1 are read and u_new/k7 written
 //     once per step per column through L2-resident scratch; everything else stays on chip.
-//   * A(t): per step, the team evaluates the drive channels (FP64 sin/cos/sqrt/Horner) for the five
-//     distinct stage times in parallel across lanes and refreshes only the time-dependent value
-//     slots in shared memory.
+//   * A(t): per trajectory the drive descriptors are resolved against the parameter row into
+//     shared memory; per step the team evaluates the drive channels (FP64 sin/cos/sqrt/Horner) for
+//     the five distinct stage times in parallel across lanes and refreshes only the time-dependent
+//     value slots.
+//   * step controller: EEst^b1 / qold^b2 as exp(b1 log EEst - b2 log qold), log qold carried over.
 //   * work distribution: persistent CTAs, dynamic queue over trajectories (atomic counter).
 // No reductions use atomics, so results are bitwise reproducible and independent of the save grid.
 #pragma once
@@ -31,9 +34,12 @@
 
 namespace qsim {
 
+static_assert(sizeof(ResolvedEval) == 18 * sizeof(double), "ResolvedEval layout");
+
 struct DevGenerator {
     int n, max_nnz, n_slots, n_dyn_slots, n_chan, n_evals;
-    const uint32_t *ell;      // [max_nnz][n]
+    int n_dyn_pairs;          // pairs of the dynamic slots (a prefix of the pair arrays)
+    const uint32_t *ell;      // [max_nnz][n]: src | slot << 16, 0xFFFFFFFF = padding
     const uint8_t *row_len;   // [n]
     const int32_t *slot_ptr;  // [n_slots+1]
     const int32_t *pair_chan;
@@ -55,8 +61,9 @@ struct LaunchArgs {
     unsigned long long *work_counter;
     double2 *scratch;     // streamed mode: [n_teams_total][4][n_batches*cpb*n]
     int team_warps, teams_per_cta, n_batches, groups, streamed;
-    int nvp, ncp;         // padded slot / channel counts
-    int team_smem_doubles;  // shared-memory doubles per team
+    int nvp, ncp;         // padded slot / channel counts (nvp > n_slots: slot n_slots is the zero slot)
+    int common_bytes;     // CTA-wide shared region (series tables + dynamic pair lists)
+    int team_bytes;       // shared bytes per team
     double reltol, abstol, gamma, qmin, qmax, beta1, beta2, qoldinit, dtmax;
     long long maxiters;
 };
@@ -94,6 +101,29 @@ static __device__ __constant__ double kStageC[5] = {0.161, 0.327, 0.9, 0.9800255
 #define BT6 -0.45808210592918697
 #define BT7 0.015151515151515152
 
+// ---- shared memory through 32-bit addresses ------------------------------------------
+__device__ __forceinline__ double2 lds2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts2(uint32_t addr, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ double lds1(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts1(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ int ldsi(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ void team_sync(int team_warps, int bar_id) {
     if (team_warps == 1)
         __syncwarp();
@@ -107,130 +137,118 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Deterministic team-wide sum of up to NV values held per thread.
+// Deterministic team-wide sum of NV values held per thread (fixed order: no atomics).
 template <int NV>
-__device__ __forceinline__ void team_sum(double (&v)[NV], double *red, int team_warps, int warp_in_team, int lane,
+__device__ __forceinline__ void team_sum(double (&v)[NV], uint32_t red, int team_warps, int warp_in_team, int lane,
                                          int bar_id) {
 #pragma unroll
     for (int i = 0; i < NV; i++) v[i] = warp_sum(v[i]);
     if (team_warps == 1) return;
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < NV; i++) red[warp_in_team * NV + i] = v[i];
+        for (int i = 0; i < NV; i++) sts1(red + 8 * (warp_in_team * NV + i), v[i]);
     }
     team_sync(team_warps, bar_id);
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         double s = 0.0;
-        for (int w = 0; w < team_warps; w++) s += red[w * NV + i];
+        for (int w = 0; w < team_warps; w++) s += lds1(red + 8 * (w * NV + i));
         v[i] = s;
     }
     team_sync(team_warps, bar_id);
 }
 
-template <int RPL, int CPL, int MAXNNZ>
-struct Solver {
-    static constexpr int E = RPL * CPL;
-
-    // ---- per-thread constants -------------------------------------------------
-    const LaunchArgs &a;
+// Per-thread geometry (all scalars; arrays are kept separately so they stay in registers).
+struct Geo {
     int lane, warp_in_team, team_thread, team_threads, bar_id;
-    int g_idx, row0, cpb, colofs;
-    bool lane_active;
-    bool row_ok[RPL];
-    int row_of[RPL];
-    uint32_t ell[RPL][MAXNNZ];
-    // shared memory
-    double2 *V;      // [5][nvp]
-    double *chan;    // [5][ncp]
-    double *red;     // [team_warps*4 + 8]
-    double2 *ybuf;   // per warp: [2][n*cpb]
-    // per-trajectory
-    const double *prow;
-    double2 *sc_u[2], *sc_k[2];  // streamed scratch (cur/next)
+    int cpb, colofs;
+    // shared-memory byte addresses
+    uint32_t sm_tab, sm_dptr, sm_dchan, sm_dw;  // CTA-wide: series tables, dynamic pair lists
+    uint32_t sm_V, sm_chan, sm_rev, sm_red;     // team
+    uint32_t sm_y0, sm_y1;                      // this warp's two stage buffers (+ column offset)
+    uint32_t v_stride;                          // bytes between value tables
+};
 
-    __device__ Solver(const LaunchArgs &args) : a(args) {}
-
-    __device__ __forceinline__ void setup(double *team_smem, int team_global_idx) {
-        const int n = a.g.n;
-        lane = threadIdx.x & 31;
-        team_threads = a.team_warps * 32;
-        team_thread = threadIdx.x % team_threads;
-        warp_in_team = team_thread >> 5;
-        bar_id = 1 + threadIdx.x / team_threads;
-        cpb = a.groups * CPL;
-        if (a.groups > 1) {
-            g_idx = lane / n;
-            row0 = lane % n;
-            lane_active = g_idx < a.groups;
-        } else {
-            g_idx = 0;
-            row0 = lane;
-            lane_active = true;
-        }
-        colofs = g_idx * CPL;
-#pragma unroll
-        for (int i = 0; i < RPL; i++) {
-            row_of[i] = row0 + 32 * i;
-            row_ok[i] = lane_active && row_of[i] < n;
-#pragma unroll
-            for (int j = 0; j < MAXNNZ; j++)
-                ell[i][j] = (row_ok[i] && j < a.g.max_nnz) ? a.g.ell[(size_t)j * n + row_of[i]] : 0xFFFFFFFFu;
-        }
-        V = reinterpret_cast<double2 *>(team_smem);
-        chan = team_smem + 2 * 5 * a.nvp;
-        red = chan + 5 * a.ncp;
-        ybuf = reinterpret_cast<double2 *>(red + a.team_warps * 4 + 8) + (size_t)warp_in_team * 2 * n * cpb;
-        if (a.streamed) {
-            const size_t buf = (size_t)a.n_batches * cpb * n;
-            double2 *base = a.scratch + (size_t)team_global_idx * 4 * buf;
-            sc_u[0] = base;
-            sc_k[0] = base + buf;
-            sc_u[1] = base + 2 * buf;
-            sc_k[1] = base + 3 * buf;
-        }
+// Stops the compiler from hoisting per-entry address arithmetic out of the step loop (register pressure).
+#define QSIM_LAUNDER_ELL()                                                      \
+    _Pragma("unroll") for (int i_ = 0; i_ < RPL; i_++) {                        \
+        _Pragma("unroll") for (int j_ = 0; j_ < MAXNNZ; j_++)                   \
+            asm volatile("" : "+r"(const_cast<uint32_t &>(ell[i_][j_])));       \
     }
 
-    // ---- A(t) value tables -----------------------------------------------------
-    // Refresh tables s < ntab for the times tbase + kStageC[s]*dtv; all==false touches only
-    // time-dependent channels and slots.  Two team barriers.
-    __device__ __forceinline__ void compute_tables(double tbase, double dtv, int ntab, bool all) {
-        const DevGenerator &g = a.g;
-        const int ne = g.n_evals;
-        for (int it = team_thread; it < ntab * ne; it += team_threads) {
-            const int s = it / ne, e = it - s * ne;
-            const EvalDesc &ev = g.evals[e];
-            if (all || ev.dynamic) run_evaluator(ev, *g.tab, tbase + kStageC[s] * dtv, prow, chan + s * a.ncp);
-        }
-        team_sync(a.team_warps, bar_id);
-        const int nsl = all ? g.n_slots : g.n_dyn_slots;
-        for (int it = team_thread; it < ntab * nsl; it += team_threads) {
-            const int s = it / nsl, sl = it - s * nsl;
-            const double *ch = chan + s * a.ncp;
-            double vx = 0.0, vy = 0.0;
-            for (int q = g.slot_ptr[sl]; q < g.slot_ptr[sl + 1]; q++) {
-                const double c = ch[g.pair_chan[q]];
-                const double2 w = g.pair_w[q];
-                vx = fma(w.x, c, vx);
-                vy = fma(w.y, c, vy);
+template <int RPL, int CPL, int MAXNNZ>
+struct Kern {
+    static constexpr int E = RPL * CPL;
+    typedef double2 Vec[E];
+
+    // Refresh tables table0 + s, s < NTAB, for the times tbase + kStageC[s]*dtv.  all == false: only
+    // the time-dependent channels and slots (pair lists in shared memory); all == true: everything
+    // (pair lists from global memory; once per trajectory).  Two team barriers.
+    template <int NTAB>
+    static __device__ __forceinline__ void compute_tables(const LaunchArgs &a, const Geo &g, const double *smem_gen,
+                                                           double tbase, double dtv, bool all, int table0) {
+        const int ne = a.g.n_evals;
+        const SeriesTables *tab = reinterpret_cast<const SeriesTables *>(smem_gen);
+        const ResolvedEval *rev = reinterpret_cast<const ResolvedEval *>(smem_gen + (g.sm_rev - g.sm_tab) / 8);
+        for (int it = g.team_thread; it < NTAB * ne; it += g.team_threads) {
+            const int s = it % NTAB, e = it / NTAB;
+            const ResolvedEval r = rev[e];
+            if (all || r.dynamic) {
+                double o0, o1;
+                run_resolved(r, tab->freq, tab->anh, tbase + kStageC[s] * dtv, &o0, &o1);
+                const uint32_t ca = g.sm_chan + 8u * ((table0 + s) * a.ncp + r.out_chan);
+                sts1(ca, o0);
+                if (eval_outputs(r.kind) == 2) sts1(ca + 8, o1);
             }
-            V[s * a.nvp + sl] = make_double2(vx, vy);
         }
-        team_sync(a.team_warps, bar_id);
+        team_sync(a.team_warps, g.bar_id);
+        if (!all) {
+            const int nsl = a.g.n_dyn_slots;
+            for (int it = g.team_thread; it < NTAB * nsl; it += g.team_threads) {
+                const int s = it % NTAB, sl = it / NTAB;
+                const uint32_t ch = g.sm_chan + 8u * ((table0 + s) * a.ncp);
+                double vx = 0.0, vy = 0.0;
+                const int q1 = ldsi(g.sm_dptr + 4 * (sl + 1));
+                for (int q = ldsi(g.sm_dptr + 4 * sl); q < q1; q++) {
+                    const double c = lds1(ch + 8u * ldsi(g.sm_dchan + 4 * q));
+                    const double2 w = lds2(g.sm_dw + 16 * q);
+                    vx = fma(w.x, c, vx);
+                    vy = fma(w.y, c, vy);
+                }
+                sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
+            }
+        } else {
+            const int nsl = a.g.n_slots;
+            for (int it = g.team_thread; it < NTAB * nsl; it += g.team_threads) {
+                const int s = it % NTAB, sl = it / NTAB;
+                const uint32_t ch = g.sm_chan + 8u * ((table0 + s) * a.ncp);
+                double vx = 0.0, vy = 0.0;
+                for (int q = a.g.slot_ptr[sl]; q < a.g.slot_ptr[sl + 1]; q++) {
+                    const double c = lds1(ch + 8u * a.g.pair_chan[q]);
+                    const double2 w = a.g.pair_w[q];
+                    vx = fma(w.x, c, vx);
+                    vy = fma(w.y, c, vy);
+                }
+                sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
+            }
+        }
+        team_sync(a.team_warps, g.bar_id);
     }
 
-    // ---- stage exchange + sparse apply ------------------------------------------
-    __device__ __forceinline__ void put_stage(const double2 (&y)[E], double2 *yb) {
+    static __device__ __forceinline__ void put_stage(const Vec &y, uint32_t yb, const uint32_t (&my_off)[RPL],
+                                                     const bool (&row_ok)[RPL]) {
 #pragma unroll
         for (int i = 0; i < RPL; i++)
             if (row_ok[i]) {
 #pragma unroll
-                for (int c = 0; c < CPL; c++) yb[row_of[i] * cpb + colofs + c] = y[i * CPL + c];
+                for (int c = 0; c < CPL; c++) sts2(yb + my_off[i] + 16 * c, y[i * CPL + c]);
             }
         __syncwarp();
     }
 
-    __device__ __forceinline__ void apply(const double2 *Vs, const double2 *yb, double2 (&k)[E]) {
+    // k = A(t_s) * y : sparse row gather, value table Vs, stage vector yb (both shared-memory addresses)
+    static __device__ __forceinline__ void apply(uint32_t Vs, uint32_t yb, const uint32_t (&ell)[RPL][MAXNNZ],
+                                                 int nnz_u, Vec &k) {
 #pragma unroll
         for (int i = 0; i < RPL; i++) {
             double2 acc[CPL];
@@ -238,16 +256,16 @@ struct Solver {
             for (int c = 0; c < CPL; c++) acc[c] = make_double2(0.0, 0.0);
 #pragma unroll
             for (int j = 0; j < MAXNNZ; j++) {
-                const uint32_t e = ell[i][j];
-                if (e != 0xFFFFFFFFu) {
-                    const double2 v = Vs[e >> 16];
-                    const double2 *yp = yb + (e & 0xFFFFu) * cpb + colofs;
+                if (j < nnz_u) {  // uniform across the grid
+                    const uint32_t e = ell[i][j];
+                    const double2 v = lds2(Vs + (e >> 16));
+                    const uint32_t ya = yb + (e & 0xFFFFu);
 #pragma unroll
                     for (int c = 0; c < CPL; c++) {
-                        const double2 y = yp[c];
+                        const double2 y = lds2(ya + 16 * c);
                         acc[c].x = fma(v.x, y.x, acc[c].x);
-                        acc[c].x = fma(-v.y, y.y, acc[c].x);
                         acc[c].y = fma(v.x, y.y, acc[c].y);
+                        acc[c].x = fma(-v.y, y.y, acc[c].x);
                         acc[c].y = fma(v.y, y.x, acc[c].y);
                     }
                 }
@@ -257,44 +275,8 @@ struct Solver {
         }
     }
 
-    // column index of local column c in batch b; validity
-    __device__ __forceinline__ int col_of(int b, int c) const { return b * cpb + colofs + c; }
-
-    __device__ __forceinline__ void initial_state(int b, long long traj, double2 (&u)[E]) {
-#pragma unroll
-        for (int i = 0; i < RPL; i++)
-#pragma unroll
-            for (int c = 0; c < CPL; c++) {
-                double2 v = make_double2(0.0, 0.0);
-                const int col = col_of(b, c);
-                if (row_ok[i] && col < a.ncols) {
-                    if (a.identity_init)
-                        v.x = (row_of[i] == col) ? 1.0 : 0.0;
-                    else
-                        v = a.init[(size_t)traj * a.init_stride + row_of[i]];
-                }
-                u[i * CPL + c] = v;
-            }
-    }
-
-    __device__ __forceinline__ void load_batch(const double2 *buf, int b, double2 (&x)[E]) {
-        const int n = a.g.n;
-#pragma unroll
-        for (int i = 0; i < RPL; i++)
-#pragma unroll
-            for (int c = 0; c < CPL; c++)
-                x[i * CPL + c] = row_ok[i] ? buf[(size_t)col_of(b, c) * n + row_of[i]] : make_double2(0.0, 0.0);
-    }
-    __device__ __forceinline__ void store_batch(double2 *buf, int b, const double2 (&x)[E]) {
-        const int n = a.g.n;
-#pragma unroll
-        for (int i = 0; i < RPL; i++)
-            if (row_ok[i]) {
-#pragma unroll
-                for (int c = 0; c < CPL; c++) buf[(size_t)col_of(b, c) * n + row_of[i]] = x[i * CPL + c];
-            }
-    }
-    __device__ __forceinline__ void write_out(long long traj, int ksave, int b, const double2 (&x)[E]) {
+    static __device__ __forceinline__ void write_out(const LaunchArgs &a, long long traj, int ksave, int col0,
+                                                     const int (&row_of)[RPL], const bool (&row_ok)[RPL], const Vec &x) {
         const int n = a.g.n;
         double2 *dst = a.out + ((size_t)traj * a.n_ts + ksave) * (size_t)a.ncols * n;
 #pragma unroll
@@ -302,23 +284,40 @@ struct Solver {
             if (row_ok[i]) {
 #pragma unroll
                 for (int c = 0; c < CPL; c++) {
-                    const int col = col_of(b, c);
+                    const int col = col0 + c;
                     if (col < a.ncols) dst[(size_t)col * n + row_of[i]] = x[i * CPL + c];
                 }
             }
     }
 
-    // Dense output for the save points ks in [k_lo, k_hi) of the step [t, t+dt] (tnew = snapped end).
-    __device__ __forceinline__ void save_points(long long traj, const double *ts, int k_lo, int k_hi, double t,
-                                                double dt, double tnew, int b, const double2 (&u)[E],
-                                                const double2 (&k1)[E], const double2 (&k2)[E],
-                                                const double2 (&k3)[E], const double2 (&k4)[E],
-                                                const double2 (&k5)[E], const double2 (&k6)[E],
-                                                const double2 (&k7)[E], const double2 (&unew)[E]) {
+    static __device__ __forceinline__ void initial_state(const LaunchArgs &a, long long traj, int col0,
+                                                         const int (&row_of)[RPL], const bool (&row_ok)[RPL], Vec &u) {
+#pragma unroll
+        for (int i = 0; i < RPL; i++)
+#pragma unroll
+            for (int c = 0; c < CPL; c++) {
+                double2 v = make_double2(0.0, 0.0);
+                if (row_ok[i] && col0 + c < a.ncols) {
+                    if (a.identity_init)
+                        v.x = (row_of[i] == col0 + c) ? 1.0 : 0.0;
+                    else
+                        v = a.init[(size_t)traj * a.init_stride + row_of[i]];
+                }
+                u[i * CPL + c] = v;
+            }
+    }
+
+    // Dense output (Tsit5 free interpolant) for save points [k_lo, k_hi) of the step [t, t+dt].
+    static __device__ __forceinline__ void save_points(const LaunchArgs &a, long long traj, const double *ts, int k_lo,
+                                                       int k_hi, double t, double dt, double tnew, int col0,
+                                                       const int (&row_of)[RPL], const bool (&row_ok)[RPL],
+                                                       const Vec &u, const Vec &k1, const Vec &k2, const Vec &k3,
+                                                       const Vec &k4, const Vec &k5, const Vec &k6, const Vec &k7,
+                                                       const Vec &unew) {
         for (int ks = k_lo; ks < k_hi; ks++) {
             const double tsv = ts[ks];
             if (tsv == tnew) {
-                write_out(traj, ks, b, unew);
+                write_out(a, traj, ks, col0, row_of, row_ok, unew);
             } else {
                 const double th = (tsv - t) / dt;
                 const double th2 = th * th;
@@ -329,7 +328,7 @@ struct Solver {
                 const double b5 = th2 * (37.50931341651104 + th * (-88.1789048947664 + th * 47.37952196281928));
                 const double b6 = th2 * (-27.896526289197286 + th * (65.09189467479366 + th * -34.87065786149661));
                 const double b7 = th2 * (1.5 + th * (-4.0 + th * 2.5));
-                double2 o[E];
+                Vec o;
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     double sx = k1[e].x * b1, sy = k1[e].y * b1;
@@ -341,50 +340,86 @@ struct Solver {
                     sx += k7[e].x * b7; sy += k7[e].y * b7;
                     o[e] = make_double2(u[e].x + dt * sx, u[e].y + dt * sy);
                 }
-                write_out(traj, ks, b, o);
+                write_out(a, traj, ks, col0, row_of, row_ok, o);
             }
         }
     }
 
-    // ---- one trajectory -----------------------------------------------------------
-    __device__ void run(long long traj) {
+    static __device__ __forceinline__ void load_batch(const double2 *buf, int n, int col0, const int (&row_of)[RPL],
+                                                      const bool (&row_ok)[RPL], Vec &x) {
+#pragma unroll
+        for (int i = 0; i < RPL; i++)
+#pragma unroll
+            for (int c = 0; c < CPL; c++)
+                x[i * CPL + c] = row_ok[i] ? buf[(size_t)(col0 + c) * n + row_of[i]] : make_double2(0.0, 0.0);
+    }
+    static __device__ __forceinline__ void store_batch(double2 *buf, int n, int col0, const int (&row_of)[RPL],
+                                                       const bool (&row_ok)[RPL], const Vec &x) {
+#pragma unroll
+        for (int i = 0; i < RPL; i++)
+            if (row_ok[i]) {
+#pragma unroll
+                for (int c = 0; c < CPL; c++) buf[(size_t)(col0 + c) * n + row_of[i]] = x[i * CPL + c];
+            }
+    }
+
+    // ---- one trajectory -----------------------------------------------------------------
+    static __device__ __forceinline__ void run(const LaunchArgs &a, const Geo &g, const double *smem_gen,
+                                               const uint32_t (&ell)[RPL][MAXNNZ], const uint32_t (&my_off)[RPL],
+                                               const int (&row_of)[RPL], const bool (&row_ok)[RPL], double2 *sc_base,
+                                               long long traj) {
         const int n = a.g.n;
+        const int nnz_u = a.g.max_nnz;
         const double *ts = a.ts + (size_t)traj * a.ts_stride;
-        prow = a.params + (size_t)traj * a.n_params;
+        const double *prow = a.params + (size_t)traj * a.n_params;
         const double t0 = ts[0], tend = ts[a.n_ts - 1];
         const double ntot = (double)n * (double)a.ncols;
-        double2 *yb0 = ybuf, *yb1 = ybuf + (size_t)n * cpb;
-        const double2 *V0 = V, *V1 = V + a.nvp, *V2 = V + 2 * a.nvp, *V3 = V + 3 * a.nvp, *V4 = V + 4 * a.nvp;
+        const uint32_t V0 = g.sm_V, V1 = V0 + g.v_stride, V2 = V1 + g.v_stride, V3 = V2 + g.v_stride, V4 = V3 + g.v_stride;
+        const uint32_t yb0 = g.sm_y0, yb1 = g.sm_y1;
+        const size_t sbuf = (size_t)a.n_batches * g.cpb * n;
+        double2 *const sc_u0 = sc_base, *const sc_k0 = sc_base + sbuf;
 
         qsim_traj_stats st;
         st.retcode = QSIM_RET_SUCCESS;
-        st.n_accept = st.n_reject = st.n_rhs = 0;
+        st.n_accept = st.n_reject = 0;
+        st.n_rhs = 0;
         st.dt_init = 0.0;
-        st.t_final = t0;
 
-        // constant channel + all evaluators at t0 (sets static channels and static slots in all 5 tables)
-        for (int s = team_thread; s < 5; s += team_threads) chan[s * a.ncp] = 1.0;
-        team_sync(a.team_warps, bar_id);
-        compute_tables(t0, 0.0, 5, true);
+        // resolve the drive descriptors against this trajectory's parameter row; constant channel
+        {
+            ResolvedEval *rev = const_cast<ResolvedEval *>(
+                reinterpret_cast<const ResolvedEval *>(smem_gen + (g.sm_rev - g.sm_tab) / 8));
+            for (int e = g.team_thread; e < a.g.n_evals; e += g.team_threads) {
+                ResolvedEval r;
+                resolve_eval(a.g.evals[e], prow, r);
+                rev[e] = r;
+            }
+            for (int s = g.team_thread; s < 5; s += g.team_threads) sts1(g.sm_chan + 8u * (s * a.ncp), 1.0);
+        }
+        team_sync(a.team_warps, g.bar_id);
+        compute_tables<5>(a, g, smem_gen, t0, 0.0, true, 0);
 
-        double2 u[E], k1[E], k2[E], k3[E], k4[E], k5[E], k6[E], k7[E], tmp[E];
+        Vec u, k1, k2, k3, k4, k5, k6, k7, tmp;
         int cur = 0;
         int nsave = 0;
         while (nsave < a.n_ts && ts[nsave] <= t0) nsave++;  // save_start: every ts[k] == t0
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        double ts_next = nsave < a.n_ts ? ts[nsave] : inf;
 
         double t = t0, dt = 0.0;
         if (tend > t0) {
             const double dtmax = a.dtmax > 0.0 ? a.dtmax : tend - t0;
             // ---- initial step (DiffEqBase ode_determine_initdt) ----
             double acc2[2] = {0.0, 0.0};
-            for (int b = warp_in_team; b < a.n_batches; b += a.team_warps) {
-                initial_state(b, traj, u);
-                for (int ks = 0; ks < nsave; ks++) write_out(traj, ks, b, u);
-                put_stage(u, yb0);
-                apply(V0, yb0, k1);
+            for (int b = g.warp_in_team; b < a.n_batches; b += a.team_warps) {
+                const int col0 = b * g.cpb + g.colofs;
+                initial_state(a, traj, col0, row_of, row_ok, u);
+                for (int ks = 0; ks < nsave; ks++) write_out(a, traj, ks, col0, row_of, row_ok, u);
+                put_stage(u, yb0, my_off, row_ok);
+                apply(V0, yb0, ell, nnz_u, k1);
                 if (a.streamed) {
-                    store_batch(sc_u[0], b, u);
-                    store_batch(sc_k[0], b, k1);
+                    store_batch(sc_u0, n, col0, row_of, row_ok, u);
+                    store_batch(sc_k0, n, col0, row_of, row_ok, k1);
                 }
 #pragma unroll
                 for (int e = 0; e < E; e++) {
@@ -394,30 +429,22 @@ struct Solver {
                     acc2[1] += fx * fx + fy * fy;
                 }
             }
-            team_sum<2>(acc2, red, a.team_warps, warp_in_team, lane, bar_id);
+            team_sum<2>(acc2, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
             const double d0 = sqrt(acc2[0] / ntot), d1 = sqrt(acc2[1] / ntot);
             double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
             dt0 = fmin(dt0, dtmax);
-            // table 1 <- t0 + dt0 (table 0 keeps t0): evaluate through offset pointers
-            {
-                double *chan_save = chan;
-                double2 *V_save = V;
-                chan = chan + a.ncp;
-                V = V + a.nvp;
-                compute_tables(t0 + dt0, 0.0, 1, false);
-                chan = chan_save;
-                V = V_save;
-            }
+            compute_tables<1>(a, g, smem_gen, t0 + dt0, 0.0, false, 1);  // table 1 <- t0 + dt0 (table 0 keeps t0)
             double acc1[1] = {0.0};
-            for (int b = warp_in_team; b < a.n_batches; b += a.team_warps) {
+            for (int b = g.warp_in_team; b < a.n_batches; b += a.team_warps) {
+                const int col0 = b * g.cpb + g.colofs;
                 if (a.streamed) {
-                    load_batch(sc_u[0], b, u);
-                    load_batch(sc_k[0], b, k1);
+                    load_batch(sc_u0, n, col0, row_of, row_ok, u);
+                    load_batch(sc_k0, n, col0, row_of, row_ok, k1);
                 }
 #pragma unroll
                 for (int e = 0; e < E; e++) tmp[e] = make_double2(u[e].x + dt0 * k1[e].x, u[e].y + dt0 * k1[e].y);
-                put_stage(tmp, yb1);
-                apply(V1, yb1, k2);
+                put_stage(tmp, yb1, my_off, row_ok);
+                apply(V1, yb1, ell, nnz_u, k2);
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     const double sk = a.abstol + sqrt(u[e].x * u[e].x + u[e].y * u[e].y) * a.reltol;
@@ -425,23 +452,26 @@ struct Solver {
                     acc1[0] += fx * fx + fy * fy;
                 }
             }
-            team_sum<1>(acc1, red, a.team_warps, warp_in_team, lane, bar_id);
+            team_sum<1>(acc1, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
             const double d2 = sqrt(acc1[0] / ntot) / dt0;
             const double md = fmax(d1, d2);
             const double dt1 = md <= 1e-15 ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(md)) / 5.0);
             dt = fmin(fmin(100.0 * dt0, dt1), dtmax);
             st.dt_init = dt;
-            st.n_rhs = 3;  // the reference evaluates f(u0,t0) twice (init-dt, then the integrator's first stage)
 
             // ---- main loop ----
-            double qold = a.qoldinit;
+            const double lq_init = log(a.qoldinit);
+            double lqold = lq_init;
+            const double inv_gamma = 1.0 / a.gamma, qlo = 1.0 / a.qmax, qhi = 1.0 / a.qmin;
             long long iters = 0;
+            int n_attempt = 0;
             while (t < tend) {
                 if (++iters > a.maxiters) { st.retcode = QSIM_RET_MAXITERS; break; }
                 dt = fmin(dt, dtmax);
                 dt = fmin(dt, tend - t);
                 if (!(dt > fabs(t) * 2.220446049250313e-16)) { st.retcode = QSIM_RET_DT_UNDERFLOW; break; }
-                compute_tables(t, dt, 5, false);
+                compute_tables<5>(a, g, smem_gen, t, dt, false, 0);
+                QSIM_LAUNDER_ELL();
                 double tnew = t + dt;
                 {
                     const double mx = fmax(t, tend);
@@ -450,29 +480,32 @@ struct Solver {
                     if (fabs(tnew - tend) < 10.0 * ulp) tnew = tend;
                 }
                 int nsave_hi = nsave;
-                while (nsave_hi < a.n_ts && ts[nsave_hi] <= tnew) nsave_hi++;
+                if (ts_next <= tnew) {
+                    while (nsave_hi < a.n_ts && ts[nsave_hi] <= tnew) nsave_hi++;
+                }
 
                 double err[1] = {0.0};
-                for (int b = warp_in_team; b < a.n_batches; b += a.team_warps) {
+                for (int b = g.warp_in_team; b < a.n_batches; b += a.team_warps) {
+                    const int col0 = b * g.cpb + g.colofs;
                     if (a.streamed) {
-                        load_batch(sc_u[cur], b, u);
-                        load_batch(sc_k[cur], b, k1);
+                        load_batch(sc_u0 + (size_t)(2 * cur) * sbuf, n, col0, row_of, row_ok, u);
+                        load_batch(sc_k0 + (size_t)(2 * cur) * sbuf, n, col0, row_of, row_ok, k1);
                     }
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         const double ax = A21 * k1[e].x, ay = A21 * k1[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
-                    put_stage(tmp, yb0);
-                    apply(V0, yb0, k2);
+                    put_stage(tmp, yb0, my_off, row_ok);
+                    apply(V0, yb0, ell, nnz_u, k2);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A31 * k1[e].x, ay = A31 * k1[e].y;
                         ax += A32 * k2[e].x; ay += A32 * k2[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
-                    put_stage(tmp, yb1);
-                    apply(V1, yb1, k3);
+                    put_stage(tmp, yb1, my_off, row_ok);
+                    apply(V1, yb1, ell, nnz_u, k3);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A41 * k1[e].x, ay = A41 * k1[e].y;
@@ -480,8 +513,8 @@ struct Solver {
                         ax += A43 * k3[e].x; ay += A43 * k3[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
-                    put_stage(tmp, yb0);
-                    apply(V2, yb0, k4);
+                    put_stage(tmp, yb0, my_off, row_ok);
+                    apply(V2, yb0, ell, nnz_u, k4);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A51 * k1[e].x, ay = A51 * k1[e].y;
@@ -490,8 +523,8 @@ struct Solver {
                         ax += A54 * k4[e].x; ay += A54 * k4[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
-                    put_stage(tmp, yb1);
-                    apply(V3, yb1, k5);
+                    put_stage(tmp, yb1, my_off, row_ok);
+                    apply(V3, yb1, ell, nnz_u, k5);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A61 * k1[e].x, ay = A61 * k1[e].y;
@@ -501,8 +534,8 @@ struct Solver {
                         ax += A65 * k5[e].x; ay += A65 * k5[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
-                    put_stage(tmp, yb0);
-                    apply(V4, yb0, k6);
+                    put_stage(tmp, yb0, my_off, row_ok);
+                    apply(V4, yb0, ell, nnz_u, k6);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A71 * k1[e].x, ay = A71 * k1[e].y;
@@ -513,8 +546,8 @@ struct Solver {
                         ax += A76 * k6[e].x; ay += A76 * k6[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);  // u_new
                     }
-                    put_stage(tmp, yb1);
-                    apply(V4, yb1, k7);
+                    put_stage(tmp, yb1, my_off, row_ok);
+                    apply(V4, yb1, ell, nnz_u, k7);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ex = BT1 * k1[e].x, ey = BT1 * k1[e].y;
@@ -524,40 +557,42 @@ struct Solver {
                         ex += BT5 * k5[e].x; ey += BT5 * k5[e].y;
                         ex += BT6 * k6[e].x; ey += BT6 * k6[e].y;
                         ex += BT7 * k7[e].x; ey += BT7 * k7[e].y;
-                        ex *= dt; ey *= dt;
                         const double m2 = fmax(u[e].x * u[e].x + u[e].y * u[e].y, tmp[e].x * tmp[e].x + tmp[e].y * tmp[e].y);
-                        const double sk = a.abstol + sqrt(m2) * a.reltol;
-                        ex /= sk; ey /= sk;
+                        const double rs = dt / (a.abstol + sqrt(m2) * a.reltol);
+                        ex *= rs; ey *= rs;
                         err[0] += ex * ex + ey * ey;
                     }
                     if (a.streamed) {
-                        // tentative: next buffers are only adopted if the step is accepted; dense output
-                        // slots are rewritten by the retried / later step if it is not
-                        store_batch(sc_u[cur ^ 1], b, tmp);
-                        store_batch(sc_k[cur ^ 1], b, k7);
-                        save_points(traj, ts, nsave, nsave_hi, t, dt, tnew, b, u, k1, k2, k3, k4, k5, k6, k7, tmp);
+                        // tentative: the next buffers are adopted only if the step is accepted; dense-output
+                        // slots are rewritten by the retried / a later step if it is not
+                        store_batch(sc_u0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, row_of, row_ok, tmp);
+                        store_batch(sc_k0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, row_of, row_ok, k7);
+                        if (nsave_hi > nsave)
+                            save_points(a, traj, ts, nsave, nsave_hi, t, dt, tnew, col0, row_of, row_ok, u, k1, k2, k3,
+                                        k4, k5, k6, k7, tmp);
                     }
                 }
-                st.n_rhs += 6;
-                team_sum<1>(err, red, a.team_warps, warp_in_team, lane, bar_id);
+                n_attempt++;
+                team_sum<1>(err, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
                 const double eest = sqrt(err[0] / ntot);
                 if (!isfinite(eest)) { st.retcode = QSIM_RET_NONFINITE; break; }
-                // PI controller (stepsize_controller! / step_accept_controller! / step_reject_controller!)
-                double q, q11 = 0.0;
+                // PI controller (stepsize_controller! / step_accept_controller! / step_reject_controller!):
+                // q = EEst^beta1 / qold^beta2 / gamma, clamped to [1/qmax, 1/qmin]
+                double q, le = 0.0;
                 if (eest == 0.0) {
-                    q = 1.0 / a.qmax;
+                    q = qlo;
                 } else {
-                    q11 = pow(eest, a.beta1);
-                    q = q11 / pow(qold, a.beta2);
-                    q = fmax(1.0 / a.qmax, fmin(1.0 / a.qmin, q / a.gamma));
+                    le = log(eest);
+                    q = exp(a.beta1 * le - a.beta2 * lqold) * inv_gamma;
+                    q = fmax(qlo, fmin(qhi, q));
                 }
                 if (eest <= 1.0) {
                     st.n_accept++;
-                    qold = fmax(eest, a.qoldinit);
+                    lqold = eest == 0.0 ? lq_init : fmax(le, lq_init);  // qold = max(EEst, qoldinit)
                     if (!a.streamed) {
-                        if (warp_in_team < a.n_batches)
-                            save_points(traj, ts, nsave, nsave_hi, t, dt, tnew, warp_in_team, u, k1, k2, k3, k4, k5, k6,
-                                        k7, tmp);
+                        if (nsave_hi > nsave && g.warp_in_team < a.n_batches)
+                            save_points(a, traj, ts, nsave, nsave_hi, t, dt, tnew, g.warp_in_team * g.cpb + g.colofs,
+                                        row_of, row_ok, u, k1, k2, k3, k4, k5, k6, k7, tmp);
 #pragma unroll
                         for (int e = 0; e < E; e++) {
                             u[e] = tmp[e];
@@ -566,19 +601,25 @@ struct Solver {
                     } else {
                         cur ^= 1;
                     }
-                    nsave = nsave_hi;
+                    if (nsave_hi > nsave) {
+                        nsave = nsave_hi;
+                        ts_next = nsave < a.n_ts ? ts[nsave] : inf;
+                    }
                     t = tnew;
                     dt = dt / q;
                 } else {
                     st.n_reject++;
-                    dt = dt / fmin(1.0 / a.qmin, q11 / a.gamma);
+                    const double q11 = eest == 0.0 ? 0.0 : exp(a.beta1 * le);
+                    dt = dt / fmin(qhi, q11 * inv_gamma);
                 }
             }
+            st.n_rhs = 3 + 6 * n_attempt;  // the reference also evaluates f(u0,t0) a second time
         } else {
             // zero-length span: only the start saves
-            for (int b = warp_in_team; b < a.n_batches; b += a.team_warps) {
-                initial_state(b, traj, u);
-                for (int ks = 0; ks < nsave; ks++) write_out(traj, ks, b, u);
+            for (int b = g.warp_in_team; b < a.n_batches; b += a.team_warps) {
+                const int col0 = b * g.cpb + g.colofs;
+                initial_state(a, traj, col0, row_of, row_ok, u);
+                for (int ks = 0; ks < nsave; ks++) write_out(a, traj, ks, col0, row_of, row_ok, u);
             }
         }
         // unreached save points of a failed trajectory: NaN
@@ -586,52 +627,127 @@ struct Solver {
             const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
             for (int e = 0; e < E; e++) tmp[e] = make_double2(qnan, qnan);
-            for (int b = warp_in_team; b < a.n_batches; b += a.team_warps)
-                for (int ks = nsave; ks < a.n_ts; ks++) write_out(traj, ks, b, tmp);
+            for (int b = g.warp_in_team; b < a.n_batches; b += a.team_warps)
+                for (int ks = nsave; ks < a.n_ts; ks++) write_out(a, traj, ks, b * g.cpb + g.colofs, row_of, row_ok, tmp);
         }
         st.t_final = t;
-        if (team_thread == 0 && a.stats) a.stats[traj] = st;
+        if (g.team_thread == 0 && a.stats) a.stats[traj] = st;
     }
 };
 
-template <int RPL, int CPL, int MAXNNZ>
-__global__ void __launch_bounds__(320) solve_kernel(const __grid_constant__ LaunchArgs a) {
+// MAXT: largest block the variant is launched with (128: one-warp teams, 4 per CTA, up to 255
+// registers; 288: teams of up to 9 warps, up to 168 registers).
+template <int RPL, int CPL, int MAXNNZ, int MAXT>
+__global__ void __launch_bounds__(MAXT) solve_kernel(const __grid_constant__ LaunchArgs a) {
     extern __shared__ __align__(16) double smem[];
-    const int team_threads = a.team_warps * 32;
-    const int team_in_cta = threadIdx.x / team_threads;
-    double *team_smem = smem + (size_t)team_in_cta * a.team_smem_doubles;
-    Solver<RPL, CPL, MAXNNZ> s(a);
-    s.setup(team_smem, blockIdx.x * a.teams_per_cta + team_in_cta);
-    // work index broadcast slot: last 2 doubles of the team's `red` area
-    unsigned long long *wslot = reinterpret_cast<unsigned long long *>(s.red + a.team_warps * 4 + 6);
+    typedef Kern<RPL, CPL, MAXNNZ> K;
+    const int n = a.g.n;
+    Geo g;
+    g.lane = threadIdx.x & 31;
+    g.team_threads = a.team_warps * 32;
+    const int team_in_cta = threadIdx.x / g.team_threads;
+    g.team_thread = threadIdx.x - team_in_cta * g.team_threads;
+    g.warp_in_team = g.team_thread >> 5;
+    g.bar_id = 1 + team_in_cta;
+    g.cpb = a.groups * CPL;
+    int g_idx = 0, row0 = g.lane;
+    bool lane_active = true;
+    if (a.groups > 1) {
+        g_idx = g.lane / n;
+        row0 = g.lane - g_idx * n;
+        lane_active = g_idx < a.groups;
+    }
+    g.colofs = g_idx * CPL;
+
+    // ---- shared memory map (byte addresses) ----
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    g.sm_tab = sbase;
+    g.sm_dptr = sbase + 512;                             // int[n_dyn_slots + 1]
+    g.sm_dchan = g.sm_dptr + 4 * (a.g.n_dyn_slots + 1);  // int[n_dyn_pairs]
+    g.sm_dw = sbase + a.common_bytes - 16 * (a.g.n_dyn_pairs > 0 ? a.g.n_dyn_pairs : 1);  // double2[n_dyn_pairs]
+    const uint32_t tbase = sbase + a.common_bytes + team_in_cta * a.team_bytes;
+    g.v_stride = 16u * a.nvp;
+    g.sm_V = tbase;
+    g.sm_chan = g.sm_V + 5 * g.v_stride;
+    g.sm_rev = g.sm_chan + 8u * 5 * a.ncp;
+    g.sm_red = g.sm_rev + (uint32_t)sizeof(ResolvedEval) * (a.g.n_evals > 0 ? a.g.n_evals : 1);
+    const uint32_t ybytes = 16u * n * g.cpb;
+    g.sm_y0 = g.sm_red + 8u * (a.team_warps * 4 + 8) + g.warp_in_team * 2 * ybytes + 16u * g.colofs;
+    g.sm_y1 = g.sm_y0 + ybytes;
+
+    // ---- CTA-wide constants: series tables and the dynamic slots' pair lists ----
+    {
+        const double *src = reinterpret_cast<const double *>(a.g.tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(SeriesTables) / 8); i += blockDim.x) sts1(g.sm_tab + 8 * i, src[i]);
+        int *dptr = reinterpret_cast<int *>(smem) + 128;
+        for (int i = threadIdx.x; i <= a.g.n_dyn_slots; i += blockDim.x) dptr[i] = a.g.slot_ptr[i];
+        for (int i = threadIdx.x; i < a.g.n_dyn_pairs; i += blockDim.x) {
+            dptr[a.g.n_dyn_slots + 1 + i] = a.g.pair_chan[i];
+            sts2(g.sm_dw + 16 * i, a.g.pair_w[i]);
+        }
+        // the zero slot of every table (padding entries of short rows read it)
+        for (int s = g.team_thread; s < 5; s += g.team_threads)
+            sts2(g.sm_V + s * g.v_stride + 16 * a.g.n_slots, make_double2(0.0, 0.0));
+    }
+    __syncthreads();
+
+    // ---- per-lane sparse rows, kept in registers for the whole kernel ----
+    int row_of[RPL];
+    bool row_ok[RPL];
+    uint32_t my_off[RPL];
+    uint32_t ell[RPL][MAXNNZ];
+#pragma unroll
+    for (int i = 0; i < RPL; i++) {
+        row_of[i] = row0 + 32 * i;
+        row_ok[i] = lane_active && row_of[i] < n;
+        my_off[i] = 16u * (row_of[i] * g.cpb);
+        const uint32_t pad = (row_ok[i] ? my_off[i] : 0u) | ((16u * a.g.n_slots) << 16);
+#pragma unroll
+        for (int j = 0; j < MAXNNZ; j++) {
+            uint32_t e = 0xFFFFFFFFu;
+            if (row_ok[i] && j < a.g.max_nnz) e = a.g.ell[(size_t)j * n + row_of[i]];
+            ell[i][j] = (e == 0xFFFFFFFFu) ? pad : ((16u * (e & 0xFFFFu) * g.cpb) | ((16u * (e >> 16)) << 16));
+        }
+    }
+    double2 *sc_base = nullptr;
+    if (a.streamed)
+        sc_base = a.scratch + (size_t)(blockIdx.x * a.teams_per_cta + team_in_cta) * 4 * ((size_t)a.n_batches * g.cpb * n);
+
+    const uint32_t wslot = g.sm_red + 8u * (a.team_warps * 4 + 6);
     for (;;) {
-        if (s.team_thread == 0) *wslot = atomicAdd(a.work_counter, 1ULL);
-        team_sync(a.team_warps, s.bar_id);
-        const unsigned long long traj = *wslot;
-        team_sync(a.team_warps, s.bar_id);
+        if (g.team_thread == 0) {
+            const unsigned long long w = atomicAdd(a.work_counter, 1ULL);
+            asm volatile("st.shared.u64 [%0], %1;" ::"r"(wslot), "l"(w) : "memory");
+        }
+        team_sync(a.team_warps, g.bar_id);
+        unsigned long long traj;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(traj) : "r"(wslot));
+        team_sync(a.team_warps, g.bar_id);
         if (traj >= (unsigned long long)a.n_traj) break;
-        s.run((long long)traj);
+        K::run(a, g, smem, ell, my_off, row_of, row_ok, sc_base, (long long)traj);
     }
 }
 
 // Host-side launcher for one (RPL, CPL, MAXNNZ) instantiation.
 typedef cudaError_t (*launch_fn)(const LaunchArgs &, int grid, int block, size_t smem, cudaStream_t);
 
-template <int RPL, int CPL, int MAXNNZ>
+template <int RPL, int CPL, int MAXNNZ, int MAXT>
 cudaError_t launch_solver(const LaunchArgs &a, int grid, int block, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    if (block > MAXT) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    solve_kernel<RPL, CPL, MAXNNZ><<<grid, block, smem, stream>>>(a);
+    solve_kernel<RPL, CPL, MAXNNZ, MAXT><<<grid, block, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <int RPL, int CPL, int MAXNNZ>
+template <int RPL, int CPL, int MAXNNZ, int MAXT>
 cudaError_t occupancy_solver(int block, size_t smem, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solve_kernel<RPL, CPL, MAXNNZ>, block, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solve_kernel<RPL, CPL, MAXNNZ, MAXT>, block,
+                                                         smem);
 }
 
 }  // namespace qsim
