@@ -175,7 +175,8 @@ def main():
     ctx = Context(local_rank)
     prob = Problem(cqs)
     which = 0
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # a real (non-NULL) stream: the C ABI treats NULL as "the ctx stream"
+    torch.cuda.set_stream(stream)
     opts = _abi.default_opts(flags=_abi.FLAG_DEVICE_PTRS, stream=stream.cuda_stream)
 
     d_params = torch.from_numpy(params).to(dev)

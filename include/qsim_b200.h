@@ -242,8 +242,9 @@ int qsim_me_state(qsim_ctx *ctx, qsim_problem *prob, int64_t n_traj,
                   qsim_traj_stats *stats);
 
 /* Executed FP64 flop of the generator application per right-hand-side call of
- * one trajectory (8 flop per complex multiply-add actually issued), for the
- * roofline arithmetic.  which: 0 unitary_propagator, 1 unitary_state,
+ * one trajectory (8 flop per complex multiply-add actually issued; 4 when the
+ * generator is purely imaginary, i.e. a real Hamiltonian), for the roofline
+ * arithmetic.  which: 0 unitary_propagator, 1 unitary_state,
  * 2 me_propagator, 3 me_state.                                                */
 int qsim_problem_flops_per_rhs(qsim_problem *prob, int which, double *flops);
 

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "qsim_registry.h"
@@ -327,16 +328,22 @@ struct Plan {
     size_t smem = 0, scratch_per_team = 0;
 };
 
-static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block) {
-    const KernelVariant *(*lists[])(int *) = {variants_r1c1, variants_r1c3, variants_r2c1, variants_r2c2, variants_r3c1};
+static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int imag) {
+    const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c1_t288, variants_r1c3_t128,
+                                              variants_r1c3_t288, variants_r2c1_t128, variants_r2c1_t288,
+                                              variants_r2c2_t128, variants_r2c2_t288, variants_r3c1_t128,
+                                              variants_r3c1_t288};
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
         int cnt = 0;
         const KernelVariant *v = fn(&cnt);
         for (int i = 0; i < cnt; i++)
             if (v[i].rpl == rpl && v[i].cpl == cpl && v[i].maxnnz >= max_nnz && v[i].maxt >= block &&
-                (!best || v[i].maxnnz < best->maxnnz || (v[i].maxnnz == best->maxnnz && v[i].maxt < best->maxt)))
-                best = &v[i];
+                v[i].imag == imag) {
+                // smallest row capacity, then smallest block bound, then the preferred occupancy target
+                auto key = [&](const KernelVariant &k) { return std::make_tuple(k.maxnnz, k.maxt); };
+                if (!best || key(v[i]) < key(*best)) best = &v[i];
+            }
     }
     return best;
 }
@@ -381,7 +388,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         if (v >= 1 && v <= 15 && v * pl.team_warps * 32 <= 288) pl.teams_per_cta = v;
     }
     pl.block = pl.team_warps * 32 * pl.teams_per_cta;
-    pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block);
+    pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block, g.imag_only ? 1 : 0);
     if (!pl.kv)
         return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
                                               std::to_string(g.max_nnz) + ")");
@@ -392,7 +399,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     pl.n_dyn_pairs = g.slot_ptr[g.n_dyn_slots];
     const int n_ev = std::max<int>((int)g.evals.size(), 1);
     pl.common_bytes = 512 + ((4 * (g.n_dyn_slots + 1 + pl.n_dyn_pairs) + 15) & ~15) + 16 * std::max(pl.n_dyn_pairs, 1);
-    pl.team_bytes = 16 * 5 * pl.nvp + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 8 * (pl.team_warps * 4 + 8) +
+    pl.team_bytes = (((g.imag_only ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 8 * (pl.team_warps * 4 + 8) +
                     pl.team_warps * 2 * 16 * n * cpb;
     pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
     pl.scratch_per_team = pl.streamed ? (size_t)4 * pl.n_batches * cpb * n * sizeof(double2) : 0;
@@ -414,7 +421,8 @@ extern "C" int qsim_problem_flops_per_rhs(qsim_problem *p, int which, double *fl
     if (int rc = ensure_generator(p, w)) return rc;
     const Generator &g = p->gen[w];
     const double ncols = (which == 0 || which == 2) ? (double)g.n : 1.0;
-    *flops = 8.0 * (double)g.nnz * ncols;
+    // a complex multiply-add is 4 DFMA (8 flop); a purely imaginary generator needs 2 (4 flop)
+    *flops = (g.imag_only ? 4.0 : 8.0) * (double)g.nnz * ncols;
     return QSIM_OK;
 }
 

@@ -289,6 +289,9 @@ void build_generator(const qsim_problem &p, int which, Generator &g) {
         }
         g.slot_ptr.push_back((int32_t)g.pair_chan.size());
     }
+    g.imag_only = true;
+    for (const auto &w : g.pair_w)
+        if (w.real() != 0.0) g.imag_only = false;
     g.max_nnz = 0;
     g.nnz = 0;
     g.row_len.assign((size_t)n, 0);

@@ -5,28 +5,37 @@
 namespace qsim {
 
 struct KernelVariant {
-    int rpl, cpl, maxnnz, maxt;
+    int rpl, cpl, maxnnz, maxt, minb, imag;
     const char *name;
     launch_fn launch;
     cudaError_t (*occupancy)(int block, size_t smem, int *ctas_per_sm);
 };
 
 // defined one per translation unit (qsim_inst_*.cu) so the variants compile in parallel
-const KernelVariant *variants_r1c1(int *count);
-const KernelVariant *variants_r1c3(int *count);
-const KernelVariant *variants_r2c1(int *count);
-const KernelVariant *variants_r2c2(int *count);
-const KernelVariant *variants_r3c1(int *count);
+#define QSIM_DECLARE(FN) const KernelVariant *FN(int *count);
+QSIM_DECLARE(variants_r1c1_t128) QSIM_DECLARE(variants_r1c1_t288)
+QSIM_DECLARE(variants_r1c3_t128) QSIM_DECLARE(variants_r1c3_t288)
+QSIM_DECLARE(variants_r2c1_t128) QSIM_DECLARE(variants_r2c1_t288)
+QSIM_DECLARE(variants_r2c2_t128) QSIM_DECLARE(variants_r2c2_t288)
+QSIM_DECLARE(variants_r3c1_t128) QSIM_DECLARE(variants_r3c1_t288)
 
-#define QSIM_VARIANT(R, C, M, T) \
-    { R, C, M, T, "tsit5_r" #R "c" #C "_nnz" #M "_t" #T, launch_solver<R, C, M, T>, occupancy_solver<R, C, M, T> }
+#define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \
+    {                                                                                                     \
+        R, C, M, T, B, I, "tsit5_r" #R "c" #C "_nnz" #M "_t" #T "_im" #I,                                   \
+            launch_solver<R, C, M, T, B, (I != 0)>, occupancy_solver<R, C, M, T, B, (I != 0)>               \
+    }
 
-#define QSIM_DEFINE_VARIANTS(FN, R, C)                                                                     \
-    const KernelVariant *FN(int *count) {                                                                  \
-        static const KernelVariant v[] = {QSIM_VARIANT(R, C, 8, 128), QSIM_VARIANT(R, C, 16, 128),         \
-                                          QSIM_VARIANT(R, C, 8, 288), QSIM_VARIANT(R, C, 16, 288)};        \
-        *count = 4;                                                                                        \
-        return v;                                                                                          \
+// Row capacities 5 / 9 / 12 / 16: the generator rows are padded to the variant's capacity and applied
+// without per-entry branches (5 and 9 are the exact row lengths of the 2- and 3-transmon gate Hamiltonians).
+#define QSIM_DEFINE_VARIANTS(FN, R, C, T, B)                                                              \
+    const KernelVariant *FN(int *count) {                                                                 \
+        static const KernelVariant v[] = {                                                                \
+            QSIM_VARIANT(R, C, 5, T, B, 0),  QSIM_VARIANT(R, C, 5, T, B, 1),                              \
+            QSIM_VARIANT(R, C, 9, T, B, 0),  QSIM_VARIANT(R, C, 9, T, B, 1),                              \
+            QSIM_VARIANT(R, C, 12, T, B, 0), QSIM_VARIANT(R, C, 12, T, B, 1),                             \
+            QSIM_VARIANT(R, C, 16, T, B, 0), QSIM_VARIANT(R, C, 16, T, B, 1)};                            \
+        *count = (int)(sizeof(v) / sizeof(v[0]));                                                         \
+        return v;                                                                                         \
     }
 
 }  // namespace qsim

@@ -71,35 +71,45 @@ struct LaunchArgs {
 // stage-time fractions c2..c5 and c6 = c7 = 1 (stages 6 and 7 share one table)
 static __device__ __constant__ double kStageC[5] = {0.161, 0.327, 0.9, 0.9800255409045097, 1.0};
 
-// Tsit5 tableau (OrdinaryDiffEq Tsit5ConstantCache, Float64)
-#define A21 0.161
-#define A31 -0.008480655492356989
-#define A32 0.335480655492357
-#define A41 2.8971530571054935
-#define A42 -6.359448489975075
-#define A43 4.3622954328695815
-#define A51 5.325864828439257
-#define A52 -11.748883564062828
-#define A53 7.4955393428898365
-#define A54 -0.09249506636175525
-#define A61 5.86145544294642
-#define A62 -12.92096931784711
-#define A63 8.159367898576159
-#define A64 -0.071584973281401
-#define A65 -0.028269050394068383
-#define A71 0.09646076681806523
-#define A72 0.01
-#define A73 0.4798896504144996
-#define A74 1.379008574103742
-#define A75 -3.290069515436081
-#define A76 2.324710524099774
-#define BT1 -0.00178001105222577714
-#define BT2 -0.0008164344596567469
-#define BT3 0.007880878010261995
-#define BT4 -0.1447110071732629
-#define BT5 0.5823571654525552
-#define BT6 -0.45808210592918697
-#define BT7 0.015151515151515152
+// Tsit5 tableau (OrdinaryDiffEq Tsit5ConstantCache, Float64), in constant memory so that DFMA takes
+// the coefficient straight from the constant bank instead of materialising 64-bit immediates.
+static __device__ __constant__ double kTsit[28] = {
+    0.161,                                                                                        // a21
+    -0.008480655492356989, 0.335480655492357,                                                     // a31 a32
+    2.8971530571054935, -6.359448489975075, 4.3622954328695815,                                   // a41..a43
+    5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525,             // a51..a54
+    5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383,  // a61..a65
+    0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774,  // a71..a76
+    -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+    0.5823571654525552, -0.45808210592918697, 0.015151515151515152};                              // btilde1..7
+#define A21 kTsit[0]
+#define A31 kTsit[1]
+#define A32 kTsit[2]
+#define A41 kTsit[3]
+#define A42 kTsit[4]
+#define A43 kTsit[5]
+#define A51 kTsit[6]
+#define A52 kTsit[7]
+#define A53 kTsit[8]
+#define A54 kTsit[9]
+#define A61 kTsit[10]
+#define A62 kTsit[11]
+#define A63 kTsit[12]
+#define A64 kTsit[13]
+#define A65 kTsit[14]
+#define A71 kTsit[15]
+#define A72 kTsit[16]
+#define A73 kTsit[17]
+#define A74 kTsit[18]
+#define A75 kTsit[19]
+#define A76 kTsit[20]
+#define BT1 kTsit[21]
+#define BT2 kTsit[22]
+#define BT3 kTsit[23]
+#define BT4 kTsit[24]
+#define BT5 kTsit[25]
+#define BT6 kTsit[26]
+#define BT7 kTsit[27]
 
 // ---- shared memory through 32-bit addresses ------------------------------------------
 __device__ __forceinline__ double2 lds2(uint32_t addr) {
@@ -176,9 +186,10 @@ struct Geo {
             asm volatile("" : "+r"(const_cast<uint32_t &>(ell[i_][j_])));       \
     }
 
-template <int RPL, int CPL, int MAXNNZ>
+template <int RPL, int CPL, int MAXNNZ, bool IM>
 struct Kern {
     static constexpr int E = RPL * CPL;
+    static constexpr uint32_t VB = IM ? 8u : 16u;  // bytes per value slot (IM: imaginary part only)
     typedef double2 Vec[E];
 
     // Refresh tables table0 + s, s < NTAB, for the times tbase + kStageC[s]*dtv.  all == false: only
@@ -189,10 +200,15 @@ struct Kern {
                                                            double tbase, double dtv, bool all, int table0) {
         const int ne = a.g.n_evals;
         const SeriesTables *tab = reinterpret_cast<const SeriesTables *>(smem_gen);
-        const ResolvedEval *rev = reinterpret_cast<const ResolvedEval *>(smem_gen + (g.sm_rev - g.sm_tab) / 8);
         for (int it = g.team_thread; it < NTAB * ne; it += g.team_threads) {
             const int s = it % NTAB, e = it / NTAB;
-            const ResolvedEval r = rev[e];
+            union {
+                ResolvedEval r;
+                double2 q[9];
+            } ld;
+#pragma unroll
+            for (int i = 0; i < 9; i++) ld.q[i] = lds2(g.sm_rev + (uint32_t)sizeof(ResolvedEval) * e + 16 * i);
+            const ResolvedEval &r = ld.r;
             if (all || r.dynamic) {
                 double o0, o1;
                 run_resolved(r, tab->freq, tab->anh, tbase + kStageC[s] * dtv, &o0, &o1);
@@ -215,7 +231,10 @@ struct Kern {
                     vx = fma(w.x, c, vx);
                     vy = fma(w.y, c, vy);
                 }
-                sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
+                if (IM)
+                    sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * sl, vy);
+                else
+                    sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
             }
         } else {
             const int nsl = a.g.n_slots;
@@ -229,7 +248,10 @@ struct Kern {
                     vx = fma(w.x, c, vx);
                     vy = fma(w.y, c, vy);
                 }
-                sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
+                if (IM)
+                    sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * sl, vy);
+                else
+                    sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
             }
         }
         team_sync(a.team_warps, g.bar_id);
@@ -256,17 +278,29 @@ struct Kern {
             for (int c = 0; c < CPL; c++) acc[c] = make_double2(0.0, 0.0);
 #pragma unroll
             for (int j = 0; j < MAXNNZ; j++) {
-                if (j < nnz_u) {  // uniform across the grid
+                {   // no per-entry branch: short rows are padded with the zero slot, so all loads of a
+                    // stage can be hoisted ahead of the multiply-adds
                     const uint32_t e = ell[i][j];
-                    const double2 v = lds2(Vs + (e >> 16));
                     const uint32_t ya = yb + (e & 0xFFFFu);
+                    if (IM) {
+                        // A = i B with B real: (iB)(yr + i yi) = -B yi + i B yr
+                        const double v = lds1(Vs + (e >> 16));
 #pragma unroll
-                    for (int c = 0; c < CPL; c++) {
-                        const double2 y = lds2(ya + 16 * c);
-                        acc[c].x = fma(v.x, y.x, acc[c].x);
-                        acc[c].y = fma(v.x, y.y, acc[c].y);
-                        acc[c].x = fma(-v.y, y.y, acc[c].x);
-                        acc[c].y = fma(v.y, y.x, acc[c].y);
+                        for (int c = 0; c < CPL; c++) {
+                            const double2 y = lds2(ya + 16 * c);
+                            acc[c].x = fma(-v, y.y, acc[c].x);
+                            acc[c].y = fma(v, y.x, acc[c].y);
+                        }
+                    } else {
+                        const double2 v = lds2(Vs + (e >> 16));
+#pragma unroll
+                        for (int c = 0; c < CPL; c++) {
+                            const double2 y = lds2(ya + 16 * c);
+                            acc[c].x = fma(v.x, y.x, acc[c].x);
+                            acc[c].y = fma(v.x, y.y, acc[c].y);
+                            acc[c].x = fma(-v.y, y.y, acc[c].x);
+                            acc[c].y = fma(v.y, y.x, acc[c].y);
+                        }
                     }
                 }
             }
@@ -462,7 +496,7 @@ struct Kern {
             // ---- main loop ----
             const double lq_init = log(a.qoldinit);
             double lqold = lq_init;
-            const double inv_gamma = 1.0 / a.gamma, qlo = 1.0 / a.qmax, qhi = 1.0 / a.qmin;
+            const double inv_ntot = 1.0 / ntot;
             long long iters = 0;
             int n_attempt = 0;
             while (t < tend) {
@@ -557,8 +591,10 @@ struct Kern {
                         ex += BT5 * k5[e].x; ey += BT5 * k5[e].y;
                         ex += BT6 * k6[e].x; ey += BT6 * k6[e].y;
                         ex += BT7 * k7[e].x; ey += BT7 * k7[e].y;
+                        // residual scale abstol + max(|u|, |u_new|) reltol: sqrt as x*rsqrt(x), 1/x by __drcp_rn
                         const double m2 = fmax(u[e].x * u[e].x + u[e].y * u[e].y, tmp[e].x * tmp[e].x + tmp[e].y * tmp[e].y);
-                        const double rs = dt / (a.abstol + sqrt(m2) * a.reltol);
+                        const double mag = m2 > 0.0 ? m2 * rsqrt(m2) : 0.0;
+                        const double rs = dt * __drcp_rn(fma(mag, a.reltol, a.abstol));
                         ex *= rs; ey *= rs;
                         err[0] += ex * ex + ey * ey;
                     }
@@ -574,21 +610,22 @@ struct Kern {
                 }
                 n_attempt++;
                 team_sum<1>(err, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
-                const double eest = sqrt(err[0] / ntot);
-                if (!isfinite(eest)) { st.retcode = QSIM_RET_NONFINITE; break; }
-                // PI controller (stepsize_controller! / step_accept_controller! / step_reject_controller!):
-                // q = EEst^beta1 / qold^beta2 / gamma, clamped to [1/qmax, 1/qmin]
-                double q, le = 0.0;
-                if (eest == 0.0) {
-                    q = qlo;
+                // EEst^2 = mean |r_i|^2.  PI controller (stepsize_controller! / step_accept_controller! /
+                // step_reject_controller!): q = EEst^beta1 / qold^beta2 / gamma clamped to [1/qmax, 1/qmin];
+                // evaluated as dt * r with r = 1/q = gamma exp(beta2 log qold - beta1 log EEst).
+                const double e2 = err[0] * inv_ntot;
+                if (!isfinite(e2)) { st.retcode = QSIM_RET_NONFINITE; break; }
+                double r, le = 0.0;
+                if (e2 == 0.0) {
+                    r = a.qmax;
                 } else {
-                    le = log(eest);
-                    q = exp(a.beta1 * le - a.beta2 * lqold) * inv_gamma;
-                    q = fmax(qlo, fmin(qhi, q));
+                    le = 0.5 * log(e2);
+                    r = a.gamma * exp(a.beta2 * lqold - a.beta1 * le);
+                    r = fmin(a.qmax, fmax(a.qmin, r));
                 }
-                if (eest <= 1.0) {
+                if (e2 <= 1.0) {
                     st.n_accept++;
-                    lqold = eest == 0.0 ? lq_init : fmax(le, lq_init);  // qold = max(EEst, qoldinit)
+                    lqold = e2 == 0.0 ? lq_init : fmax(le, lq_init);  // qold = max(EEst, qoldinit)
                     if (!a.streamed) {
                         if (nsave_hi > nsave && g.warp_in_team < a.n_batches)
                             save_points(a, traj, ts, nsave, nsave_hi, t, dt, tnew, g.warp_in_team * g.cpb + g.colofs,
@@ -606,11 +643,11 @@ struct Kern {
                         ts_next = nsave < a.n_ts ? ts[nsave] : inf;
                     }
                     t = tnew;
-                    dt = dt / q;
+                    dt = dt * r;
                 } else {
                     st.n_reject++;
-                    const double q11 = eest == 0.0 ? 0.0 : exp(a.beta1 * le);
-                    dt = dt / fmin(qhi, q11 * inv_gamma);
+                    // dt / min(1/qmin, q11/gamma), q11 = EEst^beta1
+                    dt = dt * fmax(a.qmin, a.gamma * exp(-a.beta1 * le));
                 }
             }
             st.n_rhs = 3 + 6 * n_attempt;  // the reference also evaluates f(u0,t0) a second time
@@ -637,10 +674,12 @@ struct Kern {
 
 // MAXT: largest block the variant is launched with (128: one-warp teams, 4 per CTA, up to 255
 // registers; 288: teams of up to 9 warps, up to 168 registers).
-template <int RPL, int CPL, int MAXNNZ, int MAXT>
-__global__ void __launch_bounds__(MAXT) solve_kernel(const __grid_constant__ LaunchArgs a) {
+// MINB: minimum resident CTAs per SM the register allocation must allow; IM: purely imaginary generator
+// (unitary evolution under a real Hamiltonian): value slots hold Im(A) only, 2 DFMA per multiply-add.
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM>
+__global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant__ LaunchArgs a) {
     extern __shared__ __align__(16) double smem[];
-    typedef Kern<RPL, CPL, MAXNNZ> K;
+    typedef Kern<RPL, CPL, MAXNNZ, IM> K;
     const int n = a.g.n;
     Geo g;
     g.lane = threadIdx.x & 31;
@@ -666,9 +705,9 @@ __global__ void __launch_bounds__(MAXT) solve_kernel(const __grid_constant__ Lau
     g.sm_dchan = g.sm_dptr + 4 * (a.g.n_dyn_slots + 1);  // int[n_dyn_pairs]
     g.sm_dw = sbase + a.common_bytes - 16 * (a.g.n_dyn_pairs > 0 ? a.g.n_dyn_pairs : 1);  // double2[n_dyn_pairs]
     const uint32_t tbase = sbase + a.common_bytes + team_in_cta * a.team_bytes;
-    g.v_stride = 16u * a.nvp;
+    g.v_stride = K::VB * a.nvp;
     g.sm_V = tbase;
-    g.sm_chan = g.sm_V + 5 * g.v_stride;
+    g.sm_chan = g.sm_V + ((5 * g.v_stride + 15u) & ~15u);
     g.sm_rev = g.sm_chan + 8u * 5 * a.ncp;
     g.sm_red = g.sm_rev + (uint32_t)sizeof(ResolvedEval) * (a.g.n_evals > 0 ? a.g.n_evals : 1);
     const uint32_t ybytes = 16u * n * g.cpb;
@@ -687,7 +726,10 @@ __global__ void __launch_bounds__(MAXT) solve_kernel(const __grid_constant__ Lau
         }
         // the zero slot of every table (padding entries of short rows read it)
         for (int s = g.team_thread; s < 5; s += g.team_threads)
-            sts2(g.sm_V + s * g.v_stride + 16 * a.g.n_slots, make_double2(0.0, 0.0));
+            if (IM)
+                sts1(g.sm_V + s * g.v_stride + 8 * a.g.n_slots, 0.0);
+            else
+                sts2(g.sm_V + s * g.v_stride + 16 * a.g.n_slots, make_double2(0.0, 0.0));
     }
     __syncthreads();
 
@@ -701,12 +743,12 @@ __global__ void __launch_bounds__(MAXT) solve_kernel(const __grid_constant__ Lau
         row_of[i] = row0 + 32 * i;
         row_ok[i] = lane_active && row_of[i] < n;
         my_off[i] = 16u * (row_of[i] * g.cpb);
-        const uint32_t pad = (row_ok[i] ? my_off[i] : 0u) | ((16u * a.g.n_slots) << 16);
+        const uint32_t pad = (row_ok[i] ? my_off[i] : 0u) | ((K::VB * a.g.n_slots) << 16);
 #pragma unroll
         for (int j = 0; j < MAXNNZ; j++) {
             uint32_t e = 0xFFFFFFFFu;
             if (row_ok[i] && j < a.g.max_nnz) e = a.g.ell[(size_t)j * n + row_of[i]];
-            ell[i][j] = (e == 0xFFFFFFFFu) ? pad : ((16u * (e & 0xFFFFu) * g.cpb) | ((16u * (e >> 16)) << 16));
+            ell[i][j] = (e == 0xFFFFFFFFu) ? pad : ((16u * (e & 0xFFFFu) * g.cpb) | ((K::VB * (e >> 16)) << 16));
         }
     }
     double2 *sc_base = nullptr;
@@ -731,23 +773,23 @@ __global__ void __launch_bounds__(MAXT) solve_kernel(const __grid_constant__ Lau
 // Host-side launcher for one (RPL, CPL, MAXNNZ) instantiation.
 typedef cudaError_t (*launch_fn)(const LaunchArgs &, int grid, int block, size_t smem, cudaStream_t);
 
-template <int RPL, int CPL, int MAXNNZ, int MAXT>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM>
 cudaError_t launch_solver(const LaunchArgs &a, int grid, int block, size_t smem, cudaStream_t stream) {
     if (block > MAXT) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT>,
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    solve_kernel<RPL, CPL, MAXNNZ, MAXT><<<grid, block, smem, stream>>>(a);
+    solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM><<<grid, block, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <int RPL, int CPL, int MAXNNZ, int MAXT>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM>
 cudaError_t occupancy_solver(int block, size_t smem, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT>,
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solve_kernel<RPL, CPL, MAXNNZ, MAXT>, block,
-                                                         smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM>,
+                                                         block, smem);
 }
 
 }  // namespace qsim

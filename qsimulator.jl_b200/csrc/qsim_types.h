@@ -59,6 +59,7 @@ struct Generator {
     std::vector<cplx> pair_w;
     std::vector<EvalDesc> evals;
     int64_t nnz = 0;           // total stored entries (executed complex MACs per column per RHS)
+    bool imag_only = false;    // every value slot is purely imaginary (A = i B, B real): real H, no dissipator
 };
 
 }  // namespace qsim
