@@ -325,8 +325,57 @@ struct Plan {
     int w = 0, ncols = 1, identity = 0;
     int groups = 1, n_batches = 1, team_warps = 1, teams_per_cta = 1, streamed = 0;
     int block = 32, grid = 1, nvp = 0, ncp = 0, common_bytes = 0, team_bytes = 0, n_dyn_pairs = 0;
+    int y_row_stride = 1, y_grp_stride = 1;
     size_t smem = 0, scratch_per_team = 0;
 };
+
+// Shared-memory wavefronts of the stage-vector gathers and stores for a candidate layout: the stage
+// buffer holds element (row, group g, column c) at 16-byte unit row*S + g*Cg + c.  A 128-bit shared
+// access is served a quarter warp (8 lanes) at a time; lanes hitting the same 16-byte bank group
+// (unit mod 8) at different addresses serialise.
+static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S, int Cg) {
+    const int n = g.n;
+    long cost = 0;
+    for (int i = 0; i < rpl; i++) {
+        for (int j = 0; j <= g.max_nnz; j++) {  // j == max_nnz: the lane's own store
+            for (int q = 0; q < 4; q++) {
+                int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int seen[8][8];
+                for (int l = 8 * q; l < 8 * q + 8; l++) {
+                    int gi = 0, r = l + 32 * i;
+                    bool active = true;
+                    if (groups > 1) {
+                        active = l < groups * n;
+                        const int le = active ? l : groups * n - 1;
+                        gi = le / n;
+                        r = le % n;
+                    }
+                    if (r >= n) {
+                        active = false;
+                        r = n - 1;
+                    }
+                    int src = r;
+                    if (j == g.max_nnz) {
+                        if (!active) continue;  // inactive lanes do not store
+                    } else if (j == 0) {
+                        continue;  // diagonal operand comes from registers
+                    } else {
+                        src = (int)(g.ell[(size_t)j * n + r] & 0xFFFFu);
+                    }
+                    const int unit = src * S + gi * Cg;
+                    const int b = unit & 7;
+                    bool dup = false;
+                    for (int k = 0; k < cnt[b]; k++) dup = dup || seen[b][k] == unit;
+                    if (!dup) seen[b][cnt[b]++] = unit;
+                }
+                int w = 0;
+                for (int b = 0; b < 8; b++) w = std::max(w, cnt[b]);
+                cost += (long)w * cpl;
+            }
+        }
+    }
+    return cost;
+}
 
 static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int imag) {
     const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c1_t288, variants_r1c3_t128,
@@ -392,15 +441,35 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     if (!pl.kv)
         return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
                                               std::to_string(g.max_nnz) + ")");
-    if (16 * n * cpb > 65535 || g.n_slots > 4094)
-        return fail(QSIM_ERR_UNSUPPORTED, "generator too large for the packed 16-bit row/slot offsets");
+    // stage-buffer layout: smallest-cost (row stride, group stride) near the dense one
+    {
+        long best = -1;
+        for (int Cg = cpl; Cg <= cpl + 16; Cg++)
+            for (int S = (pl.groups - 1) * Cg + cpl; S <= (pl.groups - 1) * Cg + cpl + 16; S++) {
+                if (pl.groups == 1 && Cg > cpl) break;  // no groups: only the row stride matters
+                if (16 * n * S > 65535) continue;
+                const long c = layout_cost(g, rpl, cpl, pl.groups, S, Cg) * 64 + S;  // ties: smaller buffer
+                if (best < 0 || c < best) {
+                    best = c;
+                    pl.y_row_stride = S;
+                    pl.y_grp_stride = Cg;
+                }
+            }
+        if (best < 0) return fail(QSIM_ERR_UNSUPPORTED, "state too large for the packed 16-bit row offsets");
+        if (std::getenv("QSIM_DEBUG"))
+            std::fprintf(stderr, "[qsim] n=%d groups=%d cpl=%d: stage layout S=%d Cg=%d wavefronts %ld (dense layout %ld)\n", n,
+                         pl.groups, cpl, pl.y_row_stride, pl.y_grp_stride, best / 64,
+                         layout_cost(g, rpl, cpl, pl.groups, cpb, cpl));
+    }
+    if (g.n_slots > 4094)
+        return fail(QSIM_ERR_UNSUPPORTED, "generator too large for the packed 16-bit slot offsets");
     pl.nvp = (g.n_slots + 1 + 1) & ~1;  // + the zero slot, even
     pl.ncp = (g.n_chan + 1) & ~1;
     pl.n_dyn_pairs = g.slot_ptr[g.n_dyn_slots];
     const int n_ev = std::max<int>((int)g.evals.size(), 1);
     pl.common_bytes = 512 + ((4 * (g.n_dyn_slots + 1 + pl.n_dyn_pairs) + 15) & ~15) + 16 * std::max(pl.n_dyn_pairs, 1);
     pl.team_bytes = (((g.imag_only ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 8 * (pl.team_warps * 4 + 8) +
-                    pl.team_warps * 2 * 16 * n * cpb;
+                    pl.team_warps * 2 * 16 * n * pl.y_row_stride;
     pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
     pl.scratch_per_team = pl.streamed ? (size_t)4 * pl.n_batches * cpb * n * sizeof(double2) : 0;
     if (pl.smem > 220 * 1024) return fail(QSIM_ERR_UNSUPPORTED, "problem needs more shared memory than one SM has");
@@ -563,6 +632,8 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.teams_per_cta = pl.teams_per_cta;
     a.n_batches = pl.n_batches;
     a.groups = pl.groups;
+    a.y_row_stride = pl.y_row_stride;
+    a.y_grp_stride = pl.y_grp_stride;
     a.streamed = pl.streamed;
     a.nvp = pl.nvp;
     a.ncp = pl.ncp;

@@ -292,19 +292,58 @@ void build_generator(const qsim_problem &p, int which, Generator &g) {
     g.imag_only = true;
     for (const auto &w : g.pair_w)
         if (w.real() != 0.0) g.imag_only = false;
-    g.max_nnz = 0;
+    // Row layout: entry 0 is the diagonal (an explicit zero, slot 0xFFFF, if the row stores none), so the
+    // kernels can take that operand from registers.  Off-diagonal entries are aligned by diagonal offset
+    // (src - row) when that does not lengthen the rows: entry j of every row then reads a shifted copy of
+    // the row index, which keeps the shared-memory gathers of a quarter warp on distinct banks.
     g.nnz = 0;
-    g.row_len.assign((size_t)n, 0);
+    int plain_max = 0;
+    std::vector<int> offsets;
     for (int r = 0; r < n; r++) {
-        g.max_nnz = std::max(g.max_nnz, (int)row_entries[r].size());
+        int cnt = 1;
+        for (auto &e : row_entries[r])
+            if (e.first != r) {
+                cnt++;
+                offsets.push_back(e.first - r);
+            }
+        plain_max = std::max(plain_max, cnt);
         g.nnz += (int64_t)row_entries[r].size();
-        if (row_entries[r].size() > 255) throw std::runtime_error("generator row longer than 255 entries");
-        g.row_len[r] = (uint8_t)row_entries[r].size();
     }
-    g.ell.assign((size_t)std::max(g.max_nnz, 1) * n, 0xFFFFFFFFu);
-    for (int r = 0; r < n; r++)
-        for (size_t j = 0; j < row_entries[r].size(); j++)
-            g.ell[j * n + r] = (uint32_t)row_entries[r][j].first | ((uint32_t)new_id[row_entries[r][j].second] << 16);
+    std::sort(offsets.begin(), offsets.end());
+    offsets.erase(std::unique(offsets.begin(), offsets.end()), offsets.end());
+    const bool aligned = 1 + (int)offsets.size() <= plain_max;
+    g.max_nnz = aligned ? 1 + (int)offsets.size() : plain_max;
+    if (g.max_nnz > 255) throw std::runtime_error("generator row longer than 255 entries");
+    g.row_len.assign((size_t)n, (uint8_t)g.max_nnz);
+    g.ell.assign((size_t)g.max_nnz * n, 0xFFFFFFFFu);
+    for (int r = 0; r < n; r++) {
+        uint32_t diag = (uint32_t)r | (0xFFFFu << 16);
+        int next = 1;
+        for (auto &e : row_entries[r]) {
+            const uint32_t packed = (uint32_t)e.first | ((uint32_t)new_id[e.second] << 16);
+            if (e.first == r) {
+                diag = packed;
+            } else {
+                const int j = aligned ? 1 + (int)(std::lower_bound(offsets.begin(), offsets.end(), e.first - r) -
+                                                  offsets.begin())
+                                      : next++;
+                g.ell[(size_t)j * n + r] = packed;
+            }
+        }
+        g.ell[r] = diag;
+        // padding entries carry slot 0xFFFF (zero).  In aligned mode they still read "their" diagonal's
+        // source row (shifted by multiples of 8 rows into range), which keeps the bank pattern regular.
+        for (int j = 1; j < g.max_nnz; j++) {
+            if (g.ell[(size_t)j * n + r] != 0xFFFFFFFFu) continue;
+            int src = r;
+            if (aligned && n >= 8) {
+                src = r + offsets[j - 1];
+                while (src >= n) src -= 8;
+                while (src < 0) src += 8;
+            }
+            g.ell[(size_t)j * n + r] = (uint32_t)src | (0xFFFFu << 16);
+        }
+    }
 }
 
 // Dense A(t) from the compiled generator (tests / introspection).
@@ -329,8 +368,9 @@ void host_eval_generator(const Generator &g, double t, const double *row, cplx *
     const int n = g.n;
     for (size_t q = 0; q < (size_t)n * n; q++) dense[q] = cplx(0, 0);
     for (int r = 0; r < n; r++)
-        for (int j = 0; j < g.row_len[r]; j++) {
+        for (int j = 0; j < g.max_nnz; j++) {
             uint32_t e = g.ell[(size_t)j * n + r];
+            if ((e >> 16) == 0xFFFFu) continue;  // padding / explicit zero diagonal
             dense[(size_t)r + (size_t)(e & 0xFFFF) * n] += V[e >> 16];
         }
 }

@@ -61,6 +61,7 @@ struct LaunchArgs {
     unsigned long long *work_counter;
     double2 *scratch;     // streamed mode: [n_teams_total][4][n_batches*cpb*n]
     int team_warps, teams_per_cta, n_batches, groups, streamed;
+    int y_row_stride, y_grp_stride;  // stage-buffer layout in 16-byte units (chosen on the host to avoid bank conflicts)
     int nvp, ncp;         // padded slot / channel counts (nvp > n_slots: slot n_slots is the zero slot)
     int common_bytes;     // CTA-wide shared region (series tables + dynamic pair lists)
     int team_bytes;       // shared bytes per team
@@ -268,9 +269,10 @@ struct Kern {
         __syncwarp();
     }
 
-    // k = A(t_s) * y : sparse row gather, value table Vs, stage vector yb (both shared-memory addresses)
+    // k = A(t_s) * y : sparse row gather, value table Vs, stage vector yb (both shared-memory addresses).
+    // Entry 0 of every row is its diagonal: that operand is the lane's own stage value `yreg`.
     static __device__ __forceinline__ void apply(uint32_t Vs, uint32_t yb, const uint32_t (&ell)[RPL][MAXNNZ],
-                                                 int nnz_u, Vec &k) {
+                                                 const Vec &yreg, Vec &k) {
 #pragma unroll
         for (int i = 0; i < RPL; i++) {
             double2 acc[CPL];
@@ -287,7 +289,7 @@ struct Kern {
                         const double v = lds1(Vs + (e >> 16));
 #pragma unroll
                         for (int c = 0; c < CPL; c++) {
-                            const double2 y = lds2(ya + 16 * c);
+                            const double2 y = j == 0 ? yreg[i * CPL + c] : lds2(ya + 16 * c);
                             acc[c].x = fma(-v, y.y, acc[c].x);
                             acc[c].y = fma(v, y.x, acc[c].y);
                         }
@@ -295,7 +297,7 @@ struct Kern {
                         const double2 v = lds2(Vs + (e >> 16));
 #pragma unroll
                         for (int c = 0; c < CPL; c++) {
-                            const double2 y = lds2(ya + 16 * c);
+                            const double2 y = j == 0 ? yreg[i * CPL + c] : lds2(ya + 16 * c);
                             acc[c].x = fma(v.x, y.x, acc[c].x);
                             acc[c].y = fma(v.x, y.y, acc[c].y);
                             acc[c].x = fma(-v.y, y.y, acc[c].x);
@@ -403,7 +405,6 @@ struct Kern {
                                                const int (&row_of)[RPL], const bool (&row_ok)[RPL], double2 *sc_base,
                                                long long traj) {
         const int n = a.g.n;
-        const int nnz_u = a.g.max_nnz;
         const double *ts = a.ts + (size_t)traj * a.ts_stride;
         const double *prow = a.params + (size_t)traj * a.n_params;
         const double t0 = ts[0], tend = ts[a.n_ts - 1];
@@ -450,7 +451,7 @@ struct Kern {
                 initial_state(a, traj, col0, row_of, row_ok, u);
                 for (int ks = 0; ks < nsave; ks++) write_out(a, traj, ks, col0, row_of, row_ok, u);
                 put_stage(u, yb0, my_off, row_ok);
-                apply(V0, yb0, ell, nnz_u, k1);
+                apply(V0, yb0, ell, u, k1);
                 if (a.streamed) {
                     store_batch(sc_u0, n, col0, row_of, row_ok, u);
                     store_batch(sc_k0, n, col0, row_of, row_ok, k1);
@@ -478,7 +479,7 @@ struct Kern {
 #pragma unroll
                 for (int e = 0; e < E; e++) tmp[e] = make_double2(u[e].x + dt0 * k1[e].x, u[e].y + dt0 * k1[e].y);
                 put_stage(tmp, yb1, my_off, row_ok);
-                apply(V1, yb1, ell, nnz_u, k2);
+                apply(V1, yb1, ell, tmp, k2);
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     const double sk = a.abstol + sqrt(u[e].x * u[e].x + u[e].y * u[e].y) * a.reltol;
@@ -531,7 +532,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(tmp, yb0, my_off, row_ok);
-                    apply(V0, yb0, ell, nnz_u, k2);
+                    apply(V0, yb0, ell, tmp, k2);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A31 * k1[e].x, ay = A31 * k1[e].y;
@@ -539,7 +540,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(tmp, yb1, my_off, row_ok);
-                    apply(V1, yb1, ell, nnz_u, k3);
+                    apply(V1, yb1, ell, tmp, k3);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A41 * k1[e].x, ay = A41 * k1[e].y;
@@ -548,7 +549,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(tmp, yb0, my_off, row_ok);
-                    apply(V2, yb0, ell, nnz_u, k4);
+                    apply(V2, yb0, ell, tmp, k4);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A51 * k1[e].x, ay = A51 * k1[e].y;
@@ -558,7 +559,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(tmp, yb1, my_off, row_ok);
-                    apply(V3, yb1, ell, nnz_u, k5);
+                    apply(V3, yb1, ell, tmp, k5);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A61 * k1[e].x, ay = A61 * k1[e].y;
@@ -569,7 +570,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(tmp, yb0, my_off, row_ok);
-                    apply(V4, yb0, ell, nnz_u, k6);
+                    apply(V4, yb0, ell, tmp, k6);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A71 * k1[e].x, ay = A71 * k1[e].y;
@@ -581,7 +582,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);  // u_new
                     }
                     put_stage(tmp, yb1, my_off, row_ok);
-                    apply(V4, yb1, ell, nnz_u, k7);
+                    apply(V4, yb1, ell, tmp, k7);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ex = BT1 * k1[e].x, ey = BT1 * k1[e].y;
@@ -689,12 +690,15 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     g.warp_in_team = g.team_thread >> 5;
     g.bar_id = 1 + team_in_cta;
     g.cpb = a.groups * CPL;
+    // lane -> (row, column group).  Lanes without a row mimic the addresses of the last active lane so
+    // that their (discarded) gathers broadcast instead of adding bank conflicts.
     int g_idx = 0, row0 = g.lane;
     bool lane_active = true;
     if (a.groups > 1) {
-        g_idx = g.lane / n;
-        row0 = g.lane - g_idx * n;
-        lane_active = g_idx < a.groups;
+        lane_active = g.lane < a.groups * n;
+        const int le = lane_active ? g.lane : a.groups * n - 1;
+        g_idx = le / n;
+        row0 = le - g_idx * n;
     }
     g.colofs = g_idx * CPL;
 
@@ -710,8 +714,8 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     g.sm_chan = g.sm_V + ((5 * g.v_stride + 15u) & ~15u);
     g.sm_rev = g.sm_chan + 8u * 5 * a.ncp;
     g.sm_red = g.sm_rev + (uint32_t)sizeof(ResolvedEval) * (a.g.n_evals > 0 ? a.g.n_evals : 1);
-    const uint32_t ybytes = 16u * n * g.cpb;
-    g.sm_y0 = g.sm_red + 8u * (a.team_warps * 4 + 8) + g.warp_in_team * 2 * ybytes + 16u * g.colofs;
+    const uint32_t ybytes = 16u * n * a.y_row_stride;
+    g.sm_y0 = g.sm_red + 8u * (a.team_warps * 4 + 8) + g.warp_in_team * 2 * ybytes + 16u * g_idx * a.y_grp_stride;
     g.sm_y1 = g.sm_y0 + ybytes;
 
     // ---- CTA-wide constants: series tables and the dynamic slots' pair lists ----
@@ -742,13 +746,16 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     for (int i = 0; i < RPL; i++) {
         row_of[i] = row0 + 32 * i;
         row_ok[i] = lane_active && row_of[i] < n;
-        my_off[i] = 16u * (row_of[i] * g.cpb);
-        const uint32_t pad = (row_ok[i] ? my_off[i] : 0u) | ((K::VB * a.g.n_slots) << 16);
+        const int row_eff = row_of[i] < n ? row_of[i] : n - 1;
+        my_off[i] = 16u * (row_eff * a.y_row_stride);
 #pragma unroll
         for (int j = 0; j < MAXNNZ; j++) {
-            uint32_t e = 0xFFFFFFFFu;
-            if (row_ok[i] && j < a.g.max_nnz) e = a.g.ell[(size_t)j * n + row_of[i]];
-            ell[i][j] = (e == 0xFFFFFFFFu) ? pad : ((16u * (e & 0xFFFFu) * g.cpb) | ((K::VB * (e >> 16)) << 16));
+            // rows shorter than the variant's capacity: own row, zero slot
+            uint32_t e = (uint32_t)row_eff | (0xFFFFu << 16);
+            if (j < a.g.max_nnz) e = a.g.ell[(size_t)j * n + row_eff];
+            // slot 0xFFFF marks a zero entry (padding, or a row without a stored diagonal)
+            const uint32_t sl = (!row_ok[i] || (e >> 16) == 0xFFFFu) ? (uint32_t)a.g.n_slots : (e >> 16);
+            ell[i][j] = (16u * (e & 0xFFFFu) * a.y_row_stride) | ((K::VB * sl) << 16);
         }
     }
     double2 *sc_base = nullptr;
