@@ -48,7 +48,8 @@ def build_workload(world: int, rank: int):
     else:
         grid = W.amp_freq_grid(N_AMP, N_FREQ * world)
         ts = np.arange(0.0, 201.0)
-    params = np.ascontiguousarray(grid[rank::world])
+    from qsim_b200 import shard_params
+    params, _ = shard_params(grid, world, rank)   # block-cyclic by parameter index
     return cqs, params, ts
 
 

@@ -19,3 +19,4 @@ from .composite import (CompositeQSystem, add_hamiltonian, add_lindblad, embed, 
 from . import _abi
 from ._ffi import Context, Problem, QsimError, PinnedArray, default_context
 from .time_evolution import unitary_propagator, unitary_state, me_propagator, me_state
+from .sweep import shard_indices, shard_params, scatter_back, gather_results
