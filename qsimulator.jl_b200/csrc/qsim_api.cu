@@ -73,7 +73,11 @@ struct qsim_problem::DeviceCopy {
     int32_t *slot_ptr = nullptr, *pair_chan = nullptr;
     double2 *pair_w = nullptr;
     EvalDesc *evals = nullptr;
+    uint32_t *ell_packed = nullptr;  // row-split kernels
+    int packed_stride = -1;
     void free_all() {
+        cudaFree(ell_packed);
+        ell_packed = nullptr;
         cudaFree(ell); cudaFree(row_len); cudaFree(slot_ptr); cudaFree(pair_chan); cudaFree(pair_w); cudaFree(evals);
         ell = nullptr; row_len = nullptr; slot_ptr = nullptr; pair_chan = nullptr; pair_w = nullptr; evals = nullptr;
     }
@@ -325,7 +329,7 @@ struct Plan {
     int w = 0, ncols = 1, identity = 0;
     int groups = 1, n_batches = 1, team_warps = 1, teams_per_cta = 1, streamed = 0;
     int block = 32, grid = 1, nvp = 0, ncp = 0, common_bytes = 0, team_bytes = 0, n_dyn_pairs = 0;
-    int y_row_stride = 1, y_grp_stride = 1;
+    int y_row_stride = 1, y_grp_stride = 1, rowsplit = 0;
     size_t smem = 0, scratch_per_team = 0;
 };
 
@@ -377,18 +381,18 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
     return cost;
 }
 
-static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int imag) {
+static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int imag, int rs) {
     const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c1_t288, variants_r1c3_t128,
                                               variants_r1c3_t288, variants_r2c1_t128, variants_r2c1_t288,
                                               variants_r2c2_t128, variants_r2c2_t288, variants_r3c1_t128,
-                                              variants_r3c1_t288};
+                                              variants_r3c1_t288, variants_rowsplit};
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
         int cnt = 0;
         const KernelVariant *v = fn(&cnt);
         for (int i = 0; i < cnt; i++)
-            if (v[i].rpl == rpl && v[i].cpl == cpl && v[i].maxnnz >= max_nnz && v[i].maxt >= block &&
-                v[i].imag == imag) {
+            if (v[i].rpl == rpl && v[i].cpl == cpl && (rs || v[i].maxnnz >= max_nnz) && v[i].maxt >= block &&
+                v[i].imag == imag && v[i].rs == rs) {
                 // smallest row capacity, then smallest block bound, then the preferred occupancy target
                 auto key = [&](const KernelVariant &k) { return std::make_tuple(k.maxnnz, k.maxt); };
                 if (!best || key(v[i]) < key(*best)) best = &v[i];
@@ -419,12 +423,20 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     } else if (n <= 96) {
         rpl = 3;
         cpl = 1;
+    } else if (n <= 9 * 96) {
+        // row split: one column at a time, its rows spread over ceil(n/96) warps
+        rpl = 3;
+        cpl = 1;
+        pl.rowsplit = 1;
     } else {
-        return fail(QSIM_ERR_UNSUPPORTED, "state vectors longer than 96 entries (e.g. d^2 = 729 Lindblad) have no kernel yet");
+        return fail(QSIM_ERR_UNSUPPORTED, "state vectors longer than 864 entries have no kernel yet");
     }
     const int cpb = pl.groups * cpl;
     pl.n_batches = (pl.ncols + cpb - 1) / cpb;
-    if (pl.n_batches <= 9) {
+    if (pl.rowsplit) {
+        pl.team_warps = (n + 95) / 96;
+        pl.streamed = pl.n_batches > 1 ? 1 : 0;
+    } else if (pl.n_batches <= 9) {
         pl.streamed = 0;
         pl.team_warps = pl.n_batches;
     } else {
@@ -437,7 +449,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         if (v >= 1 && v <= 15 && v * pl.team_warps * 32 <= 288) pl.teams_per_cta = v;
     }
     pl.block = pl.team_warps * 32 * pl.teams_per_cta;
-    pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block, g.imag_only ? 1 : 0);
+    pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block, g.imag_only ? 1 : 0, pl.rowsplit);
     if (!pl.kv)
         return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
                                               std::to_string(g.max_nnz) + ")");
@@ -469,7 +481,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     const int n_ev = std::max<int>((int)g.evals.size(), 1);
     pl.common_bytes = 512 + ((4 * (g.n_dyn_slots + 1 + pl.n_dyn_pairs) + 15) & ~15) + 16 * std::max(pl.n_dyn_pairs, 1);
     pl.team_bytes = (((g.imag_only ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 8 * (pl.team_warps * 4 + 8) +
-                    pl.team_warps * 2 * 16 * n * pl.y_row_stride;
+                    (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride;
     pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
     pl.scratch_per_team = pl.streamed ? (size_t)4 * pl.n_batches * cpb * n * sizeof(double2) : 0;
     if (pl.smem > 220 * 1024) return fail(QSIM_ERR_UNSUPPORTED, "problem needs more shared memory than one SM has");
@@ -561,7 +573,28 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     CU(cudaSetDevice(c->device));
     if (int rc = ensure_device_copy(c, p, pl.w)) return rc;
     const Generator &g = p->gen[pl.w];
-    const qsim_problem::DeviceCopy *dc = p->dev[pl.w];
+    qsim_problem::DeviceCopy *dc = p->dev[pl.w];
+    if (pl.rowsplit && (!dc->ell_packed || dc->packed_stride != pl.y_row_stride)) {
+        // translated sparse rows for the row-split kernels: byte offsets into the stage buffer / value table,
+        // plus eight zero-slot padding rows for the lanes past the last row
+        const int rows = g.n + 8;
+        const uint32_t vb = g.imag_only ? 8u : 16u;
+        std::vector<uint32_t> packed((size_t)g.max_nnz * rows);
+        for (int j = 0; j < g.max_nnz; j++)
+            for (int r = 0; r < rows; r++) {
+                uint32_t src = (uint32_t)(g.n - 1), sl = (uint32_t)g.n_slots;
+                if (r < g.n) {
+                    const uint32_t e = g.ell[(size_t)j * g.n + r];
+                    src = e & 0xFFFFu;
+                    if ((e >> 16) != 0xFFFFu) sl = e >> 16;
+                }
+                packed[(size_t)j * rows + r] = (16u * src * (uint32_t)pl.y_row_stride) | ((vb * sl) << 16);
+            }
+        if (dc->ell_packed) cudaFree(dc->ell_packed);
+        dc->ell_packed = nullptr;
+        CU(upload(&dc->ell_packed, packed));
+        dc->packed_stride = pl.y_row_stride;
+    }
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : c->stream;
 
     int ctas_per_sm = 0;
@@ -620,6 +653,8 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.g.pair_w = dc->pair_w;
     a.g.evals = dc->evals;
     a.g.tab = c->d_tab;
+    a.ell_packed = dc->ell_packed;
+    a.ell_rows = g.n + 8;
     a.ncols = pl.ncols;
     a.identity_init = pl.identity;
     a.n_params = p->n_params;

@@ -1,0 +1,9 @@
+// Instantiates the row-split Tsit5 kernels (state vectors longer than 96 entries, e.g. d^2 = 729).
+#include "qsim_registry.h"
+namespace qsim {
+const KernelVariant *variants_rowsplit(int *count) {
+    static const KernelVariant v[] = {QSIM_VARIANT_RS(0), QSIM_VARIANT_RS(1)};
+    *count = 2;
+    return v;
+}
+}

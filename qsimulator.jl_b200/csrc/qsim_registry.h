@@ -5,7 +5,7 @@
 namespace qsim {
 
 struct KernelVariant {
-    int rpl, cpl, maxnnz, maxt, minb, imag;
+    int rpl, cpl, maxnnz, maxt, minb, imag, rs;
     const char *name;
     launch_fn launch;
     cudaError_t (*occupancy)(int block, size_t smem, int *ctas_per_sm);
@@ -18,11 +18,18 @@ QSIM_DECLARE(variants_r1c3_t128) QSIM_DECLARE(variants_r1c3_t288)
 QSIM_DECLARE(variants_r2c1_t128) QSIM_DECLARE(variants_r2c1_t288)
 QSIM_DECLARE(variants_r2c2_t128) QSIM_DECLARE(variants_r2c2_t288)
 QSIM_DECLARE(variants_r3c1_t128) QSIM_DECLARE(variants_r3c1_t288)
+QSIM_DECLARE(variants_rowsplit)
 
 #define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \
     {                                                                                                     \
-        R, C, M, T, B, I, "tsit5_r" #R "c" #C "_nnz" #M "_t" #T "_im" #I,                                   \
-            launch_solver<R, C, M, T, B, (I != 0)>, occupancy_solver<R, C, M, T, B, (I != 0)>               \
+        R, C, M, T, B, I, 0, "tsit5_r" #R "c" #C "_nnz" #M "_t" #T "_im" #I,                                \
+            launch_solver<R, C, M, T, B, (I != 0), false>, occupancy_solver<R, C, M, T, B, (I != 0), false> \
+    }
+// row-split variants: rows spread over the team's warps, sparse rows streamed from global memory
+#define QSIM_VARIANT_RS(I)                                                                                \
+    {                                                                                                     \
+        3, 1, 1, 288, 1, I, 1, "tsit5_rowsplit_r3c1_t288_im" #I, launch_solver<3, 1, 1, 288, 1, (I != 0), true>, \
+            occupancy_solver<3, 1, 1, 288, 1, (I != 0), true>                                             \
     }
 
 // Row capacities 5 / 9 / 12 / 16: the generator rows are padded to the variant's capacity and applied

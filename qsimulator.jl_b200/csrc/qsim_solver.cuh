@@ -60,6 +60,8 @@ struct LaunchArgs {
     qsim_traj_stats *stats;
     unsigned long long *work_counter;
     double2 *scratch;     // streamed mode: [n_teams_total][4][n_batches*cpb*n]
+    const uint32_t *ell_packed;  // row-split mode: [max_nnz][ell_rows] translated (source offset | slot offset << 16)
+    int ell_rows;                // n + 8: eight zero-slot padding rows for lanes past the last row
     int team_warps, teams_per_cta, n_batches, groups, streamed;
     int y_row_stride, y_grp_stride;  // stage-buffer layout in 16-byte units (chosen on the host to avoid bank conflicts)
     int nvp, ncp;         // padded slot / channel counts (nvp > n_slots: slot n_slots is the zero slot)
@@ -187,7 +189,10 @@ struct Geo {
             asm volatile("" : "+r"(const_cast<uint32_t &>(ell[i_][j_])));       \
     }
 
-template <int RPL, int CPL, int MAXNNZ, bool IM>
+// RS (row split): the rows of one column are spread over all warps of the team (n > 96, e.g. the
+// d^2 = 729 Lindblad propagator): stage buffers are team-wide, stage exchange uses the team barrier,
+// every warp visits every column, and the sparse rows are read from global memory (L1-resident).
+template <int RPL, int CPL, int MAXNNZ, bool IM, bool RS>
 struct Kern {
     static constexpr int E = RPL * CPL;
     static constexpr uint32_t VB = IM ? 8u : 16u;  // bytes per value slot (IM: imaginary part only)
@@ -258,53 +263,68 @@ struct Kern {
         team_sync(a.team_warps, g.bar_id);
     }
 
-    static __device__ __forceinline__ void put_stage(const Vec &y, uint32_t yb, const uint32_t (&my_off)[RPL],
-                                                     const bool (&row_ok)[RPL]) {
+    static __device__ __forceinline__ void put_stage(const LaunchArgs &a, const Geo &g, const Vec &y, uint32_t yb,
+                                                     const uint32_t (&my_off)[RPL], const bool (&row_ok)[RPL]) {
 #pragma unroll
         for (int i = 0; i < RPL; i++)
             if (row_ok[i]) {
 #pragma unroll
                 for (int c = 0; c < CPL; c++) sts2(yb + my_off[i] + 16 * c, y[i * CPL + c]);
             }
-        __syncwarp();
+        if (RS)
+            team_sync(a.team_warps, g.bar_id);
+        else
+            __syncwarp();
     }
 
     // k = A(t_s) * y : sparse row gather, value table Vs, stage vector yb (both shared-memory addresses).
     // Entry 0 of every row is its diagonal: that operand is the lane's own stage value `yreg`.
-    static __device__ __forceinline__ void apply(uint32_t Vs, uint32_t yb, const uint32_t (&ell)[RPL][MAXNNZ],
+    static __device__ __forceinline__ void mac(uint32_t Vs, uint32_t yb, uint32_t e, bool diag, const double2 *yreg,
+                                               double2 (&acc)[CPL]) {
+        const uint32_t ya = yb + (e & 0xFFFFu);
+        if (IM) {
+            // A = i B with B real: (iB)(yr + i yi) = -B yi + i B yr
+            const double v = lds1(Vs + (e >> 16));
+#pragma unroll
+            for (int c = 0; c < CPL; c++) {
+                const double2 y = diag ? yreg[c] : lds2(ya + 16 * c);
+                acc[c].x = fma(-v, y.y, acc[c].x);
+                acc[c].y = fma(v, y.x, acc[c].y);
+            }
+        } else {
+            const double2 v = lds2(Vs + (e >> 16));
+#pragma unroll
+            for (int c = 0; c < CPL; c++) {
+                const double2 y = diag ? yreg[c] : lds2(ya + 16 * c);
+                acc[c].x = fma(v.x, y.x, acc[c].x);
+                acc[c].y = fma(v.x, y.y, acc[c].y);
+                acc[c].x = fma(-v.y, y.y, acc[c].x);
+                acc[c].y = fma(v.y, y.x, acc[c].y);
+            }
+        }
+    }
+
+    static __device__ __forceinline__ void apply(const LaunchArgs &a, uint32_t Vs, uint32_t yb,
+                                                 const uint32_t (&ell)[RPL][MAXNNZ], const int (&row_of)[RPL],
                                                  const Vec &yreg, Vec &k) {
 #pragma unroll
         for (int i = 0; i < RPL; i++) {
             double2 acc[CPL];
 #pragma unroll
             for (int c = 0; c < CPL; c++) acc[c] = make_double2(0.0, 0.0);
+            if (RS) {
+                // rows come from global memory (translated on the host); rows past n read row n-1's
+                // entries with the zero slot substituted by the host-side table's padding row
+                const uint32_t *er = a.ell_packed + row_of[i];
+                const int nnz = a.g.max_nnz, stride = a.ell_rows;
+                mac(Vs, yb, __ldg(er), true, &yreg[i * CPL], acc);
+#pragma unroll 4
+                for (int j = 1; j < nnz; j++) mac(Vs, yb, __ldg(er + (size_t)j * stride), false, &yreg[i * CPL], acc);
+            } else {
+                // no per-entry branch: short rows are padded with the zero slot, so all loads of a stage can
+                // be hoisted ahead of the multiply-adds
 #pragma unroll
-            for (int j = 0; j < MAXNNZ; j++) {
-                {   // no per-entry branch: short rows are padded with the zero slot, so all loads of a
-                    // stage can be hoisted ahead of the multiply-adds
-                    const uint32_t e = ell[i][j];
-                    const uint32_t ya = yb + (e & 0xFFFFu);
-                    if (IM) {
-                        // A = i B with B real: (iB)(yr + i yi) = -B yi + i B yr
-                        const double v = lds1(Vs + (e >> 16));
-#pragma unroll
-                        for (int c = 0; c < CPL; c++) {
-                            const double2 y = j == 0 ? yreg[i * CPL + c] : lds2(ya + 16 * c);
-                            acc[c].x = fma(-v, y.y, acc[c].x);
-                            acc[c].y = fma(v, y.x, acc[c].y);
-                        }
-                    } else {
-                        const double2 v = lds2(Vs + (e >> 16));
-#pragma unroll
-                        for (int c = 0; c < CPL; c++) {
-                            const double2 y = j == 0 ? yreg[i * CPL + c] : lds2(ya + 16 * c);
-                            acc[c].x = fma(v.x, y.x, acc[c].x);
-                            acc[c].y = fma(v.x, y.y, acc[c].y);
-                            acc[c].x = fma(-v.y, y.y, acc[c].x);
-                            acc[c].y = fma(v.y, y.x, acc[c].y);
-                        }
-                    }
-                }
+                for (int j = 0; j < MAXNNZ; j++) mac(Vs, yb, ell[i][j], j == 0, &yreg[i * CPL], acc);
             }
 #pragma unroll
             for (int c = 0; c < CPL; c++) k[i * CPL + c] = acc[c];
@@ -446,12 +466,12 @@ struct Kern {
             const double dtmax = a.dtmax > 0.0 ? a.dtmax : tend - t0;
             // ---- initial step (DiffEqBase ode_determine_initdt) ----
             double acc2[2] = {0.0, 0.0};
-            for (int b = g.warp_in_team; b < a.n_batches; b += a.team_warps) {
+            for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                 const int col0 = b * g.cpb + g.colofs;
                 initial_state(a, traj, col0, row_of, row_ok, u);
                 for (int ks = 0; ks < nsave; ks++) write_out(a, traj, ks, col0, row_of, row_ok, u);
-                put_stage(u, yb0, my_off, row_ok);
-                apply(V0, yb0, ell, u, k1);
+                put_stage(a, g, u, yb0, my_off, row_ok);
+                apply(a, V0, yb0, ell, row_of, u, k1);
                 if (a.streamed) {
                     store_batch(sc_u0, n, col0, row_of, row_ok, u);
                     store_batch(sc_k0, n, col0, row_of, row_ok, k1);
@@ -470,7 +490,7 @@ struct Kern {
             dt0 = fmin(dt0, dtmax);
             compute_tables<1>(a, g, smem_gen, t0 + dt0, 0.0, false, 1);  // table 1 <- t0 + dt0 (table 0 keeps t0)
             double acc1[1] = {0.0};
-            for (int b = g.warp_in_team; b < a.n_batches; b += a.team_warps) {
+            for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                 const int col0 = b * g.cpb + g.colofs;
                 if (a.streamed) {
                     load_batch(sc_u0, n, col0, row_of, row_ok, u);
@@ -478,8 +498,8 @@ struct Kern {
                 }
 #pragma unroll
                 for (int e = 0; e < E; e++) tmp[e] = make_double2(u[e].x + dt0 * k1[e].x, u[e].y + dt0 * k1[e].y);
-                put_stage(tmp, yb1, my_off, row_ok);
-                apply(V1, yb1, ell, tmp, k2);
+                put_stage(a, g, tmp, yb1, my_off, row_ok);
+                apply(a, V1, yb1, ell, row_of, tmp, k2);
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     const double sk = a.abstol + sqrt(u[e].x * u[e].x + u[e].y * u[e].y) * a.reltol;
@@ -520,7 +540,7 @@ struct Kern {
                 }
 
                 double err[1] = {0.0};
-                for (int b = g.warp_in_team; b < a.n_batches; b += a.team_warps) {
+                for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                     const int col0 = b * g.cpb + g.colofs;
                     if (a.streamed) {
                         load_batch(sc_u0 + (size_t)(2 * cur) * sbuf, n, col0, row_of, row_ok, u);
@@ -531,16 +551,16 @@ struct Kern {
                         const double ax = A21 * k1[e].x, ay = A21 * k1[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
-                    put_stage(tmp, yb0, my_off, row_ok);
-                    apply(V0, yb0, ell, tmp, k2);
+                    put_stage(a, g, tmp, yb0, my_off, row_ok);
+                    apply(a, V0, yb0, ell, row_of, tmp, k2);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A31 * k1[e].x, ay = A31 * k1[e].y;
                         ax += A32 * k2[e].x; ay += A32 * k2[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
-                    put_stage(tmp, yb1, my_off, row_ok);
-                    apply(V1, yb1, ell, tmp, k3);
+                    put_stage(a, g, tmp, yb1, my_off, row_ok);
+                    apply(a, V1, yb1, ell, row_of, tmp, k3);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A41 * k1[e].x, ay = A41 * k1[e].y;
@@ -548,8 +568,8 @@ struct Kern {
                         ax += A43 * k3[e].x; ay += A43 * k3[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
-                    put_stage(tmp, yb0, my_off, row_ok);
-                    apply(V2, yb0, ell, tmp, k4);
+                    put_stage(a, g, tmp, yb0, my_off, row_ok);
+                    apply(a, V2, yb0, ell, row_of, tmp, k4);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A51 * k1[e].x, ay = A51 * k1[e].y;
@@ -558,8 +578,8 @@ struct Kern {
                         ax += A54 * k4[e].x; ay += A54 * k4[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
-                    put_stage(tmp, yb1, my_off, row_ok);
-                    apply(V3, yb1, ell, tmp, k5);
+                    put_stage(a, g, tmp, yb1, my_off, row_ok);
+                    apply(a, V3, yb1, ell, row_of, tmp, k5);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A61 * k1[e].x, ay = A61 * k1[e].y;
@@ -569,8 +589,8 @@ struct Kern {
                         ax += A65 * k5[e].x; ay += A65 * k5[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
-                    put_stage(tmp, yb0, my_off, row_ok);
-                    apply(V4, yb0, ell, tmp, k6);
+                    put_stage(a, g, tmp, yb0, my_off, row_ok);
+                    apply(a, V4, yb0, ell, row_of, tmp, k6);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A71 * k1[e].x, ay = A71 * k1[e].y;
@@ -581,8 +601,8 @@ struct Kern {
                         ax += A76 * k6[e].x; ay += A76 * k6[e].y;
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);  // u_new
                     }
-                    put_stage(tmp, yb1, my_off, row_ok);
-                    apply(V4, yb1, ell, tmp, k7);
+                    put_stage(a, g, tmp, yb1, my_off, row_ok);
+                    apply(a, V4, yb1, ell, row_of, tmp, k7);
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ex = BT1 * k1[e].x, ey = BT1 * k1[e].y;
@@ -628,8 +648,9 @@ struct Kern {
                     st.n_accept++;
                     lqold = e2 == 0.0 ? lq_init : fmax(le, lq_init);  // qold = max(EEst, qoldinit)
                     if (!a.streamed) {
-                        if (nsave_hi > nsave && g.warp_in_team < a.n_batches)
-                            save_points(a, traj, ts, nsave, nsave_hi, t, dt, tnew, g.warp_in_team * g.cpb + g.colofs,
+                        if (nsave_hi > nsave && (RS || g.warp_in_team < a.n_batches))
+                            save_points(a, traj, ts, nsave, nsave_hi, t, dt, tnew,
+                                        (RS ? 0 : g.warp_in_team) * g.cpb + g.colofs,
                                         row_of, row_ok, u, k1, k2, k3, k4, k5, k6, k7, tmp);
 #pragma unroll
                         for (int e = 0; e < E; e++) {
@@ -654,7 +675,7 @@ struct Kern {
             st.n_rhs = 3 + 6 * n_attempt;  // the reference also evaluates f(u0,t0) a second time
         } else {
             // zero-length span: only the start saves
-            for (int b = g.warp_in_team; b < a.n_batches; b += a.team_warps) {
+            for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                 const int col0 = b * g.cpb + g.colofs;
                 initial_state(a, traj, col0, row_of, row_ok, u);
                 for (int ks = 0; ks < nsave; ks++) write_out(a, traj, ks, col0, row_of, row_ok, u);
@@ -665,7 +686,7 @@ struct Kern {
             const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
             for (int e = 0; e < E; e++) tmp[e] = make_double2(qnan, qnan);
-            for (int b = g.warp_in_team; b < a.n_batches; b += a.team_warps)
+            for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps)
                 for (int ks = nsave; ks < a.n_ts; ks++) write_out(a, traj, ks, b * g.cpb + g.colofs, row_of, row_ok, tmp);
         }
         st.t_final = t;
@@ -677,10 +698,10 @@ struct Kern {
 // registers; 288: teams of up to 9 warps, up to 168 registers).
 // MINB: minimum resident CTAs per SM the register allocation must allow; IM: purely imaginary generator
 // (unitary evolution under a real Hamiltonian): value slots hold Im(A) only, 2 DFMA per multiply-add.
-template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM, bool RS>
 __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant__ LaunchArgs a) {
     extern __shared__ __align__(16) double smem[];
-    typedef Kern<RPL, CPL, MAXNNZ, IM> K;
+    typedef Kern<RPL, CPL, MAXNNZ, IM, RS> K;
     const int n = a.g.n;
     Geo g;
     g.lane = threadIdx.x & 31;
@@ -715,7 +736,8 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     g.sm_rev = g.sm_chan + 8u * 5 * a.ncp;
     g.sm_red = g.sm_rev + (uint32_t)sizeof(ResolvedEval) * (a.g.n_evals > 0 ? a.g.n_evals : 1);
     const uint32_t ybytes = 16u * n * a.y_row_stride;
-    g.sm_y0 = g.sm_red + 8u * (a.team_warps * 4 + 8) + g.warp_in_team * 2 * ybytes + 16u * g_idx * a.y_grp_stride;
+    g.sm_y0 = g.sm_red + 8u * (a.team_warps * 4 + 8) + (RS ? 0 : g.warp_in_team) * 2 * ybytes +
+              16u * g_idx * a.y_grp_stride;
     g.sm_y1 = g.sm_y0 + ybytes;
 
     // ---- CTA-wide constants: series tables and the dynamic slots' pair lists ----
@@ -744,15 +766,16 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     uint32_t ell[RPL][MAXNNZ];
 #pragma unroll
     for (int i = 0; i < RPL; i++) {
-        row_of[i] = row0 + 32 * i;
+        row_of[i] = row0 + 32 * i + (RS ? g.warp_in_team * 32 * RPL : 0);
         row_ok[i] = lane_active && row_of[i] < n;
         const int row_eff = row_of[i] < n ? row_of[i] : n - 1;
+        if (RS) row_of[i] = row_ok[i] ? row_of[i] : n + (row_of[i] - n) % 8;  // padding rows of the packed table
         my_off[i] = 16u * (row_eff * a.y_row_stride);
 #pragma unroll
         for (int j = 0; j < MAXNNZ; j++) {
             // rows shorter than the variant's capacity: own row, zero slot
             uint32_t e = (uint32_t)row_eff | (0xFFFFu << 16);
-            if (j < a.g.max_nnz) e = a.g.ell[(size_t)j * n + row_eff];
+            if (!RS && j < a.g.max_nnz) e = a.g.ell[(size_t)j * n + row_eff];
             // slot 0xFFFF marks a zero entry (padding, or a row without a stored diagonal)
             const uint32_t sl = (!row_ok[i] || (e >> 16) == 0xFFFFu) ? (uint32_t)a.g.n_slots : (e >> 16);
             ell[i][j] = (16u * (e & 0xFFFFu) * a.y_row_stride) | ((K::VB * sl) << 16);
@@ -780,22 +803,22 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
 // Host-side launcher for one (RPL, CPL, MAXNNZ) instantiation.
 typedef cudaError_t (*launch_fn)(const LaunchArgs &, int grid, int block, size_t smem, cudaStream_t);
 
-template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM, bool RS>
 cudaError_t launch_solver(const LaunchArgs &a, int grid, int block, size_t smem, cudaStream_t stream) {
     if (block > MAXT) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM>,
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM, RS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM><<<grid, block, smem, stream>>>(a);
+    solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM, RS><<<grid, block, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM, bool RS>
 cudaError_t occupancy_solver(int block, size_t smem, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM>,
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM, RS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM>,
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM, RS>,
                                                          block, smem);
 }
 
