@@ -382,9 +382,9 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
 }
 
 static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int imag, int rs) {
-    const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c1_t288, variants_r1c3_t128,
-                                              variants_r1c3_t288, variants_r2c1_t128, variants_r2c1_t288,
-                                              variants_r2c2_t128, variants_r2c2_t288, variants_r3c1_t128,
+    const KernelVariant *(*lists[])(int *) = {variants_r1c1_t160, variants_r1c1_t288, variants_r1c3_t160,
+                                              variants_r1c3_t288, variants_r2c1_t160, variants_r2c1_t288,
+                                              variants_r2c2_t160, variants_r2c2_t288, variants_r3c1_t160,
                                               variants_r3c1_t288, variants_rowsplit};
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
@@ -443,7 +443,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.streamed = 1;
         pl.team_warps = 9;
     }
-    pl.teams_per_cta = pl.team_warps == 1 ? 4 : 1;
+    pl.teams_per_cta = pl.team_warps == 1 ? 5 : 1;  // one-warp teams: 5 per CTA, 2 CTAs (10 warps) per SM
     if (const char *env = std::getenv("QSIM_TEAMS_PER_CTA")) {  // tuning knob (development)
         const int v = std::atoi(env);
         if (v >= 1 && v <= 15 && v * pl.team_warps * 32 <= 288) pl.teams_per_cta = v;

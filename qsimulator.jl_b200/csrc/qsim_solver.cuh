@@ -694,8 +694,8 @@ struct Kern {
     }
 };
 
-// MAXT: largest block the variant is launched with (128: one-warp teams, 4 per CTA, up to 255
-// registers; 288: teams of up to 9 warps, up to 168 registers).
+// MAXT: largest block the variant is launched with (160: one-warp teams, 5 per CTA, 2 CTAs per SM;
+// 288: teams of up to 9 warps); both end up at 168 registers.
 // MINB: minimum resident CTAs per SM the register allocation must allow; IM: purely imaginary generator
 // (unitary evolution under a real Hamiltonian): value slots hold Im(A) only, 2 DFMA per multiply-add.
 template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM, bool RS>
