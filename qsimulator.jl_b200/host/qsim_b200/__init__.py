@@ -20,3 +20,5 @@ from . import _abi
 from ._ffi import Context, Problem, QsimError, PinnedArray, default_context
 from .time_evolution import unitary_propagator, unitary_state, me_propagator, me_state
 from .sweep import shard_indices, shard_params, scatter_back, gather_results
+from .floquet import (floquet_propagator, floquet_rise_fall_propagator, choose_times_floquet,
+                      decompose_times_floquet, unique_tol)
