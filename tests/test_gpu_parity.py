@@ -279,3 +279,34 @@ def test_cfg5_three_transmon_lindblad():
         assert np.abs(vi @ s - vi).max() < 1e-5
         rp = (s @ rho0.ravel(order="F")).reshape(27, 27, order="F")
         assert np.abs(rp - rho).max() < 1e-5      # different step sequences: solver tolerance, not 1e-8
+
+
+# ---------------------------------------------------------------- BASELINE.json sizes
+def test_cfg2_full_length_subsample():
+    """cfg2 at full length (ts = 0:200, ~65.6k steps per trajectory) on 16 points spread over the 64x64 grid:
+    elementwise 1e-8 against the oracle at every one of the 201 save points, identical step counts."""
+    cqs, params, ts, _ = W.config("cfg2")
+    pr = params[np.linspace(0, len(params) - 1, 16).astype(int)]
+    got, st, err = check_parity(cqs, "unitary_propagator", ts, pr)
+    assert st["n_accept"].min() > 60000
+    print(f"cfg2 full length: max rel err {err:.2e}, steps {st['n_accept'].min()}..{st['n_accept'].max()}")
+
+
+def test_cfg2_full_sweep_properties():
+    """The whole 4096-point sweep at full length: size-independent properties (no oracle at this size):
+    every trajectory succeeds, start save is the identity, the propagators are unitary to the reference
+    tolerances' own error, and a sharded run (2 x 2048, block-cyclic) is bitwise identical."""
+    from qsim_b200 import shard_params
+    cqs, params, ts, _ = W.config("cfg2")
+    ts2 = np.array([0.0, 100.0, 200.0])
+    P = Problem(cqs)
+    full, st = P.solve("unitary_propagator", ts2, params=params)
+    assert np.all(st["retcode"] == 0) and np.all(st["t_final"] == 200.0)
+    assert np.array_equal(full[:, 0], np.broadcast_to(np.eye(9), (len(params), 9, 9)))
+    u = full[:, -1]
+    unit = np.abs(np.einsum("tji,tjk->tik", u.conj(), u) - np.eye(9)).max()
+    assert unit < 5e-3
+    for rank in range(2):
+        loc, idx = shard_params(params, 2, rank)
+        part, _ = P.solve("unitary_propagator", ts2, params=loc)
+        assert np.array_equal(part, full[idx])
