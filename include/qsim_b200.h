@@ -151,7 +151,12 @@ typedef struct {
 enum {
     /* params/ts/init/out/stats are DEVICE pointers on the ctx's device; the
      * call enqueues on the stream and returns without synchronising.          */
-    QSIM_FLAG_DEVICE_PTRS = 1
+    QSIM_FLAG_DEVICE_PTRS = 1,
+    /* Evaluate the drive descriptors directly at every stage time.  By default the kernels build
+     * windowed Chebyshev interpolants of the drive channels (12 nodes over a few tens of steps, checked
+     * against direct evaluation to 2e-14 relative, shrunk or abandoned per trajectory if the check
+     * fails) and evaluate those at the stage times.                                                  */
+    QSIM_FLAG_DIRECT_DRIVES = 2
 };
 
 typedef struct {

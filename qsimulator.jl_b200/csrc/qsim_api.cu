@@ -61,6 +61,7 @@ struct qsim_ctx {
     cudaStream_t stream = nullptr;
     cudaDeviceProp prop;
     SeriesTables *d_tab = nullptr;
+    double *d_cheb = nullptr;  // Chebyshev transform / nodes / check points for the drive windows
     unsigned long long *d_counter = nullptr;
     DevBuf params, ts, init, out, stats, scratch;
     int64_t launches = 0;
@@ -122,6 +123,21 @@ int qsim_create(int device, qsim_ctx **out) {
     CU(cudaMalloc(&c->d_tab, sizeof(SeriesTables)));
     CU(cudaMemcpy(c->d_tab, &series_tables(), sizeof(SeriesTables), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
+    {
+        // c_k = sum_j T[k][j] f(x_j), x_j = cos(pi (j + 1/2) / N): p(x) = sum_k c_k T_k(x)
+        const int N = QSIM_NN;
+        std::vector<double> cheb((size_t)N * N + N + 3);
+        const double pi = 3.14159265358979323846;
+        for (int k = 0; k < N; k++)
+            for (int j = 0; j < N; j++)
+                cheb[(size_t)k * N + j] = (k == 0 ? 1.0 : 2.0) / N * std::cos(pi * k * (j + 0.5) / N);
+        for (int j = 0; j < N; j++) cheb[(size_t)N * N + j] = std::cos(pi * (j + 0.5) / N);
+        cheb[(size_t)N * N + N + 0] = -0.85;
+        cheb[(size_t)N * N + N + 1] = 0.1;
+        cheb[(size_t)N * N + N + 2] = 0.92;
+        CU(cudaMalloc(&c->d_cheb, sizeof(double) * cheb.size()));
+        CU(cudaMemcpy(c->d_cheb, cheb.data(), sizeof(double) * cheb.size(), cudaMemcpyHostToDevice));
+    }
     *out = c;
     return QSIM_OK;
 }
@@ -132,6 +148,7 @@ int qsim_destroy(qsim_ctx *c) {
     cudaStreamSynchronize(c->stream);
     c->params.release(); c->ts.release(); c->init.release(); c->out.release(); c->stats.release(); c->scratch.release();
     cudaFree(c->d_tab);
+    cudaFree(c->d_cheb);
     cudaFree(c->d_counter);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -479,8 +496,8 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     pl.ncp = (g.n_chan + 1) & ~1;
     pl.n_dyn_pairs = g.slot_ptr[g.n_dyn_slots];
     const int n_ev = std::max<int>((int)g.evals.size(), 1);
-    pl.common_bytes = 512 + ((4 * (g.n_dyn_slots + 1 + pl.n_dyn_pairs) + 15) & ~15) + 16 * std::max(pl.n_dyn_pairs, 1);
-    pl.team_bytes = (((g.imag_only ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 8 * (pl.team_warps * 4 + 8) +
+    pl.common_bytes = 512 + 1280 + ((4 * (g.n_dyn_slots + 1 + pl.n_dyn_pairs) + 15) & ~15) + 16 * std::max(pl.n_dyn_pairs, 1);
+    pl.team_bytes = (((g.imag_only ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
                     (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride;
     pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
     pl.scratch_per_team = pl.streamed ? (size_t)4 * pl.n_batches * cpb * n * sizeof(double2) : 0;
@@ -653,6 +670,17 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.g.pair_w = dc->pair_w;
     a.g.evals = dc->evals;
     a.g.tab = c->d_tab;
+    a.cheb = c->d_cheb;
+    a.dyn_chan_mask = 0;
+    bool any_dyn = false;
+    for (const auto &e : g.evals)
+        if (e.dynamic) {
+            any_dyn = true;
+            const int n_out = eval_outputs(e.kind);
+            for (int q = 0; q < n_out; q++)
+                if (e.out_chan + q < 32) a.dyn_chan_mask |= 1u << (e.out_chan + q);
+        }
+    a.use_windows = (any_dyn && g.n_chan <= 32 && !(o.flags & QSIM_FLAG_DIRECT_DRIVES)) ? 1 : 0;
     a.ell_packed = dc->ell_packed;
     a.ell_rows = g.n + 8;
     a.ncols = pl.ncols;

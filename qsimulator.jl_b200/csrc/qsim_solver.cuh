@@ -65,7 +65,10 @@ struct LaunchArgs {
     int team_warps, teams_per_cta, n_batches, groups, streamed;
     int y_row_stride, y_grp_stride;  // stage-buffer layout in 16-byte units (chosen on the host to avoid bank conflicts)
     int nvp, ncp;         // padded slot / channel counts (nvp > n_slots: slot n_slots is the zero slot)
-    int common_bytes;     // CTA-wide shared region (series tables + dynamic pair lists)
+    int common_bytes;     // CTA-wide shared region (series tables + Chebyshev block + dynamic pair lists)
+    const double *cheb;   // [NN*NN] coefficient transform, [NN] nodes, [3] check points (NN = 12)
+    unsigned dyn_chan_mask;  // channels produced by time-dependent evaluators
+    int use_windows;      // 1: drive channels through windowed Chebyshev interpolants (see build_window)
     int team_bytes;       // shared bytes per team
     double reltol, abstol, gamma, qmin, qmax, beta1, beta2, qoldinit, dtmax;
     long long maxiters;
@@ -171,13 +174,29 @@ __device__ __forceinline__ void team_sum(double (&v)[NV], uint32_t red, int team
     team_sync(team_warps, bar_id);
 }
 
+// Deterministic team-wide maximum.
+__device__ __forceinline__ double team_max(double v, uint32_t red, int team_warps, int warp_in_team, int lane, int bar_id) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (team_warps == 1) return v;
+    if (lane == 0) sts1(red + 8 * warp_in_team, v);
+    team_sync(team_warps, bar_id);
+    double m = lds1(red);
+    for (int w = 1; w < team_warps; w++) m = fmax(m, lds1(red + 8 * w));
+    team_sync(team_warps, bar_id);
+    return m;
+}
+
+#define QSIM_NN 12             // Chebyshev nodes per drive window
+#define QSIM_WIN_TOL 2e-14     // accepted interpolation error relative to the channel's magnitude
+
 // Per-thread geometry (all scalars; arrays are kept separately so they stay in registers).
 struct Geo {
     int lane, warp_in_team, team_thread, team_threads, bar_id;
     int cpb, colofs;
     // shared-memory byte addresses
-    uint32_t sm_tab, sm_dptr, sm_dchan, sm_dw;  // CTA-wide: series tables, dynamic pair lists
-    uint32_t sm_V, sm_chan, sm_rev, sm_red;     // team
+    uint32_t sm_tab, sm_cheb, sm_dptr, sm_dchan, sm_dw;  // CTA-wide: series tables, Chebyshev block, dynamic pair lists
+    uint32_t sm_V, sm_chan, sm_rev, sm_win, sm_red;  // team (sm_win: per channel 12 nodes, 3 checks, 12 coefficients)
     uint32_t sm_y0, sm_y1;                      // this warp's two stage buffers (+ column offset)
     uint32_t v_stride;                          // bytes between value tables
 };
@@ -201,20 +220,101 @@ struct Kern {
     // Refresh tables table0 + s, s < NTAB, for the times tbase + kStageC[s]*dtv.  all == false: only
     // the time-dependent channels and slots (pair lists in shared memory); all == true: everything
     // (pair lists from global memory; once per trajectory).  Two team barriers.
-    template <int NTAB>
-    static __device__ __forceinline__ void compute_tables(const LaunchArgs &a, const Geo &g, const double *smem_gen,
-                                                           double tbase, double dtv, bool all, int table0) {
+    static __device__ __forceinline__ void load_resolved(uint32_t addr, ResolvedEval &r) {
+        union {
+            ResolvedEval r;
+            double2 q[9];
+        } ld;
+#pragma unroll
+        for (int i = 0; i < 9; i++) ld.q[i] = lds2(addr + 16 * i);
+        r = ld.r;
+    }
+
+    // Chebyshev series sum_k c_k T_k(x) by Clenshaw's recurrence; coefficients in shared memory.
+    static __device__ __forceinline__ double clenshaw(uint32_t coef, double x) {
+        const double tx = 2.0 * x;
+        double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+        for (int k = QSIM_NN - 1; k >= 1; k--) {
+            const double b0 = fma(tx, b1, lds1(coef + 8 * k)) - b2;
+            b2 = b1;
+            b1 = b0;
+        }
+        return fma(x, b1, lds1(coef)) - b2;
+    }
+
+    // Drive window: evaluate every time-dependent channel at the 12 Chebyshev nodes of [Tw, Tw+W]
+    // (one SIMT pass, a lane per node) plus 3 check points, turn the node values into Chebyshev
+    // coefficients, and return the interpolant's worst error at the check points relative to the
+    // channel's magnitude.  Stage times inside the window then cost a 12-term recurrence instead of
+    // the sin/cos/sqrt/Horner chain; the caller shrinks the window until the check passes or falls
+    // back to direct evaluation, so the interpolant is only used where it is exact to rounding.
+    static __device__ __forceinline__ double build_window(const LaunchArgs &a, const Geo &g, const double *smem_gen,
+                                                         double Tw, double W) {
         const int ne = a.g.n_evals;
         const SeriesTables *tab = reinterpret_cast<const SeriesTables *>(smem_gen);
+        for (int it = g.team_thread; it < (QSIM_NN + 3) * ne; it += g.team_threads) {
+            const int j = it % (QSIM_NN + 3), e = it / (QSIM_NN + 3);
+            ResolvedEval r;
+            load_resolved(g.sm_rev + (uint32_t)sizeof(ResolvedEval) * e, r);
+            if (r.dynamic) {
+                const double x = lds1(g.sm_cheb + 8 * (QSIM_NN * QSIM_NN + j));
+                double o0, o1;
+                run_resolved(r, tab->freq, tab->anh, Tw + 0.5 * W * (1.0 + x), &o0, &o1);
+                sts1(g.sm_win + 256u * r.out_chan + 8 * j, o0);
+                if (eval_outputs(r.kind) == 2) sts1(g.sm_win + 256u * (r.out_chan + 1) + 8 * j, o1);
+            }
+        }
+        team_sync(a.team_warps, g.bar_id);
+        for (int it = g.team_thread; it < QSIM_NN * a.g.n_chan; it += g.team_threads) {
+            const int k = it % QSIM_NN, ch = it / QSIM_NN;
+            if ((a.dyn_chan_mask >> ch) & 1u) {
+                double c = 0.0;
+#pragma unroll
+                for (int j = 0; j < QSIM_NN; j++)
+                    c = fma(lds1(g.sm_cheb + 8 * (k * QSIM_NN + j)), lds1(g.sm_win + 256u * ch + 8 * j), c);
+                sts1(g.sm_win + 256u * ch + 128 + 8 * k, c);
+            }
+        }
+        team_sync(a.team_warps, g.bar_id);
+        double bad = 0.0;
+        for (int it = g.team_thread; it < 3 * a.g.n_chan; it += g.team_threads) {
+            const int i = it % 3, ch = it / 3;
+            if ((a.dyn_chan_mask >> ch) & 1u) {
+                const double x = lds1(g.sm_cheb + 8 * (QSIM_NN * QSIM_NN + QSIM_NN + i));
+                const double p = clenshaw(g.sm_win + 256u * ch + 128, x);
+                const double f = lds1(g.sm_win + 256u * ch + 8 * (QSIM_NN + i));
+                double scale = 0.0;
+#pragma unroll
+                for (int j = 0; j < QSIM_NN; j++) scale = fmax(scale, fabs(lds1(g.sm_win + 256u * ch + 8 * j)));
+                const double err = fabs(p - f) / (scale > 0.0 ? scale : 1.0);
+                bad = fmax(bad, err == err ? err : 1.0);  // NaN counts as failure
+            }
+        }
+        return team_max(bad, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
+    }
+
+    template <int NTAB>
+    static __device__ __forceinline__ void compute_tables(const LaunchArgs &a, const Geo &g, const double *smem_gen,
+                                                           double tbase, double dtv, bool all, int table0,
+                                                           bool use_win = false, double win_t = 0.0, double win_w = 1.0) {
+        const int ne = a.g.n_evals;
+        const SeriesTables *tab = reinterpret_cast<const SeriesTables *>(smem_gen);
+        if (use_win) {
+            // stage times inside the current drive window: Chebyshev interpolants
+            const double sc = 2.0 / win_w;
+            for (int it = g.team_thread; it < NTAB * a.g.n_chan; it += g.team_threads) {
+                const int s = it % NTAB, ch = it / NTAB;
+                if ((a.dyn_chan_mask >> ch) & 1u) {
+                    const double x = fma((tbase + kStageC[s] * dtv) - win_t, sc, -1.0);
+                    sts1(g.sm_chan + 8u * ((table0 + s) * a.ncp + ch), clenshaw(g.sm_win + 256u * ch + 128, x));
+                }
+            }
+        } else
         for (int it = g.team_thread; it < NTAB * ne; it += g.team_threads) {
             const int s = it % NTAB, e = it / NTAB;
-            union {
-                ResolvedEval r;
-                double2 q[9];
-            } ld;
-#pragma unroll
-            for (int i = 0; i < 9; i++) ld.q[i] = lds2(g.sm_rev + (uint32_t)sizeof(ResolvedEval) * e + 16 * i);
-            const ResolvedEval &r = ld.r;
+            ResolvedEval r;
+            load_resolved(g.sm_rev + (uint32_t)sizeof(ResolvedEval) * e, r);
             if (all || r.dynamic) {
                 double o0, o1;
                 run_resolved(r, tab->freq, tab->anh, tbase + kStageC[s] * dtv, &o0, &o1);
@@ -520,12 +620,33 @@ struct Kern {
             const double inv_ntot = 1.0 / ntot;
             long long iters = 0;
             int n_attempt = 0;
+            int win_state = a.use_windows ? 0 : -1;  // -1 direct evaluation, 0 no window yet, 1 window valid
+            double win_t = 0.0, win_w = 1.0, win_next = 0.0;
             while (t < tend) {
                 if (++iters > a.maxiters) { st.retcode = QSIM_RET_MAXITERS; break; }
                 dt = fmin(dt, dtmax);
                 dt = fmin(dt, tend - t);
                 if (!(dt > fabs(t) * 2.220446049250313e-16)) { st.retcode = QSIM_RET_DT_UNDERFLOW; break; }
-                compute_tables<5>(a, g, smem_gen, t, dt, false, 0);
+                if (win_state >= 0 && (win_state == 0 || t + dt > win_t + win_w)) {
+                    // (re)build the drive window starting at this step; shrink until the check passes
+                    double wt = fmax(win_state == 0 ? 6.0 * dt : win_next, 1.25 * dt);
+                    for (;;) {
+                        const double werr = build_window(a, g, smem_gen, t, wt);
+                        if (werr <= QSIM_WIN_TOL) {
+                            win_t = t;
+                            win_w = wt;
+                            win_state = 1;
+                            win_next = werr <= QSIM_WIN_TOL / 64.0 ? fmin(1.5 * wt, 128.0 * dt) : wt;
+                            break;
+                        }
+                        if (wt <= 1.3 * dt) {  // not even one step fits: evaluate this trajectory's drives directly
+                            win_state = -1;
+                            break;
+                        }
+                        wt = fmax(0.5 * wt, 1.25 * dt);
+                    }
+                }
+                compute_tables<5>(a, g, smem_gen, t, dt, false, 0, win_state == 1, win_t, win_w);
                 QSIM_LAUNDER_ELL();
                 double tnew = t + dt;
                 {
@@ -726,7 +847,8 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     // ---- shared memory map (byte addresses) ----
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     g.sm_tab = sbase;
-    g.sm_dptr = sbase + 512;                             // int[n_dyn_slots + 1]
+    g.sm_cheb = sbase + 512;                             // double[NN*NN + NN + 3] (1280 bytes reserved)
+    g.sm_dptr = sbase + 512 + 1280;                      // int[n_dyn_slots + 1]
     g.sm_dchan = g.sm_dptr + 4 * (a.g.n_dyn_slots + 1);  // int[n_dyn_pairs]
     g.sm_dw = sbase + a.common_bytes - 16 * (a.g.n_dyn_pairs > 0 ? a.g.n_dyn_pairs : 1);  // double2[n_dyn_pairs]
     const uint32_t tbase = sbase + a.common_bytes + team_in_cta * a.team_bytes;
@@ -734,7 +856,8 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     g.sm_V = tbase;
     g.sm_chan = g.sm_V + ((5 * g.v_stride + 15u) & ~15u);
     g.sm_rev = g.sm_chan + 8u * 5 * a.ncp;
-    g.sm_red = g.sm_rev + (uint32_t)sizeof(ResolvedEval) * (a.g.n_evals > 0 ? a.g.n_evals : 1);
+    g.sm_win = g.sm_rev + (uint32_t)sizeof(ResolvedEval) * (a.g.n_evals > 0 ? a.g.n_evals : 1);
+    g.sm_red = g.sm_win + 256u * a.ncp;
     const uint32_t ybytes = 16u * n * a.y_row_stride;
     g.sm_y0 = g.sm_red + 8u * (a.team_warps * 4 + 8) + (RS ? 0 : g.warp_in_team) * 2 * ybytes +
               16u * g_idx * a.y_grp_stride;
@@ -744,7 +867,8 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     {
         const double *src = reinterpret_cast<const double *>(a.g.tab);
         for (int i = threadIdx.x; i < (int)(sizeof(SeriesTables) / 8); i += blockDim.x) sts1(g.sm_tab + 8 * i, src[i]);
-        int *dptr = reinterpret_cast<int *>(smem) + 128;
+        for (int i = threadIdx.x; i < QSIM_NN * QSIM_NN + QSIM_NN + 3; i += blockDim.x) sts1(g.sm_cheb + 8 * i, a.cheb[i]);
+        int *dptr = reinterpret_cast<int *>(smem) + (512 + 1280) / 4;
         for (int i = threadIdx.x; i <= a.g.n_dyn_slots; i += blockDim.x) dptr[i] = a.g.slot_ptr[i];
         for (int i = threadIdx.x; i < a.g.n_dyn_pairs; i += blockDim.x) {
             dptr[a.g.n_dyn_slots + 1 + i] = a.g.pair_chan[i];

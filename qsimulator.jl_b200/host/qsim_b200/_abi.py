@@ -13,6 +13,7 @@ ABI_VERSION = 1
 OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_ALLOC = 0, -1, -2, -3, -4, -5, -6
 RET_SUCCESS, RET_MAXITERS, RET_DT_UNDERFLOW, RET_NONFINITE = 0, 1, 2, 3
 FLAG_DEVICE_PTRS = 1
+FLAG_DIRECT_DRIVES = 2
 
 
 class Slot(C.Structure):

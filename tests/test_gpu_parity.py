@@ -310,3 +310,29 @@ def test_cfg2_full_sweep_properties():
         loc, idx = shard_params(params, 2, rank)
         part, _ = P.solve("unitary_propagator", ts2, params=loc)
         assert np.array_equal(part, full[idx])
+
+
+def test_drive_windows_vs_direct_evaluation():
+    """The windowed Chebyshev drive interpolants (default) and direct evaluation of the drive descriptors at
+    every stage time (QSIM_FLAG_DIRECT_DRIVES) must both meet the parity bar, take the same steps and agree
+    with each other far below it -- including a 5 GHz lab-frame dipole, where windows span under one period."""
+    direct = _abi.default_opts(flags=_abi.FLAG_DIRECT_DRIVES)
+    cqs, params, _, _ = W.config("cfg2")
+    pr = params[[7, 2222, 4000]]
+    ts = np.arange(0.0, 31.0)
+    a, sa, _ = check_parity(cqs, "unitary_propagator", ts, pr)
+    b, sb, _ = check_parity(cqs, "unitary_propagator", ts, pr, opts=direct)
+    assert np.array_equal(sa["n_accept"], sb["n_accept"]) and np.array_equal(sa["n_reject"], sb["n_reject"])
+    assert max_rel_err(a, b) < 1e-10
+    q0 = DuffingTransmon("q0", 3, DuffingSpec(5.0, -0.2))
+    rabi = CompositeQSystem([q0])
+    add_hamiltonian(rabi, q0)
+    add_hamiltonian(rabi, dipole_drive(q0, Cos(amp=0.02, freq=5.0).gaussian(10.0, 4.0), 4.9), q0)
+    ts = np.linspace(0.0, 20.0, 21)
+    a, _, _ = check_parity(rabi, "unitary_propagator", ts)
+    b, _, _ = check_parity(rabi, "unitary_propagator", ts, opts=direct)
+    assert max_rel_err(a, b) < 1e-10
+    cqs4, p4, _, _ = W.config("cfg4")
+    a, _, _ = check_parity(cqs4, "me_propagator", np.array([0.0, 2.0]), p4[[5, 8000]])
+    b, _, _ = check_parity(cqs4, "me_propagator", np.array([0.0, 2.0]), p4[[5, 8000]], opts=direct)
+    assert max_rel_err(a, b) < 1e-10
