@@ -74,11 +74,14 @@ struct qsim_problem::DeviceCopy {
     int32_t *slot_ptr = nullptr, *pair_chan = nullptr;
     double2 *pair_w = nullptr;
     EvalDesc *evals = nullptr;
+    double *dyn_rec = nullptr;       // 64-byte records of the time-dependent slots
     uint32_t *ell_packed = nullptr;  // row-split kernels
     int packed_stride = -1;
     void free_all() {
         cudaFree(ell_packed);
         ell_packed = nullptr;
+        cudaFree(dyn_rec);
+        dyn_rec = nullptr;
         cudaFree(ell); cudaFree(row_len); cudaFree(slot_ptr); cudaFree(pair_chan); cudaFree(pair_w); cudaFree(evals);
         ell = nullptr; row_len = nullptr; slot_ptr = nullptr; pair_chan = nullptr; pair_w = nullptr; evals = nullptr;
     }
@@ -347,6 +350,7 @@ struct Plan {
     int groups = 1, n_batches = 1, team_warps = 1, teams_per_cta = 1, streamed = 0;
     int block = 32, grid = 1, nvp = 0, ncp = 0, common_bytes = 0, team_bytes = 0, n_dyn_pairs = 0;
     int y_row_stride = 1, y_grp_stride = 1, rowsplit = 0;
+    int off_dptr = 0, off_dw = 0, off_drec = 0, dyn_fast = 0;
     size_t smem = 0, scratch_per_team = 0;
 };
 
@@ -496,7 +500,14 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     pl.ncp = (g.n_chan + 1) & ~1;
     pl.n_dyn_pairs = g.slot_ptr[g.n_dyn_slots];
     const int n_ev = std::max<int>((int)g.evals.size(), 1);
-    pl.common_bytes = 512 + 1280 + ((4 * (g.n_dyn_slots + 1 + pl.n_dyn_pairs) + 15) & ~15) + 16 * std::max(pl.n_dyn_pairs, 1);
+    // common shared region: series tables | Chebyshev block | controller power tables | dynamic pair lists | records
+    pl.off_dptr = 512 + 1280 + 8 * (QSIM_POW_K * 32 + 2 * QSIM_POW_NE);
+    pl.off_dw = pl.off_dptr + ((4 * (g.n_dyn_slots + 1 + pl.n_dyn_pairs) + 15) & ~15);
+    pl.off_drec = pl.off_dw + 16 * std::max(pl.n_dyn_pairs, 1);
+    pl.dyn_fast = 1;
+    for (int sl = 0; sl < g.n_dyn_slots; sl++)
+        if (g.slot_ptr[sl + 1] - g.slot_ptr[sl] > 3) pl.dyn_fast = 0;
+    pl.common_bytes = pl.off_drec + (pl.dyn_fast ? 64 * std::max(g.n_dyn_slots, 1) : 16);
     pl.team_bytes = (((g.imag_only ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
                     (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride;
     pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
@@ -553,6 +564,21 @@ static int ensure_device_copy(qsim_ctx *c, qsim_problem *p, int w) {
     CU(upload(&dc->pair_chan, g.pair_chan));
     CU(upload(&dc->pair_w, w2));
     CU(upload(&dc->evals, g.evals));
+    {
+        // {w0, w1, w2 (re, im), ch0, ch1, ch2, pad}: unused pairs carry weight 0 on the constant channel
+        std::vector<double> rec((size_t)8 * std::max(g.n_dyn_slots, 1), 0.0);
+        for (int sl = 0; sl < g.n_dyn_slots; sl++) {
+            int32_t ch[4] = {0, 0, 0, 0};
+            const int np = std::min(3, g.slot_ptr[sl + 1] - g.slot_ptr[sl]);
+            for (int q = 0; q < np; q++) {
+                rec[(size_t)8 * sl + 2 * q] = g.pair_w[g.slot_ptr[sl] + q].real();
+                rec[(size_t)8 * sl + 2 * q + 1] = g.pair_w[g.slot_ptr[sl] + q].imag();
+                ch[q] = g.pair_chan[g.slot_ptr[sl] + q];
+            }
+            std::memcpy(&rec[(size_t)8 * sl + 6], ch, sizeof(ch));
+        }
+        CU(upload(&dc->dyn_rec, rec));
+    }
     p->dev[w] = dc;
     return QSIM_OK;
 }
@@ -701,6 +727,11 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.nvp = pl.nvp;
     a.ncp = pl.ncp;
     a.common_bytes = pl.common_bytes;
+    a.off_dptr = pl.off_dptr;
+    a.off_dw = pl.off_dw;
+    a.off_drec = pl.off_drec;
+    a.dyn_fast = pl.dyn_fast;
+    a.dyn_rec = dc->dyn_rec;
     a.team_bytes = pl.team_bytes;
     a.reltol = o.reltol; a.abstol = o.abstol; a.gamma = o.gamma; a.qmin = o.qmin; a.qmax = o.qmax;
     a.beta1 = o.beta1; a.beta2 = o.beta2; a.qoldinit = o.qoldinit; a.dtmax = o.dtmax;

@@ -69,6 +69,9 @@ struct LaunchArgs {
     const double *cheb;   // [NN*NN] coefficient transform, [NN] nodes, [3] check points (NN = 12)
     unsigned dyn_chan_mask;  // channels produced by time-dependent evaluators
     int use_windows;      // 1: drive channels through windowed Chebyshev interpolants (see build_window)
+    int dyn_fast;         // 1: every time-dependent slot has <= 3 pairs (64-byte records)
+    int off_dptr, off_dw, off_drec;  // byte offsets inside the common region (after tables, Chebyshev, power tables)
+    const double *dyn_rec;           // [n_dyn_slots][8] records {w0, w1, w2 (double2), ch0, ch1, ch2, pad (int)}
     int team_bytes;       // shared bytes per team
     double reltol, abstol, gamma, qmin, qmax, beta1, beta2, qoldinit, dtmax;
     long long maxiters;
@@ -187,6 +190,9 @@ __device__ __forceinline__ double team_max(double v, uint32_t red, int team_warp
     return m;
 }
 
+#define QSIM_POW_EMIN (-80)     // controller power tables cover EEst^2 in [2^-80, 2^48)
+#define QSIM_POW_NE 128
+#define QSIM_POW_K 10          // Taylor coefficients per mantissa sub-interval (16 sub-intervals of [1,2))
 #define QSIM_NN 12             // Chebyshev nodes per drive window
 #define QSIM_WIN_TOL 2e-14     // accepted interpolation error relative to the channel's magnitude
 
@@ -195,7 +201,8 @@ struct Geo {
     int lane, warp_in_team, team_thread, team_threads, bar_id;
     int cpb, colofs;
     // shared-memory byte addresses
-    uint32_t sm_tab, sm_cheb, sm_dptr, sm_dchan, sm_dw;  // CTA-wide: series tables, Chebyshev block, dynamic pair lists
+    uint32_t sm_tab, sm_cheb, sm_pow, sm_dptr, sm_dchan, sm_dw, sm_drec;  // CTA-wide: series tables, Chebyshev block,
+                                                                          // controller power tables, dynamic pair lists / records
     uint32_t sm_V, sm_chan, sm_rev, sm_win, sm_red;  // team (sm_win: per channel 12 nodes, 3 checks, 12 coefficients)
     uint32_t sm_y0, sm_y1;                      // this warp's two stage buffers (+ column offset)
     uint32_t v_stride;                          // bytes between value tables
@@ -220,6 +227,29 @@ struct Kern {
     // Refresh tables table0 + s, s < NTAB, for the times tbase + kStageC[s]*dtv.  all == false: only
     // the time-dependent channels and slots (pair lists in shared memory); all == true: everything
     // (pair lists from global memory; once per trajectory).  Two team barriers.
+    // x^(-beta1/2) and x^(beta2/2) for x = EEst^2: split x = m 2^E, a degree-9 Taylor polynomial of m^p about the
+    // centre of m's sub-interval (16 per octave; remainder < 1e-17 relative) times a tabulated 2^(pE).  Replaces a
+    // log and an exp on the per-step critical path; false outside the tabulated exponent range (0, inf, nan too).
+    static __device__ __forceinline__ bool pow_pair(const Geo &g, double x, double &ra, double &rb) {
+        const long long b = __double_as_longlong(x);
+        const int ex = (int)((b >> 52) & 0x7ff) - 1023;
+        if (b < 0 || ex < QSIM_POW_EMIN || ex >= QSIM_POW_EMIN + QSIM_POW_NE) return false;
+        const int idx = (int)((b >> 48) & 15);
+        const double m = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+        const double t = m - (1.03125 + 0.0625 * idx);
+        const uint32_t pa = g.sm_pow + 8u * QSIM_POW_K * idx, pb = pa + 8u * QSIM_POW_K * 16;
+        double qa = lds1(pa + 8 * (QSIM_POW_K - 1)), qb = lds1(pb + 8 * (QSIM_POW_K - 1));
+#pragma unroll
+        for (int k = QSIM_POW_K - 2; k >= 0; k--) {
+            qa = fma(qa, t, lds1(pa + 8 * k));
+            qb = fma(qb, t, lds1(pb + 8 * k));
+        }
+        const uint32_t te = g.sm_pow + 8u * QSIM_POW_K * 32 + 8u * (ex - QSIM_POW_EMIN);
+        ra = qa * lds1(te);
+        rb = qb * lds1(te + 8u * QSIM_POW_NE);
+        return true;
+    }
+
     static __device__ __forceinline__ void load_resolved(uint32_t addr, ResolvedEval &r) {
         union {
             ResolvedEval r;
@@ -230,17 +260,23 @@ struct Kern {
         r = ld.r;
     }
 
-    // Chebyshev series sum_k c_k T_k(x) by Clenshaw's recurrence; coefficients in shared memory.
-    static __device__ __forceinline__ double clenshaw(uint32_t coef, double x) {
+    // Chebyshev polynomials T_0..T_{NN-1} at x (three-term recurrence: one dependent FMA per degree).
+    static __device__ __forceinline__ void cheb_basis(double x, double (&T)[QSIM_NN]) {
         const double tx = 2.0 * x;
-        double b1 = 0.0, b2 = 0.0;
+        T[0] = 1.0;
+        T[1] = x;
 #pragma unroll
-        for (int k = QSIM_NN - 1; k >= 1; k--) {
-            const double b0 = fma(tx, b1, lds1(coef + 8 * k)) - b2;
-            b2 = b1;
-            b1 = b0;
+        for (int k = 2; k < QSIM_NN; k++) T[k] = fma(tx, T[k - 1], -T[k - 2]);
+    }
+    // sum_k c_k T_k with the coefficients in shared memory; two partial sums for instruction-level parallelism
+    static __device__ __forceinline__ double cheb_dot(uint32_t coef, const double (&T)[QSIM_NN]) {
+        double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < QSIM_NN; k += 2) {
+            p0 = fma(lds1(coef + 8 * k), T[k], p0);
+            p1 = fma(lds1(coef + 8 * (k + 1)), T[k + 1], p1);
         }
-        return fma(x, b1, lds1(coef)) - b2;
+        return p0 + p1;
     }
 
     // Drive window: evaluate every time-dependent channel at the 12 Chebyshev nodes of [Tw, Tw+W]
@@ -282,7 +318,9 @@ struct Kern {
             const int i = it % 3, ch = it / 3;
             if ((a.dyn_chan_mask >> ch) & 1u) {
                 const double x = lds1(g.sm_cheb + 8 * (QSIM_NN * QSIM_NN + QSIM_NN + i));
-                const double p = clenshaw(g.sm_win + 256u * ch + 128, x);
+                double T[QSIM_NN];
+                cheb_basis(x, T);
+                const double p = cheb_dot(g.sm_win + 256u * ch + 128, T);
                 const double f = lds1(g.sm_win + 256u * ch + 8 * (QSIM_NN + i));
                 double scale = 0.0;
 #pragma unroll
@@ -302,12 +340,14 @@ struct Kern {
         const SeriesTables *tab = reinterpret_cast<const SeriesTables *>(smem_gen);
         if (use_win) {
             // stage times inside the current drive window: Chebyshev interpolants
+            // one lane per stage time: the Chebyshev basis is shared by all channels
             const double sc = 2.0 / win_w;
-            for (int it = g.team_thread; it < NTAB * a.g.n_chan; it += g.team_threads) {
-                const int s = it % NTAB, ch = it / NTAB;
-                if ((a.dyn_chan_mask >> ch) & 1u) {
-                    const double x = fma((tbase + kStageC[s] * dtv) - win_t, sc, -1.0);
-                    sts1(g.sm_chan + 8u * ((table0 + s) * a.ncp + ch), clenshaw(g.sm_win + 256u * ch + 128, x));
+            for (int s = g.team_thread; s < NTAB; s += g.team_threads) {
+                double T[QSIM_NN];
+                cheb_basis(fma((tbase + kStageC[s] * dtv) - win_t, sc, -1.0), T);
+                for (unsigned m = a.dyn_chan_mask; m; m &= m - 1) {
+                    const int ch = __ffs(m) - 1;
+                    sts1(g.sm_chan + 8u * ((table0 + s) * a.ncp + ch), cheb_dot(g.sm_win + 256u * ch + 128, T));
                 }
             }
         } else
@@ -326,6 +366,25 @@ struct Kern {
         team_sync(a.team_warps, g.bar_id);
         if (!all) {
             const int nsl = a.g.n_dyn_slots;
+            if (a.dyn_fast) {
+                // every time-dependent slot has at most 3 (channel, weight) pairs: fixed 64-byte records,
+                // no dependent index loads
+                for (int it = g.team_thread; it < NTAB * nsl; it += g.team_threads) {
+                    const int s = it % NTAB, sl = it / NTAB;
+                    const uint32_t ch = g.sm_chan + 8u * ((table0 + s) * a.ncp);
+                    const uint32_t rec = g.sm_drec + 64u * sl;
+                    const double2 w0 = lds2(rec), w1 = lds2(rec + 16), w2 = lds2(rec + 32);
+                    const double c0 = lds1(ch + 8u * ldsi(rec + 48)), c1 = lds1(ch + 8u * ldsi(rec + 52)),
+                                 c2 = lds1(ch + 8u * ldsi(rec + 56));
+                    const double vy = fma(w2.y, c2, fma(w1.y, c1, w0.y * c0));
+                    if (IM) {
+                        sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * sl, vy);
+                    } else {
+                        const double vx = fma(w2.x, c2, fma(w1.x, c1, w0.x * c0));
+                        sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
+                    }
+                }
+            } else
             for (int it = g.team_thread; it < NTAB * nsl; it += g.team_threads) {
                 const int s = it % NTAB, sl = it / NTAB;
                 const uint32_t ch = g.sm_chan + 8u * ((table0 + s) * a.ncp);
@@ -615,8 +674,10 @@ struct Kern {
             st.dt_init = dt;
 
             // ---- main loop ----
-            const double lq_init = log(a.qoldinit);
-            double lqold = lq_init;
+            // PI controller state: qold^beta2 is carried over (stepsize_controller! / step_accept_controller! /
+            // step_reject_controller!: q = EEst^beta1 / qold^beta2 / gamma clamped to [1/qmax, 1/qmin], dt_new = dt/q)
+            const double qinit_pow = pow(a.qoldinit, a.beta2), qinit2 = a.qoldinit * a.qoldinit;
+            double qold_pow = qinit_pow;
             const double inv_ntot = 1.0 / ntot;
             long long iters = 0;
             int n_attempt = 0;
@@ -649,9 +710,9 @@ struct Kern {
                 compute_tables<5>(a, g, smem_gen, t, dt, false, 0, win_state == 1, win_t, win_w);
                 QSIM_LAUNDER_ELL();
                 double tnew = t + dt;
-                {
-                    const double mx = fmax(t, tend);
+                if (tend - tnew < 1e-9 * fabs(tend)) {
                     // 10*eps(max(t, tstop)): snap the last step onto the end point
+                    const double mx = fmax(fabs(t), fabs(tend));
                     const double ulp = __longlong_as_double(__double_as_longlong(mx) + 1) - mx;
                     if (fabs(tnew - tend) < 10.0 * ulp) tnew = tend;
                 }
@@ -757,17 +818,22 @@ struct Kern {
                 // evaluated as dt * r with r = 1/q = gamma exp(beta2 log qold - beta1 log EEst).
                 const double e2 = err[0] * inv_ntot;
                 if (!isfinite(e2)) { st.retcode = QSIM_RET_NONFINITE; break; }
-                double r, le = 0.0;
-                if (e2 == 0.0) {
-                    r = a.qmax;
-                } else {
-                    le = 0.5 * log(e2);
-                    r = a.gamma * exp(a.beta2 * lqold - a.beta1 * le);
-                    r = fmin(a.qmax, fmax(a.qmin, r));
+                // ra = EEst^-beta1, rb = EEst^beta2 (EEst = sqrt(e2)) from the power tables; libm outside their range
+                double ra, rb;
+                if (!pow_pair(g, e2, ra, rb)) {
+                    if (e2 == 0.0) {
+                        ra = 1e300;   // "q = 1/qmax": largest growth after the clamp
+                        rb = 0.0;
+                    } else {
+                        const double le = 0.5 * log(e2);
+                        ra = exp(-a.beta1 * le);
+                        rb = exp(a.beta2 * le);
+                    }
                 }
                 if (e2 <= 1.0) {
                     st.n_accept++;
-                    lqold = e2 == 0.0 ? lq_init : fmax(le, lq_init);  // qold = max(EEst, qoldinit)
+                    const double r = fmin(a.qmax, fmax(a.qmin, a.gamma * ra * qold_pow));
+                    qold_pow = e2 >= qinit2 ? rb : qinit_pow;  // qold = max(EEst, qoldinit)
                     if (!a.streamed) {
                         if (nsave_hi > nsave && (RS || g.warp_in_team < a.n_batches))
                             save_points(a, traj, ts, nsave, nsave_hi, t, dt, tnew,
@@ -790,7 +856,7 @@ struct Kern {
                 } else {
                     st.n_reject++;
                     // dt / min(1/qmin, q11/gamma), q11 = EEst^beta1
-                    dt = dt * fmax(a.qmin, a.gamma * exp(-a.beta1 * le));
+                    dt = dt * fmax(a.qmin, a.gamma * ra);
                 }
             }
             st.n_rhs = 3 + 6 * n_attempt;  // the reference also evaluates f(u0,t0) a second time
@@ -848,9 +914,11 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     g.sm_tab = sbase;
     g.sm_cheb = sbase + 512;                             // double[NN*NN + NN + 3] (1280 bytes reserved)
-    g.sm_dptr = sbase + 512 + 1280;                      // int[n_dyn_slots + 1]
+    g.sm_pow = sbase + 512 + 1280;                       // double[2][16][K] Taylor coefficients, double[2][NE] 2^(pE)
+    g.sm_dptr = sbase + a.off_dptr;                      // int[n_dyn_slots + 1]
     g.sm_dchan = g.sm_dptr + 4 * (a.g.n_dyn_slots + 1);  // int[n_dyn_pairs]
-    g.sm_dw = sbase + a.common_bytes - 16 * (a.g.n_dyn_pairs > 0 ? a.g.n_dyn_pairs : 1);  // double2[n_dyn_pairs]
+    g.sm_dw = sbase + a.off_dw;                          // double2[n_dyn_pairs]
+    g.sm_drec = sbase + a.off_drec;                      // 64-byte records of the time-dependent slots
     const uint32_t tbase = sbase + a.common_bytes + team_in_cta * a.team_bytes;
     g.v_stride = K::VB * a.nvp;
     g.sm_V = tbase;
@@ -868,7 +936,23 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         const double *src = reinterpret_cast<const double *>(a.g.tab);
         for (int i = threadIdx.x; i < (int)(sizeof(SeriesTables) / 8); i += blockDim.x) sts1(g.sm_tab + 8 * i, src[i]);
         for (int i = threadIdx.x; i < QSIM_NN * QSIM_NN + QSIM_NN + 3; i += blockDim.x) sts1(g.sm_cheb + 8 * i, a.cheb[i]);
-        int *dptr = reinterpret_cast<int *>(smem) + (512 + 1280) / 4;
+        // controller power tables: p = -beta1/2 (first) and +beta2/2 (second)
+        for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+            const int idx = i & 15;
+            const double p = i < 16 ? -0.5 * a.beta1 : 0.5 * a.beta2, c = 1.03125 + 0.0625 * idx;
+            double coef = pow(c, p);
+            for (int k = 0; k < QSIM_POW_K; k++) {
+                sts1(g.sm_pow + 8u * (QSIM_POW_K * i + k), coef);
+                coef = coef * (p - k) / ((k + 1) * c);  // binom(p, k+1) c^(p-k-1)
+            }
+        }
+        for (int i = threadIdx.x; i < 2 * QSIM_POW_NE; i += blockDim.x) {
+            const double p = i < QSIM_POW_NE ? -0.5 * a.beta1 : 0.5 * a.beta2;
+            sts1(g.sm_pow + 8u * (QSIM_POW_K * 32 + i), exp2(p * (double)((i % QSIM_POW_NE) + QSIM_POW_EMIN)));
+        }
+        if (a.dyn_fast)
+            for (int i = threadIdx.x; i < 8 * a.g.n_dyn_slots; i += blockDim.x) sts1(g.sm_drec + 8 * i, a.dyn_rec[i]);
+        int *dptr = reinterpret_cast<int *>(smem) + a.off_dptr / 4;
         for (int i = threadIdx.x; i <= a.g.n_dyn_slots; i += blockDim.x) dptr[i] = a.g.slot_ptr[i];
         for (int i = threadIdx.x; i < a.g.n_dyn_pairs; i += blockDim.x) {
             dptr[a.g.n_dyn_slots + 1 + i] = a.g.pair_chan[i];
