@@ -37,6 +37,7 @@ N_AMP, N_FREQ = 64, 64
 
 
 SMALL = False  # --small: a reduced sweep for profiler captures only (never a bench value)
+POINTS = 0     # --points N: development override of the sweep size (never a bench value)
 
 
 def build_workload(world: int, rank: int):
@@ -50,6 +51,8 @@ def build_workload(world: int, rank: int):
         ts = np.arange(0.0, 201.0)
     from qsim_b200 import shard_params
     params, _ = shard_params(grid, world, rank)   # block-cyclic by parameter index
+    if POINTS:                                    # development only: occupancy experiments
+        params = np.ascontiguousarray(np.resize(params, (POINTS, params.shape[1])))
     return cqs, params, ts
 
 
@@ -148,9 +151,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--small", action="store_true", help="reduced sweep (1184 points, 20 ns) for ncu captures")
+    ap.add_argument("--points", type=int, default=0, help="development: override the number of sweep points")
     args = ap.parse_args()
-    global SMALL
+    global SMALL, POINTS
     SMALL = args.small
+    POINTS = args.points
     if args.impl == "reference":
         run_reference(args)
         return
@@ -267,7 +272,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "propagators/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD if not SMALL else "PROFILING SUBSET (1184 points, ts=0:20) of " + WORKLOAD,
+            "config": {"workload": WORKLOAD if not (SMALL or POINTS) else "DEVELOPMENT SUBSET (not a bench value) of " + WORKLOAD,
                        "points_per_gpu": n_traj, "sharding": "block-cyclic by parameter index, "
                        "no collective", "kernel": prob.kernel_name(which), "solver": "Tsit5 reltol=1e-6 abstol=1e-8 "
                        "(reference literals)", "l2": "256 MB flush write before every timed launch; each launch also "

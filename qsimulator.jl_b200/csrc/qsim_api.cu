@@ -403,9 +403,9 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
 }
 
 static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int imag, int rs) {
-    const KernelVariant *(*lists[])(int *) = {variants_r1c1_t160, variants_r1c1_t288, variants_r1c3_t160,
-                                              variants_r1c3_t288, variants_r2c1_t160, variants_r2c1_t288,
-                                              variants_r2c2_t160, variants_r2c2_t288, variants_r3c1_t160,
+    const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c1_t288, variants_r1c3_t128,
+                                              variants_r1c3_t288, variants_r2c1_t128, variants_r2c1_t288,
+                                              variants_r2c2_t128, variants_r2c2_t288, variants_r3c1_t128,
                                               variants_r3c1_t288, variants_rowsplit};
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
@@ -464,7 +464,9 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.streamed = 1;
         pl.team_warps = 9;
     }
-    pl.teams_per_cta = pl.team_warps == 1 ? 5 : 1;  // one-warp teams: 5 per CTA, 2 CTAs (10 warps) per SM
+    // one-warp teams: 4 per CTA (128 threads, 2 CTAs = 8 warps per SM when the kernel needs > 168 registers:
+    // no spills; spilled variants at 10-12 warps per SM are ~1.7x slower per warp)
+    pl.teams_per_cta = pl.team_warps == 1 ? 4 : 1;
     if (const char *env = std::getenv("QSIM_TEAMS_PER_CTA")) {  // tuning knob (development)
         const int v = std::atoi(env);
         if (v >= 1 && v <= 15 && v * pl.team_warps * 32 <= 288) pl.teams_per_cta = v;
@@ -509,7 +511,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         if (g.slot_ptr[sl + 1] - g.slot_ptr[sl] > 3) pl.dyn_fast = 0;
     pl.common_bytes = pl.off_drec + (pl.dyn_fast ? 64 * std::max(g.n_dyn_slots, 1) : 16);
     pl.team_bytes = (((g.imag_only ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
-                    (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride;
+                    (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride + 128 * pl.team_warps;
     pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
     pl.scratch_per_team = pl.streamed ? (size_t)4 * pl.n_batches * cpb * n * sizeof(double2) : 0;
     if (pl.smem > 220 * 1024) return fail(QSIM_ERR_UNSUPPORTED, "problem needs more shared memory than one SM has");

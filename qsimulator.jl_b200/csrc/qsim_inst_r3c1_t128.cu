@@ -1,0 +1,6 @@
+// Instantiates the Tsit5 solver kernels for 3 row(s) x 1 column(s) per lane, blocks of up to 128 threads
+// (one-warp teams, four per CTA, two CTAs = 8 warps per SM, no register spills).
+#include "qsim_registry.h"
+namespace qsim {
+QSIM_DEFINE_VARIANTS(variants_r3c1_t128, 3, 1, 128, 2)
+}

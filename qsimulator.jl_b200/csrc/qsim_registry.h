@@ -13,11 +13,11 @@ struct KernelVariant {
 
 // defined one per translation unit (qsim_inst_*.cu) so the variants compile in parallel
 #define QSIM_DECLARE(FN) const KernelVariant *FN(int *count);
-QSIM_DECLARE(variants_r1c1_t160) QSIM_DECLARE(variants_r1c1_t288)
-QSIM_DECLARE(variants_r1c3_t160) QSIM_DECLARE(variants_r1c3_t288)
-QSIM_DECLARE(variants_r2c1_t160) QSIM_DECLARE(variants_r2c1_t288)
-QSIM_DECLARE(variants_r2c2_t160) QSIM_DECLARE(variants_r2c2_t288)
-QSIM_DECLARE(variants_r3c1_t160) QSIM_DECLARE(variants_r3c1_t288)
+QSIM_DECLARE(variants_r1c1_t128) QSIM_DECLARE(variants_r1c1_t288)
+QSIM_DECLARE(variants_r1c3_t128) QSIM_DECLARE(variants_r1c3_t288)
+QSIM_DECLARE(variants_r2c1_t128) QSIM_DECLARE(variants_r2c1_t288)
+QSIM_DECLARE(variants_r2c2_t128) QSIM_DECLARE(variants_r2c2_t288)
+QSIM_DECLARE(variants_r3c1_t128) QSIM_DECLARE(variants_r3c1_t288)
 QSIM_DECLARE(variants_rowsplit)
 
 #define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \

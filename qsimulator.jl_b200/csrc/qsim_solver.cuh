@@ -29,6 +29,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "qsim_eval.h"
 
@@ -143,6 +144,26 @@ __device__ __forceinline__ int ldsi(uint32_t addr) {
     return v;
 }
 
+// Branch-free reciprocal square root / reciprocal: hardware seed (MUFU.RSQ64H / MUFU.RCP64H, ~2^-22) and two
+// Newton steps (full double precision up to an ulp or two).  The library versions carry special-case
+// branches that serialise the three independent per-entry chains of the error norm; arguments here are
+// positive normal numbers.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
+}
+__device__ __forceinline__ double rcp_nr(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
 __device__ __forceinline__ void team_sync(int team_warps, int bar_id) {
     if (team_warps == 1)
         __syncwarp();
@@ -193,6 +214,11 @@ __device__ __forceinline__ double team_max(double v, uint32_t red, int team_warp
 #define QSIM_POW_EMIN (-80)     // controller power tables cover EEst^2 in [2^-80, 2^48)
 #define QSIM_POW_NE 128
 #define QSIM_POW_K 10          // Taylor coefficients per mantissa sub-interval (16 sub-intervals of [1,2))
+#ifdef QSIM_TIMING   // development build: per-phase cycle counts of trajectory 0 (printed from the kernel)
+#define QSIM_TICK(i) { const long long c_ = clock64(); tk_[i] += c_ - tl_; tl_ = c_; }
+#else
+#define QSIM_TICK(i)
+#endif
 #define QSIM_NN 12             // Chebyshev nodes per drive window
 #define QSIM_WIN_TOL 2e-14     // accepted interpolation error relative to the channel's magnitude
 
@@ -205,6 +231,7 @@ struct Geo {
                                                                           // controller power tables, dynamic pair lists / records
     uint32_t sm_V, sm_chan, sm_rev, sm_win, sm_red;  // team (sm_win: per channel 12 nodes, 3 checks, 12 coefficients)
     uint32_t sm_y0, sm_y1;                      // this warp's two stage buffers (+ column offset)
+    uint32_t sm_ctl;                            // this warp's control block: step-loop scalars parked in shared memory
     uint32_t v_stride;                          // bytes between value tables
 };
 
@@ -238,15 +265,22 @@ struct Kern {
         const double m = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
         const double t = m - (1.03125 + 0.0625 * idx);
         const uint32_t pa = g.sm_pow + 8u * QSIM_POW_K * idx, pb = pa + 8u * QSIM_POW_K * 16;
-        double qa = lds1(pa + 8 * (QSIM_POW_K - 1)), qb = lds1(pb + 8 * (QSIM_POW_K - 1));
+        const uint32_t te = g.sm_pow + 8u * QSIM_POW_K * 32 + 8u * (ex - QSIM_POW_EMIN);
+        double ca[QSIM_POW_K], cb[QSIM_POW_K];
+#pragma unroll
+        for (int k = 0; k < QSIM_POW_K; k++) {  // all loads in flight before the first use
+            ca[k] = lds1(pa + 8 * k);
+            cb[k] = lds1(pb + 8 * k);
+        }
+        const double ta = lds1(te), tb = lds1(te + 8u * QSIM_POW_NE);
+        double qa = ca[QSIM_POW_K - 1], qb = cb[QSIM_POW_K - 1];
 #pragma unroll
         for (int k = QSIM_POW_K - 2; k >= 0; k--) {
-            qa = fma(qa, t, lds1(pa + 8 * k));
-            qb = fma(qb, t, lds1(pb + 8 * k));
+            qa = fma(qa, t, ca[k]);
+            qb = fma(qb, t, cb[k]);
         }
-        const uint32_t te = g.sm_pow + 8u * QSIM_POW_K * 32 + 8u * (ex - QSIM_POW_EMIN);
-        ra = qa * lds1(te);
-        rb = qb * lds1(te + 8u * QSIM_POW_NE);
+        ra = qa * ta;
+        rb = qb * tb;
         return true;
     }
 
@@ -270,11 +304,14 @@ struct Kern {
     }
     // sum_k c_k T_k with the coefficients in shared memory; two partial sums for instruction-level parallelism
     static __device__ __forceinline__ double cheb_dot(uint32_t coef, const double (&T)[QSIM_NN]) {
+        double c[QSIM_NN];
+#pragma unroll
+        for (int k = 0; k < QSIM_NN; k++) c[k] = lds1(coef + 8 * k);  // all loads in flight before the first use
         double p0 = 0.0, p1 = 0.0;
 #pragma unroll
         for (int k = 0; k < QSIM_NN; k += 2) {
-            p0 = fma(lds1(coef + 8 * k), T[k], p0);
-            p1 = fma(lds1(coef + 8 * (k + 1)), T[k + 1], p1);
+            p0 = fma(c[k], T[k], p0);
+            p1 = fma(c[k + 1], T[k + 1], p1);
         }
         return p0 + p1;
     }
@@ -480,10 +517,38 @@ struct Kern {
 #pragma unroll 4
                 for (int j = 1; j < nnz; j++) mac(Vs, yb, __ldg(er + (size_t)j * stride), false, &yreg[i * CPL], acc);
             } else {
-                // no per-entry branch: short rows are padded with the zero slot, so all loads of a stage can
-                // be hoisted ahead of the multiply-adds
+                // no per-entry branch (short rows are padded with the zero slot): every operand of the row is
+                // requested before the first multiply-add, so a stage exposes one shared-memory latency
+                double2 vv[MAXNNZ], yy[MAXNNZ][CPL];
 #pragma unroll
-                for (int j = 0; j < MAXNNZ; j++) mac(Vs, yb, ell[i][j], j == 0, &yreg[i * CPL], acc);
+                for (int j = 0; j < MAXNNZ; j++) {
+                    const uint32_t e = ell[i][j];
+                    if (IM)
+                        vv[j].y = lds1(Vs + (e >> 16));
+                    else
+                        vv[j] = lds2(Vs + (e >> 16));
+                    if (j > 0) {
+#pragma unroll
+                        for (int c = 0; c < CPL; c++) yy[j][c] = lds2(yb + (e & 0xFFFFu) + 16 * c);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < MAXNNZ; j++) {
+#pragma unroll
+                    for (int c = 0; c < CPL; c++) {
+                        const double2 y = j == 0 ? yreg[i * CPL + c] : yy[j][c];
+                        if (IM) {
+                            // A = i B with B real: (iB)(yr + i yi) = -B yi + i B yr
+                            acc[c].x = fma(-vv[j].y, y.y, acc[c].x);
+                            acc[c].y = fma(vv[j].y, y.x, acc[c].y);
+                        } else {
+                            acc[c].x = fma(vv[j].x, y.x, acc[c].x);
+                            acc[c].y = fma(vv[j].x, y.y, acc[c].y);
+                            acc[c].x = fma(-vv[j].y, y.y, acc[c].x);
+                            acc[c].y = fma(vv[j].y, y.x, acc[c].y);
+                        }
+                    }
+                }
             }
 #pragma unroll
             for (int c = 0; c < CPL; c++) k[i * CPL + c] = acc[c];
@@ -676,28 +741,50 @@ struct Kern {
             // ---- main loop ----
             // PI controller state: qold^beta2 is carried over (stepsize_controller! / step_accept_controller! /
             // step_reject_controller!: q = EEst^beta1 / qold^beta2 / gamma clamped to [1/qmax, 1/qmin], dt_new = dt/q)
-            const double qinit_pow = pow(a.qoldinit, a.beta2), qinit2 = a.qoldinit * a.qoldinit;
-            double qold_pow = qinit_pow;
-            const double inv_ntot = 1.0 / ntot;
+            // Scalars that are only needed at the head and tail of a step live in the warp's control block in
+            // shared memory and are fetched in two batches per step; keeping them in registers across the stage
+            // code costs spills whose reloads each expose a full memory latency.
+            enum { C_TEND, C_DTMAX, C_INVN, C_QIPOW, C_QI2, C_TSNEXT, C_WINT, C_WINW, C_WINNEXT, C_QOLDPOW, C_TNEW };
+#define CTL_LD(i) lds1(g.sm_ctl + 8 * (i))
+#define CTL_ST(i, v) sts1(g.sm_ctl + 8 * (i), (v))
+            CTL_ST(C_TEND, tend);
+            CTL_ST(C_DTMAX, dtmax);
+            CTL_ST(C_INVN, 1.0 / ntot);
+            CTL_ST(C_QIPOW, pow(a.qoldinit, a.beta2));
+            CTL_ST(C_QI2, a.qoldinit * a.qoldinit);
+            CTL_ST(C_TSNEXT, ts_next);
+            CTL_ST(C_WINT, 0.0);
+            CTL_ST(C_WINW, 1.0);
+            CTL_ST(C_WINNEXT, 0.0);
+            CTL_ST(C_QOLDPOW, pow(a.qoldinit, a.beta2));
+            __syncwarp();
             long long iters = 0;
             int n_attempt = 0;
             int win_state = a.use_windows ? 0 : -1;  // -1 direct evaluation, 0 no window yet, 1 window valid
-            double win_t = 0.0, win_w = 1.0, win_next = 0.0;
-            while (t < tend) {
+#ifdef QSIM_TIMING
+            long long tk_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tl_ = clock64();
+#endif
+            for (;;) {
+                QSIM_TICK(0)
+                const double c_tend = CTL_LD(C_TEND), c_dtmax = CTL_LD(C_DTMAX), c_tsnext = CTL_LD(C_TSNEXT);
+                double win_t = CTL_LD(C_WINT), win_w = CTL_LD(C_WINW);
+                if (!(t < c_tend)) break;
                 if (++iters > a.maxiters) { st.retcode = QSIM_RET_MAXITERS; break; }
-                dt = fmin(dt, dtmax);
-                dt = fmin(dt, tend - t);
+                dt = fmin(dt, c_dtmax);
+                dt = fmin(dt, c_tend - t);
                 if (!(dt > fabs(t) * 2.220446049250313e-16)) { st.retcode = QSIM_RET_DT_UNDERFLOW; break; }
                 if (win_state >= 0 && (win_state == 0 || t + dt > win_t + win_w)) {
                     // (re)build the drive window starting at this step; shrink until the check passes
-                    double wt = fmax(win_state == 0 ? 6.0 * dt : win_next, 1.25 * dt);
+                    double wt = fmax(win_state == 0 ? 6.0 * dt : CTL_LD(C_WINNEXT), 1.25 * dt);
                     for (;;) {
                         const double werr = build_window(a, g, smem_gen, t, wt);
                         if (werr <= QSIM_WIN_TOL) {
                             win_t = t;
                             win_w = wt;
                             win_state = 1;
-                            win_next = werr <= QSIM_WIN_TOL / 64.0 ? fmin(1.5 * wt, 128.0 * dt) : wt;
+                            CTL_ST(C_WINT, win_t);
+                            CTL_ST(C_WINW, win_w);
+                            CTL_ST(C_WINNEXT, werr <= QSIM_WIN_TOL / 64.0 ? fmin(1.5 * wt, 128.0 * dt) : wt);
                             break;
                         }
                         if (wt <= 1.3 * dt) {  // not even one step fits: evaluate this trajectory's drives directly
@@ -707,21 +794,27 @@ struct Kern {
                         wt = fmax(0.5 * wt, 1.25 * dt);
                     }
                 }
+                QSIM_TICK(1)
                 compute_tables<5>(a, g, smem_gen, t, dt, false, 0, win_state == 1, win_t, win_w);
+                QSIM_TICK(2)
                 QSIM_LAUNDER_ELL();
-                double tnew = t + dt;
-                if (tend - tnew < 1e-9 * fabs(tend)) {
-                    // 10*eps(max(t, tstop)): snap the last step onto the end point
-                    const double mx = fmax(fabs(t), fabs(tend));
-                    const double ulp = __longlong_as_double(__double_as_longlong(mx) + 1) - mx;
-                    if (fabs(tnew - tend) < 10.0 * ulp) tnew = tend;
-                }
                 int nsave_hi = nsave;
-                if (ts_next <= tnew) {
-                    while (nsave_hi < a.n_ts && ts[nsave_hi] <= tnew) nsave_hi++;
+                {
+                    double tnew = t + dt;
+                    if (c_tend - tnew < 1e-9 * fabs(c_tend)) {
+                        // 10*eps(max(t, tstop)): snap the last step onto the end point
+                        const double mx = fmax(fabs(t), fabs(c_tend));
+                        const double ulp = __longlong_as_double(__double_as_longlong(mx) + 1) - mx;
+                        if (fabs(tnew - c_tend) < 10.0 * ulp) tnew = c_tend;
+                    }
+                    if (c_tsnext <= tnew) {
+                        while (nsave_hi < a.n_ts && ts[nsave_hi] <= tnew) nsave_hi++;
+                    }
+                    CTL_ST(C_TNEW, tnew);
                 }
 
                 double err[1] = {0.0};
+                QSIM_TICK(3)
                 for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                     const int col0 = b * g.cpb + g.colofs;
                     if (a.streamed) {
@@ -734,7 +827,9 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb0, my_off, row_ok);
+                    QSIM_TICK(4)
                     apply(a, V0, yb0, ell, row_of, tmp, k2);
+                    QSIM_TICK(5)
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         double ax = A31 * k1[e].x, ay = A31 * k1[e].y;
@@ -785,21 +880,60 @@ struct Kern {
                     }
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
                     apply(a, V4, yb1, ell, row_of, tmp, k7);
+                    QSIM_TICK(6)
+                    {
+                        // Error norm: sum over this lane's entries of |u~|^2 / (abstol + max(|u|,|u_new|) reltol)^2.
+                        // Written operation by operation across the entries so the independent per-entry
+                        // chains (combination, reciprocal square root, reciprocal) overlap instead of running
+                        // back to back.
+                        double ex[E], ey[E], m2[E], ys[E], hx[E], dn[E], yr[E];
 #pragma unroll
-                    for (int e = 0; e < E; e++) {
-                        double ex = BT1 * k1[e].x, ey = BT1 * k1[e].y;
-                        ex += BT2 * k2[e].x; ey += BT2 * k2[e].y;
-                        ex += BT3 * k3[e].x; ey += BT3 * k3[e].y;
-                        ex += BT4 * k4[e].x; ey += BT4 * k4[e].y;
-                        ex += BT5 * k5[e].x; ey += BT5 * k5[e].y;
-                        ex += BT6 * k6[e].x; ey += BT6 * k6[e].y;
-                        ex += BT7 * k7[e].x; ey += BT7 * k7[e].y;
-                        // residual scale abstol + max(|u|, |u_new|) reltol: sqrt as x*rsqrt(x), 1/x by __drcp_rn
-                        const double m2 = fmax(u[e].x * u[e].x + u[e].y * u[e].y, tmp[e].x * tmp[e].x + tmp[e].y * tmp[e].y);
-                        const double mag = m2 > 0.0 ? m2 * rsqrt(m2) : 0.0;
-                        const double rs = dt * __drcp_rn(fma(mag, a.reltol, a.abstol));
-                        ex *= rs; ey *= rs;
-                        err[0] += ex * ex + ey * ey;
+                        for (int e = 0; e < E; e++) { ex[e] = BT1 * k1[e].x; ey[e] = BT1 * k1[e].y; }
+#pragma unroll
+                        for (int e = 0; e < E; e++) { ex[e] = fma(BT2, k2[e].x, ex[e]); ey[e] = fma(BT2, k2[e].y, ey[e]); }
+#pragma unroll
+                        for (int e = 0; e < E; e++) { ex[e] = fma(BT3, k3[e].x, ex[e]); ey[e] = fma(BT3, k3[e].y, ey[e]); }
+#pragma unroll
+                        for (int e = 0; e < E; e++) { ex[e] = fma(BT4, k4[e].x, ex[e]); ey[e] = fma(BT4, k4[e].y, ey[e]); }
+#pragma unroll
+                        for (int e = 0; e < E; e++) { ex[e] = fma(BT5, k5[e].x, ex[e]); ey[e] = fma(BT5, k5[e].y, ey[e]); }
+#pragma unroll
+                        for (int e = 0; e < E; e++) { ex[e] = fma(BT6, k6[e].x, ex[e]); ey[e] = fma(BT6, k6[e].y, ey[e]); }
+#pragma unroll
+                        for (int e = 0; e < E; e++) { ex[e] = fma(BT7, k7[e].x, ex[e]); ey[e] = fma(BT7, k7[e].y, ey[e]); }
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const double au = fma(u[e].x, u[e].x, u[e].y * u[e].y);
+                            const double an = fma(tmp[e].x, tmp[e].x, tmp[e].y * tmp[e].y);
+                            // max of non-negative doubles through their bit patterns (entries below 1e-140 count as that)
+                            const long long bu = __double_as_longlong(au), bn = __double_as_longlong(an);
+                            const long long bm = bu > bn ? bu : bn;
+                            m2[e] = __longlong_as_double(bm > 0x05d0000000000000LL ? bm : 0x05d0000000000000LL);
+                        }
+#pragma unroll
+                        for (int e = 0; e < E; e++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ys[e]) : "d"(m2[e]));
+#pragma unroll
+                        for (int e = 0; e < E; e++) hx[e] = 0.5 * m2[e];
+#pragma unroll
+                        for (int e = 0; e < E; e++) ys[e] = ys[e] * fma(-hx[e] * ys[e], ys[e], 1.5);
+#pragma unroll
+                        for (int e = 0; e < E; e++) ys[e] = ys[e] * fma(-hx[e] * ys[e], ys[e], 1.5);
+#pragma unroll
+                        for (int e = 0; e < E; e++) dn[e] = fma(m2[e] * ys[e], a.reltol, a.abstol);  // abstol + |.| reltol
+#pragma unroll
+                        for (int e = 0; e < E; e++) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(yr[e]) : "d"(dn[e]));
+#pragma unroll
+                        for (int e = 0; e < E; e++) yr[e] = fma(yr[e], fma(-dn[e], yr[e], 1.0), yr[e]);
+#pragma unroll
+                        for (int e = 0; e < E; e++) yr[e] = fma(yr[e], fma(-dn[e], yr[e], 1.0), yr[e]);
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const double rs = dt * yr[e];
+                            ex[e] *= rs;
+                            ey[e] *= rs;
+                        }
+#pragma unroll
+                        for (int e = 0; e < E; e++) err[0] += fma(ex[e], ex[e], ey[e] * ey[e]);
                     }
                     if (a.streamed) {
                         // tentative: the next buffers are adopted only if the step is accepted; dense-output
@@ -807,15 +941,19 @@ struct Kern {
                         store_batch(sc_u0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, row_of, row_ok, tmp);
                         store_batch(sc_k0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, row_of, row_ok, k7);
                         if (nsave_hi > nsave)
-                            save_points(a, traj, ts, nsave, nsave_hi, t, dt, tnew, col0, row_of, row_ok, u, k1, k2, k3,
-                                        k4, k5, k6, k7, tmp);
+                            save_points(a, traj, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok, u, k1,
+                                        k2, k3, k4, k5, k6, k7, tmp);
                     }
                 }
                 n_attempt++;
+                QSIM_TICK(7)
                 team_sum<1>(err, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
+                QSIM_TICK(8)
                 // EEst^2 = mean |r_i|^2.  PI controller (stepsize_controller! / step_accept_controller! /
                 // step_reject_controller!): q = EEst^beta1 / qold^beta2 / gamma clamped to [1/qmax, 1/qmin];
                 // evaluated as dt * r with r = 1/q = gamma exp(beta2 log qold - beta1 log EEst).
+                const double inv_ntot = CTL_LD(C_INVN), qold_pow = CTL_LD(C_QOLDPOW), qinit2 = CTL_LD(C_QI2),
+                             qinit_pow = CTL_LD(C_QIPOW), tnew = CTL_LD(C_TNEW);
                 const double e2 = err[0] * inv_ntot;
                 if (!isfinite(e2)) { st.retcode = QSIM_RET_NONFINITE; break; }
                 // ra = EEst^-beta1, rb = EEst^beta2 (EEst = sqrt(e2)) from the power tables; libm outside their range
@@ -833,7 +971,7 @@ struct Kern {
                 if (e2 <= 1.0) {
                     st.n_accept++;
                     const double r = fmin(a.qmax, fmax(a.qmin, a.gamma * ra * qold_pow));
-                    qold_pow = e2 >= qinit2 ? rb : qinit_pow;  // qold = max(EEst, qoldinit)
+                    CTL_ST(C_QOLDPOW, e2 >= qinit2 ? rb : qinit_pow);  // qold = max(EEst, qoldinit)
                     if (!a.streamed) {
                         if (nsave_hi > nsave && (RS || g.warp_in_team < a.n_batches))
                             save_points(a, traj, ts, nsave, nsave_hi, t, dt, tnew,
@@ -849,7 +987,7 @@ struct Kern {
                     }
                     if (nsave_hi > nsave) {
                         nsave = nsave_hi;
-                        ts_next = nsave < a.n_ts ? ts[nsave] : inf;
+                        CTL_ST(C_TSNEXT, nsave < a.n_ts ? ts[nsave] : inf);
                     }
                     t = tnew;
                     dt = dt * r;
@@ -859,6 +997,14 @@ struct Kern {
                     dt = dt * fmax(a.qmin, a.gamma * ra);
                 }
             }
+#ifdef QSIM_TIMING
+            if (traj == 0 && g.team_thread == 0)
+                printf("cycles/step: head %lld window %lld tables %lld head2 %lld combo+put(st2) %lld apply(st2) %lld "
+                       "stages3-7 %lld error %lld reduce %lld controller+accept %lld   steps %d\n",
+                       tk_[1] / n_attempt, 0LL, tk_[2] / n_attempt, tk_[3] / n_attempt, tk_[4] / n_attempt,
+                       tk_[5] / n_attempt, tk_[6] / n_attempt, tk_[7] / n_attempt, tk_[8] / n_attempt, tk_[0] / n_attempt,
+                       n_attempt);
+#endif
             st.n_rhs = 3 + 6 * n_attempt;  // the reference also evaluates f(u0,t0) a second time
         } else {
             // zero-length span: only the start saves
@@ -881,8 +1027,8 @@ struct Kern {
     }
 };
 
-// MAXT: largest block the variant is launched with (160: one-warp teams, 5 per CTA, 2 CTAs per SM;
-// 288: teams of up to 9 warps); both end up at 168 registers.
+// MAXT: largest block the variant is launched with (128: one-warp teams, 4 per CTA, 2 CTAs = 8 warps per SM,
+// up to 255 registers so nothing spills; 288: teams of up to 9 warps, 168 registers).
 // MINB: minimum resident CTAs per SM the register allocation must allow; IM: purely imaginary generator
 // (unitary evolution under a real Hamiltonian): value slots hold Im(A) only, 2 DFMA per multiply-add.
 template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM, bool RS>
@@ -930,6 +1076,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     g.sm_y0 = g.sm_red + 8u * (a.team_warps * 4 + 8) + (RS ? 0 : g.warp_in_team) * 2 * ybytes +
               16u * g_idx * a.y_grp_stride;
     g.sm_y1 = g.sm_y0 + ybytes;
+    g.sm_ctl = g.sm_red + 8u * (a.team_warps * 4 + 8) + (RS ? 1 : a.team_warps) * 2 * ybytes + 128u * g.warp_in_team;
 
     // ---- CTA-wide constants: series tables and the dynamic slots' pair lists ----
     {
