@@ -75,6 +75,7 @@ struct qsim_problem::DeviceCopy {
     double2 *pair_w = nullptr;
     EvalDesc *evals = nullptr;
     double *dyn_rec = nullptr;       // 64-byte records of the time-dependent slots
+    int fast_ok = 0, fast_chA = 0, fast_chB = 0;  // records are in (constant, channel A, channel B) order
     uint32_t *ell_packed = nullptr;  // row-split kernels
     int packed_stride = -1;
     void free_all() {
@@ -567,19 +568,43 @@ static int ensure_device_copy(qsim_ctx *c, qsim_problem *p, int w) {
     CU(upload(&dc->pair_w, w2));
     CU(upload(&dc->evals, g.evals));
     {
-        // {w0, w1, w2 (re, im), ch0, ch1, ch2, pad}: unused pairs carry weight 0 on the constant channel
+        // {w0, w1, w2 (re, im), ch0, ch1, ch2, pad}: unused pairs carry weight 0 on the constant channel.
+        // When the time-dependent slots involve only the constant channel and at most two time-dependent
+        // channels A < B, the records are written in (constant, A, B) order so the kernels need no indices.
+        std::vector<int> dyn_ch;
+        for (const auto &e : g.evals)
+            if (e.dynamic)
+                for (int q = 0; q < eval_outputs(e.kind); q++) dyn_ch.push_back(e.out_chan + q);
+        bool fast = !dyn_ch.empty() && dyn_ch.size() <= 2 && g.n_dyn_slots > 0;
+        const int chA = dyn_ch.empty() ? 0 : dyn_ch[0], chB = dyn_ch.size() > 1 ? dyn_ch[1] : chA;
+        for (int sl = 0; sl < g.n_dyn_slots && fast; sl++)
+            for (int q = g.slot_ptr[sl]; q < g.slot_ptr[sl + 1]; q++)
+                if (g.pair_chan[q] != 0 && g.pair_chan[q] != chA && g.pair_chan[q] != chB) fast = false;
         std::vector<double> rec((size_t)8 * std::max(g.n_dyn_slots, 1), 0.0);
         for (int sl = 0; sl < g.n_dyn_slots; sl++) {
             int32_t ch[4] = {0, 0, 0, 0};
-            const int np = std::min(3, g.slot_ptr[sl + 1] - g.slot_ptr[sl]);
-            for (int q = 0; q < np; q++) {
-                rec[(size_t)8 * sl + 2 * q] = g.pair_w[g.slot_ptr[sl] + q].real();
-                rec[(size_t)8 * sl + 2 * q + 1] = g.pair_w[g.slot_ptr[sl] + q].imag();
-                ch[q] = g.pair_chan[g.slot_ptr[sl] + q];
+            if (fast) {
+                ch[1] = chA;
+                ch[2] = chB;
+                for (int q = g.slot_ptr[sl]; q < g.slot_ptr[sl + 1]; q++) {
+                    const int pos = g.pair_chan[q] == 0 ? 0 : (g.pair_chan[q] == chA ? 1 : 2);
+                    rec[(size_t)8 * sl + 2 * pos] += g.pair_w[q].real();
+                    rec[(size_t)8 * sl + 2 * pos + 1] += g.pair_w[q].imag();
+                }
+            } else {
+                const int np = std::min(3, g.slot_ptr[sl + 1] - g.slot_ptr[sl]);
+                for (int q = 0; q < np; q++) {
+                    rec[(size_t)8 * sl + 2 * q] = g.pair_w[g.slot_ptr[sl] + q].real();
+                    rec[(size_t)8 * sl + 2 * q + 1] = g.pair_w[g.slot_ptr[sl] + q].imag();
+                    ch[q] = g.pair_chan[g.slot_ptr[sl] + q];
+                }
             }
             std::memcpy(&rec[(size_t)8 * sl + 6], ch, sizeof(ch));
         }
         CU(upload(&dc->dyn_rec, rec));
+        dc->fast_ok = fast ? 1 : 0;
+        dc->fast_chA = chA;
+        dc->fast_chB = chB;
     }
     p->dev[w] = dc;
     return QSIM_OK;
@@ -709,6 +734,9 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
                 if (e.out_chan + q < 32) a.dyn_chan_mask |= 1u << (e.out_chan + q);
         }
     a.use_windows = (any_dyn && g.n_chan <= 32 && !(o.flags & QSIM_FLAG_DIRECT_DRIVES)) ? 1 : 0;
+    a.fast_tables = (a.use_windows && pl.team_warps == 1 && dc->fast_ok) ? 1 : 0;
+    a.fast_chA = dc->fast_chA;
+    a.fast_chB = dc->fast_chB;
     a.ell_packed = dc->ell_packed;
     a.ell_rows = g.n + 8;
     a.ncols = pl.ncols;

@@ -71,6 +71,9 @@ struct LaunchArgs {
     unsigned dyn_chan_mask;  // channels produced by time-dependent evaluators
     int use_windows;      // 1: drive channels through windowed Chebyshev interpolants (see build_window)
     int dyn_fast;         // 1: every time-dependent slot has <= 3 pairs (64-byte records)
+    int fast_tables;      // 1: one-warp teams whose time-dependent slots are w0 + wA cA(t) + wB cB(t) with at most two
+                          //    time-dependent channels A, B (records hold w0, wA, wB in that order): see fast_tables()
+    int fast_chA, fast_chB;
     int off_dptr, off_dw, off_drec;  // byte offsets inside the common region (after tables, Chebyshev, power tables)
     const double *dyn_rec;           // [n_dyn_slots][8] records {w0, w1, w2 (double2), ch0, ch1, ch2, pad (int)}
     int team_bytes;       // shared bytes per team
@@ -164,6 +167,17 @@ __device__ __forceinline__ double rcp_nr(double x) {
     return y;
 }
 
+// min / max of non-negative doubles through their bit patterns (IEEE order = integer order for x >= 0):
+// a 64-bit integer compare + select instead of the NaN-aware DSETP.MIN/MAX + fix-up sequence.
+__device__ __forceinline__ double pmin(double a, double b) {
+    const long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+    return __longlong_as_double(x < y ? x : y);
+}
+__device__ __forceinline__ double pmax(double a, double b) {
+    const long long x = __double_as_longlong(a), y = __double_as_longlong(b);
+    return __longlong_as_double(x > y ? x : y);
+}
+
 __device__ __forceinline__ void team_sync(int team_warps, int bar_id) {
     if (team_warps == 1)
         __syncwarp();
@@ -232,6 +246,7 @@ struct Geo {
     uint32_t sm_V, sm_chan, sm_rev, sm_win, sm_red;  // team (sm_win: per channel 12 nodes, 3 checks, 12 coefficients)
     uint32_t sm_y0, sm_y1;                      // this warp's two stage buffers (+ column offset)
     uint32_t sm_ctl;                            // this warp's control block: step-loop scalars parked in shared memory
+    double stage_c;                             // kStageC[lane] for lanes 0..4 (fast_tables), set once per thread
     uint32_t v_stride;                          // bytes between value tables
 };
 
@@ -273,12 +288,15 @@ struct Kern {
             cb[k] = lds1(pb + 8 * k);
         }
         const double ta = lds1(te), tb = lds1(te + 8u * QSIM_POW_NE);
-        double qa = ca[QSIM_POW_K - 1], qb = cb[QSIM_POW_K - 1];
-#pragma unroll
-        for (int k = QSIM_POW_K - 2; k >= 0; k--) {
-            qa = fma(qa, t, ca[k]);
-            qb = fma(qb, t, cb[k]);
-        }
+        // Estrin evaluation of the two degree-9 polynomials (dependency depth 5 instead of 9)
+        static_assert(QSIM_POW_K == 10, "Estrin scheme below is written for 10 coefficients");
+        const double t2 = t * t, t4 = t2 * t2, t8 = t4 * t4;
+        const double a01 = fma(ca[1], t, ca[0]), a23 = fma(ca[3], t, ca[2]), a45 = fma(ca[5], t, ca[4]),
+                     a67 = fma(ca[7], t, ca[6]), a89 = fma(ca[9], t, ca[8]);
+        const double b01 = fma(cb[1], t, cb[0]), b23 = fma(cb[3], t, cb[2]), b45 = fma(cb[5], t, cb[4]),
+                     b67 = fma(cb[7], t, cb[6]), b89 = fma(cb[9], t, cb[8]);
+        const double qa = fma(t8, a89, fma(t4, fma(t2, a67, a45), fma(t2, a23, a01)));
+        const double qb = fma(t8, b89, fma(t4, fma(t2, b67, b45), fma(t2, b23, b01)));
         ra = qa * ta;
         rb = qb * tb;
         return true;
@@ -367,6 +385,61 @@ struct Kern {
             }
         }
         return team_max(bad, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
+    }
+
+    // Stage tables for the common case (one-warp team, <= 2 time-dependent channels, drive window valid):
+    // lane s < 5 evaluates both channels' Chebyshev interpolants at stage time s (basis by the double-step
+    // recurrence T_{k+2} = 2 T_2 T_k - T_{k-2}: two independent chains), the values are broadcast by shuffle,
+    // and every lane combines them with its slots' weights.  No shared-memory round trip, no barrier: the
+    // stage exchange's __syncwarp orders the table stores before the first gather.
+    static __device__ __forceinline__ void fast_tables(const LaunchArgs &a, const Geo &g, double t, double dt,
+                                                       double win_t, double win_sc) {
+        double cA = 0.0, cB = 0.0;
+        if (g.lane < 5) {
+            const double x = fma((t + g.stage_c * dt) - win_t, win_sc, -1.0);  // stage-time fraction c_{lane+2}
+            const uint32_t fa = g.sm_win + 256u * a.fast_chA + 128, fb = g.sm_win + 256u * a.fast_chB + 128;
+            double ka[QSIM_NN], kb[QSIM_NN];
+#pragma unroll
+            for (int k = 0; k < QSIM_NN; k++) {  // all loads in flight first
+                ka[k] = lds1(fa + 8 * k);
+                kb[k] = lds1(fb + 8 * k);
+            }
+            double T[QSIM_NN];
+            T[0] = 1.0;
+            T[1] = x;
+            const double c2 = fma(4.0 * x, x, -2.0);  // 2 T_2(x)
+            T[2] = 0.5 * c2;
+            T[3] = fma(c2, x, -x);
+#pragma unroll
+            for (int k = 4; k < QSIM_NN; k++) T[k] = fma(c2, T[k - 2], -T[k - 4]);
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < QSIM_NN; k += 2) {
+                a0 = fma(ka[k], T[k], a0);
+                a1 = fma(ka[k + 1], T[k + 1], a1);
+                b0 = fma(kb[k], T[k], b0);
+                b1 = fma(kb[k + 1], T[k + 1], b1);
+            }
+            cA = a0 + a1;
+            cB = b0 + b1;
+        }
+        const int n_items = 5 * a.g.n_dyn_slots;
+        for (int base = 0; base < n_items; base += 32) {  // uniform trip count: every lane joins the shuffles
+            const int it = base + g.lane;
+            const int s = it % 5, sl = it / 5;
+            const double fA = __shfl_sync(0xffffffffu, cA, s), fB = __shfl_sync(0xffffffffu, cB, s);
+            if (it < n_items) {
+                const uint32_t rec = g.sm_drec + 64u * sl;
+                const double2 w0 = lds2(rec), w1 = lds2(rec + 16), w2 = lds2(rec + 32);
+                const double vy = fma(w2.y, fB, fma(w1.y, fA, w0.y));
+                if (IM) {
+                    sts1(g.sm_V + s * g.v_stride + 8 * sl, vy);
+                } else {
+                    const double vx = fma(w2.x, fB, fma(w1.x, fA, w0.x));
+                    sts2(g.sm_V + s * g.v_stride + 16 * sl, make_double2(vx, vy));
+                }
+            }
+        }
     }
 
     template <int NTAB>
@@ -500,9 +573,15 @@ struct Kern {
         }
     }
 
+    struct NoHook {
+        __device__ __forceinline__ void operator()() const {}
+    };
+    // `hook` runs between the issue of a row's operand loads and their first use: independent work placed
+    // there (the next stage's partial combination) executes under the shared-memory latency.
+    template <typename Hook = NoHook>
     static __device__ __forceinline__ void apply(const LaunchArgs &a, uint32_t Vs, uint32_t yb,
                                                  const uint32_t (&ell)[RPL][MAXNNZ], const int (&row_of)[RPL],
-                                                 const Vec &yreg, Vec &k) {
+                                                 const Vec &yreg, Vec &k, Hook hook = Hook()) {
 #pragma unroll
         for (int i = 0; i < RPL; i++) {
             double2 acc[CPL];
@@ -513,6 +592,7 @@ struct Kern {
                 // entries with the zero slot substituted by the host-side table's padding row
                 const uint32_t *er = a.ell_packed + row_of[i];
                 const int nnz = a.g.max_nnz, stride = a.ell_rows;
+                if (i == RPL - 1) hook();
                 mac(Vs, yb, __ldg(er), true, &yreg[i * CPL], acc);
 #pragma unroll 4
                 for (int j = 1; j < nnz; j++) mac(Vs, yb, __ldg(er + (size_t)j * stride), false, &yreg[i * CPL], acc);
@@ -532,6 +612,7 @@ struct Kern {
                         for (int c = 0; c < CPL; c++) yy[j][c] = lds2(yb + (e & 0xFFFFu) + 16 * c);
                     }
                 }
+                if (i == RPL - 1) hook();
 #pragma unroll
                 for (int j = 0; j < MAXNNZ; j++) {
 #pragma unroll
@@ -744,7 +825,7 @@ struct Kern {
             // Scalars that are only needed at the head and tail of a step live in the warp's control block in
             // shared memory and are fetched in two batches per step; keeping them in registers across the stage
             // code costs spills whose reloads each expose a full memory latency.
-            enum { C_TEND, C_DTMAX, C_INVN, C_QIPOW, C_QI2, C_TSNEXT, C_WINT, C_WINW, C_WINNEXT, C_QOLDPOW, C_TNEW };
+            enum { C_TEND, C_DTMAX, C_INVN, C_QIPOW, C_QI2, C_TSNEXT, C_WINT, C_WINW, C_WINNEXT, C_QOLDPOW, C_TNEW, C_WINSC };
 #define CTL_LD(i) lds1(g.sm_ctl + 8 * (i))
 #define CTL_ST(i, v) sts1(g.sm_ctl + 8 * (i), (v))
             CTL_ST(C_TEND, tend);
@@ -756,6 +837,7 @@ struct Kern {
             CTL_ST(C_WINT, 0.0);
             CTL_ST(C_WINW, 1.0);
             CTL_ST(C_WINNEXT, 0.0);
+            CTL_ST(C_WINSC, 2.0);
             CTL_ST(C_QOLDPOW, pow(a.qoldinit, a.beta2));
             __syncwarp();
             long long iters = 0;
@@ -767,11 +849,11 @@ struct Kern {
             for (;;) {
                 QSIM_TICK(0)
                 const double c_tend = CTL_LD(C_TEND), c_dtmax = CTL_LD(C_DTMAX), c_tsnext = CTL_LD(C_TSNEXT);
-                double win_t = CTL_LD(C_WINT), win_w = CTL_LD(C_WINW);
+                double win_t = CTL_LD(C_WINT), win_w = CTL_LD(C_WINW), win_sc = CTL_LD(C_WINSC);
                 if (!(t < c_tend)) break;
                 if (++iters > a.maxiters) { st.retcode = QSIM_RET_MAXITERS; break; }
-                dt = fmin(dt, c_dtmax);
-                dt = fmin(dt, c_tend - t);
+                if (!(dt > 0.0)) { st.retcode = dt == dt ? QSIM_RET_DT_UNDERFLOW : QSIM_RET_NONFINITE; break; }
+                dt = pmin(pmin(dt, c_dtmax), c_tend - t);  // all three positive here
                 if (!(dt > fabs(t) * 2.220446049250313e-16)) { st.retcode = QSIM_RET_DT_UNDERFLOW; break; }
                 if (win_state >= 0 && (win_state == 0 || t + dt > win_t + win_w)) {
                     // (re)build the drive window starting at this step; shrink until the check passes
@@ -784,6 +866,8 @@ struct Kern {
                             win_state = 1;
                             CTL_ST(C_WINT, win_t);
                             CTL_ST(C_WINW, win_w);
+                            win_sc = 2.0 / win_w;
+                            CTL_ST(C_WINSC, win_sc);
                             CTL_ST(C_WINNEXT, werr <= QSIM_WIN_TOL / 64.0 ? fmin(1.5 * wt, 128.0 * dt) : wt);
                             break;
                         }
@@ -795,7 +879,10 @@ struct Kern {
                     }
                 }
                 QSIM_TICK(1)
-                compute_tables<5>(a, g, smem_gen, t, dt, false, 0, win_state == 1, win_t, win_w);
+                if (a.fast_tables && win_state == 1)
+                    fast_tables(a, g, t, dt, win_t, win_sc);
+                else
+                    compute_tables<5>(a, g, smem_gen, t, dt, false, 0, win_state == 1, win_t, win_w);
                 QSIM_TICK(2)
                 QSIM_LAUNDER_ELL();
                 int nsave_hi = nsave;
@@ -821,6 +908,7 @@ struct Kern {
                         load_batch(sc_u0 + (size_t)(2 * cur) * sbuf, n, col0, row_of, row_ok, u);
                         load_batch(sc_k0 + (size_t)(2 * cur) * sbuf, n, col0, row_of, row_ok, k1);
                     }
+                    Vec part;  // partial combination of the next stage, formed while the current stage's operands load
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         const double ax = A21 * k1[e].x, ay = A21 * k1[e].y;
@@ -828,77 +916,82 @@ struct Kern {
                     }
                     put_stage(a, g, tmp, yb0, my_off, row_ok);
                     QSIM_TICK(4)
-                    apply(a, V0, yb0, ell, row_of, tmp, k2);
+                    apply(a, V0, yb0, ell, row_of, tmp, k2, [&] {
+#pragma unroll
+                        for (int e = 0; e < E; e++) part[e] = make_double2(A31 * k1[e].x, A31 * k1[e].y);
+                    });
                     QSIM_TICK(5)
 #pragma unroll
                     for (int e = 0; e < E; e++) {
-                        double ax = A31 * k1[e].x, ay = A31 * k1[e].y;
-                        ax += A32 * k2[e].x; ay += A32 * k2[e].y;
+                        const double ax = fma(A32, k2[e].x, part[e].x), ay = fma(A32, k2[e].y, part[e].y);
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
-                    apply(a, V1, yb1, ell, row_of, tmp, k3);
+                    apply(a, V1, yb1, ell, row_of, tmp, k3, [&] {
+#pragma unroll
+                        for (int e = 0; e < E; e++)
+                            part[e] = make_double2(fma(A42, k2[e].x, A41 * k1[e].x), fma(A42, k2[e].y, A41 * k1[e].y));
+                    });
 #pragma unroll
                     for (int e = 0; e < E; e++) {
-                        double ax = A41 * k1[e].x, ay = A41 * k1[e].y;
-                        ax += A42 * k2[e].x; ay += A42 * k2[e].y;
-                        ax += A43 * k3[e].x; ay += A43 * k3[e].y;
+                        const double ax = fma(A43, k3[e].x, part[e].x), ay = fma(A43, k3[e].y, part[e].y);
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb0, my_off, row_ok);
-                    apply(a, V2, yb0, ell, row_of, tmp, k4);
+                    apply(a, V2, yb0, ell, row_of, tmp, k4, [&] {
+#pragma unroll
+                        for (int e = 0; e < E; e++)
+                            part[e] = make_double2(fma(A53, k3[e].x, fma(A52, k2[e].x, A51 * k1[e].x)),
+                                                   fma(A53, k3[e].y, fma(A52, k2[e].y, A51 * k1[e].y)));
+                    });
 #pragma unroll
                     for (int e = 0; e < E; e++) {
-                        double ax = A51 * k1[e].x, ay = A51 * k1[e].y;
-                        ax += A52 * k2[e].x; ay += A52 * k2[e].y;
-                        ax += A53 * k3[e].x; ay += A53 * k3[e].y;
-                        ax += A54 * k4[e].x; ay += A54 * k4[e].y;
+                        const double ax = fma(A54, k4[e].x, part[e].x), ay = fma(A54, k4[e].y, part[e].y);
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
-                    apply(a, V3, yb1, ell, row_of, tmp, k5);
+                    apply(a, V3, yb1, ell, row_of, tmp, k5, [&] {
+#pragma unroll
+                        for (int e = 0; e < E; e++)
+                            part[e] = make_double2(
+                                fma(A64, k4[e].x, fma(A63, k3[e].x, fma(A62, k2[e].x, A61 * k1[e].x))),
+                                fma(A64, k4[e].y, fma(A63, k3[e].y, fma(A62, k2[e].y, A61 * k1[e].y))));
+                    });
 #pragma unroll
                     for (int e = 0; e < E; e++) {
-                        double ax = A61 * k1[e].x, ay = A61 * k1[e].y;
-                        ax += A62 * k2[e].x; ay += A62 * k2[e].y;
-                        ax += A63 * k3[e].x; ay += A63 * k3[e].y;
-                        ax += A64 * k4[e].x; ay += A64 * k4[e].y;
-                        ax += A65 * k5[e].x; ay += A65 * k5[e].y;
+                        const double ax = fma(A65, k5[e].x, part[e].x), ay = fma(A65, k5[e].y, part[e].y);
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb0, my_off, row_ok);
-                    apply(a, V4, yb0, ell, row_of, tmp, k6);
+                    apply(a, V4, yb0, ell, row_of, tmp, k6, [&] {
+#pragma unroll
+                        for (int e = 0; e < E; e++)
+                            part[e] = make_double2(
+                                fma(A75, k5[e].x, fma(A74, k4[e].x, fma(A73, k3[e].x, fma(A72, k2[e].x, A71 * k1[e].x)))),
+                                fma(A75, k5[e].y, fma(A74, k4[e].y, fma(A73, k3[e].y, fma(A72, k2[e].y, A71 * k1[e].y)))));
+                    });
 #pragma unroll
                     for (int e = 0; e < E; e++) {
-                        double ax = A71 * k1[e].x, ay = A71 * k1[e].y;
-                        ax += A72 * k2[e].x; ay += A72 * k2[e].y;
-                        ax += A73 * k3[e].x; ay += A73 * k3[e].y;
-                        ax += A74 * k4[e].x; ay += A74 * k4[e].y;
-                        ax += A75 * k5[e].x; ay += A75 * k5[e].y;
-                        ax += A76 * k6[e].x; ay += A76 * k6[e].y;
+                        const double ax = fma(A76, k6[e].x, part[e].x), ay = fma(A76, k6[e].y, part[e].y);
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);  // u_new
                     }
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
-                    apply(a, V4, yb1, ell, row_of, tmp, k7);
+                    // while stage 7's operands load: the k1..k6 part of the error combination
+                    double ex[E], ey[E];
+                    apply(a, V4, yb1, ell, row_of, tmp, k7, [&] {
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            ex[e] = fma(BT6, k6[e].x, fma(BT5, k5[e].x, fma(BT4, k4[e].x, fma(BT3, k3[e].x, fma(BT2, k2[e].x, BT1 * k1[e].x)))));
+                            ey[e] = fma(BT6, k6[e].y, fma(BT5, k5[e].y, fma(BT4, k4[e].y, fma(BT3, k3[e].y, fma(BT2, k2[e].y, BT1 * k1[e].y)))));
+                        }
+                    });
                     QSIM_TICK(6)
                     {
                         // Error norm: sum over this lane's entries of |u~|^2 / (abstol + max(|u|,|u_new|) reltol)^2.
                         // Written operation by operation across the entries so the independent per-entry
                         // chains (combination, reciprocal square root, reciprocal) overlap instead of running
                         // back to back.
-                        double ex[E], ey[E], m2[E], ys[E], hx[E], dn[E], yr[E];
-#pragma unroll
-                        for (int e = 0; e < E; e++) { ex[e] = BT1 * k1[e].x; ey[e] = BT1 * k1[e].y; }
-#pragma unroll
-                        for (int e = 0; e < E; e++) { ex[e] = fma(BT2, k2[e].x, ex[e]); ey[e] = fma(BT2, k2[e].y, ey[e]); }
-#pragma unroll
-                        for (int e = 0; e < E; e++) { ex[e] = fma(BT3, k3[e].x, ex[e]); ey[e] = fma(BT3, k3[e].y, ey[e]); }
-#pragma unroll
-                        for (int e = 0; e < E; e++) { ex[e] = fma(BT4, k4[e].x, ex[e]); ey[e] = fma(BT4, k4[e].y, ey[e]); }
-#pragma unroll
-                        for (int e = 0; e < E; e++) { ex[e] = fma(BT5, k5[e].x, ex[e]); ey[e] = fma(BT5, k5[e].y, ey[e]); }
-#pragma unroll
-                        for (int e = 0; e < E; e++) { ex[e] = fma(BT6, k6[e].x, ex[e]); ey[e] = fma(BT6, k6[e].y, ey[e]); }
+                        double m2[E], ys[E], hx[E], dn[E], yr[E];
 #pragma unroll
                         for (int e = 0; e < E; e++) { ex[e] = fma(BT7, k7[e].x, ex[e]); ey[e] = fma(BT7, k7[e].y, ey[e]); }
 #pragma unroll
@@ -970,7 +1063,7 @@ struct Kern {
                 }
                 if (e2 <= 1.0) {
                     st.n_accept++;
-                    const double r = fmin(a.qmax, fmax(a.qmin, a.gamma * ra * qold_pow));
+                    const double r = pmin(a.qmax, pmax(a.qmin, a.gamma * ra * qold_pow));
                     CTL_ST(C_QOLDPOW, e2 >= qinit2 ? rb : qinit_pow);  // qold = max(EEst, qoldinit)
                     if (!a.streamed) {
                         if (nsave_hi > nsave && (RS || g.warp_in_team < a.n_batches))
@@ -994,7 +1087,7 @@ struct Kern {
                 } else {
                     st.n_reject++;
                     // dt / min(1/qmin, q11/gamma), q11 = EEst^beta1
-                    dt = dt * fmax(a.qmin, a.gamma * ra);
+                    dt = dt * pmax(a.qmin, a.gamma * ra);
                 }
             }
 #ifdef QSIM_TIMING
@@ -1055,6 +1148,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         row0 = le - g_idx * n;
     }
     g.colofs = g_idx * CPL;
+    g.stage_c = kStageC[g.lane < 5 ? g.lane : 4];
 
     // ---- shared memory map (byte addresses) ----
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
