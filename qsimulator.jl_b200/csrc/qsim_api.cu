@@ -403,7 +403,7 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
     return cost;
 }
 
-static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int imag, int rs) {
+static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int vm, int rs) {
     const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c1_t288, variants_r1c3_t128,
                                               variants_r1c3_t288, variants_r2c1_t128, variants_r2c1_t288,
                                               variants_r2c2_t128, variants_r2c2_t288, variants_r3c1_t128,
@@ -414,7 +414,7 @@ static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int bloc
         const KernelVariant *v = fn(&cnt);
         for (int i = 0; i < cnt; i++)
             if (v[i].rpl == rpl && v[i].cpl == cpl && (rs || v[i].maxnnz >= max_nnz) && v[i].maxt >= block &&
-                v[i].imag == imag && v[i].rs == rs) {
+                v[i].vm == vm && v[i].rs == rs) {
                 // smallest row capacity, then smallest block bound, then the preferred occupancy target
                 auto key = [&](const KernelVariant &k) { return std::make_tuple(k.maxnnz, k.maxt); };
                 if (!best || key(v[i]) < key(*best)) best = &v[i];
@@ -473,7 +473,18 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         if (v >= 1 && v <= 15 && v * pl.team_warps * 32 <= 288) pl.teams_per_cta = v;
     }
     pl.block = pl.team_warps * 32 * pl.teams_per_cta;
-    pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block, g.imag_only ? 1 : 0, pl.rowsplit);
+    // value mode: 2 when the generator is purely imaginary and only diagonal entries depend on time
+    int vm = g.imag_only ? 1 : 0;
+    if (vm == 1 && !pl.rowsplit) {
+        bool static_off = true;
+        for (int j = 1; j < g.max_nnz && static_off; j++)
+            for (int r = 0; r < n; r++) {
+                const uint32_t sl = g.ell[(size_t)j * n + r] >> 16;
+                if (sl != 0xFFFFu && (int)sl < g.n_dyn_slots) static_off = false;
+            }
+        if (static_off && find_variant(rpl, cpl, g.max_nnz, pl.block, 2, 0)) vm = 2;
+    }
+    pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block, vm, pl.rowsplit);
     if (!pl.kv)
         return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
                                               std::to_string(g.max_nnz) + ")");

@@ -5,7 +5,7 @@
 namespace qsim {
 
 struct KernelVariant {
-    int rpl, cpl, maxnnz, maxt, minb, imag, rs;
+    int rpl, cpl, maxnnz, maxt, minb, vm, rs;  // vm: value mode (0 complex, 1 imaginary, 2 imaginary + static off-diagonals)
     const char *name;
     launch_fn launch;
     cudaError_t (*occupancy)(int block, size_t smem, int *ctas_per_sm);
@@ -22,14 +22,14 @@ QSIM_DECLARE(variants_rowsplit)
 
 #define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \
     {                                                                                                     \
-        R, C, M, T, B, I, 0, "tsit5_r" #R "c" #C "_nnz" #M "_t" #T "_im" #I,                                \
-            launch_solver<R, C, M, T, B, (I != 0), false>, occupancy_solver<R, C, M, T, B, (I != 0), false> \
+        R, C, M, T, B, I, 0, "tsit5_r" #R "c" #C "_nnz" #M "_t" #T "_vm" #I,                                \
+            launch_solver<R, C, M, T, B, I, false>, occupancy_solver<R, C, M, T, B, I, false>               \
     }
 // row-split variants: rows spread over the team's warps, sparse rows streamed from global memory
 #define QSIM_VARIANT_RS(I)                                                                                \
     {                                                                                                     \
-        3, 1, 1, 288, 1, I, 1, "tsit5_rowsplit_r3c1_t288_im" #I, launch_solver<3, 1, 1, 288, 1, (I != 0), true>, \
-            occupancy_solver<3, 1, 1, 288, 1, (I != 0), true>                                             \
+        3, 1, 1, 288, 1, I, 1, "tsit5_rowsplit_r3c1_t288_vm" #I, launch_solver<3, 1, 1, 288, 1, I, true>,    \
+            occupancy_solver<3, 1, 1, 288, 1, I, true>                                                    \
     }
 
 // Row capacities 5 / 9 / 12 / 16: the generator rows are padded to the variant's capacity and applied
@@ -37,8 +37,8 @@ QSIM_DECLARE(variants_rowsplit)
 #define QSIM_DEFINE_VARIANTS(FN, R, C, T, B)                                                              \
     const KernelVariant *FN(int *count) {                                                                 \
         static const KernelVariant v[] = {                                                                \
-            QSIM_VARIANT(R, C, 5, T, B, 0),  QSIM_VARIANT(R, C, 5, T, B, 1),                              \
-            QSIM_VARIANT(R, C, 9, T, B, 0),  QSIM_VARIANT(R, C, 9, T, B, 1),                              \
+            QSIM_VARIANT(R, C, 5, T, B, 0),  QSIM_VARIANT(R, C, 5, T, B, 1),  QSIM_VARIANT(R, C, 5, T, B, 2),   \
+            QSIM_VARIANT(R, C, 9, T, B, 0),  QSIM_VARIANT(R, C, 9, T, B, 1),  QSIM_VARIANT(R, C, 9, T, B, 2),   \
             QSIM_VARIANT(R, C, 12, T, B, 0), QSIM_VARIANT(R, C, 12, T, B, 1),                             \
             QSIM_VARIANT(R, C, 16, T, B, 0), QSIM_VARIANT(R, C, 16, T, B, 1)};                            \
         *count = (int)(sizeof(v) / sizeof(v[0]));                                                         \

@@ -260,8 +260,13 @@ struct Geo {
 // RS (row split): the rows of one column are spread over all warps of the team (n > 96, e.g. the
 // d^2 = 729 Lindblad propagator): stage buffers are team-wide, stage exchange uses the team barrier,
 // every warp visits every column, and the sparse rows are read from global memory (L1-resident).
-template <int RPL, int CPL, int MAXNNZ, bool IM, bool RS>
+// VM (value mode): 0 complex value slots; 1 purely imaginary generator (slots hold Im A, 2 DFMA per
+// multiply-add); 2 as 1 with every off-diagonal entry time-independent: those values live in registers for
+// the whole trajectory and only the diagonal is read from the per-stage table.
+template <int RPL, int CPL, int MAXNNZ, int VM, bool RS>
 struct Kern {
+    static constexpr bool IM = VM >= 1;
+    static constexpr bool SV = VM == 2;
     static constexpr int E = RPL * CPL;
     static constexpr uint32_t VB = IM ? 8u : 16u;  // bytes per value slot (IM: imaginary part only)
     typedef double2 Vec[E];
@@ -580,8 +585,8 @@ struct Kern {
     // there (the next stage's partial combination) executes under the shared-memory latency.
     template <typename Hook = NoHook>
     static __device__ __forceinline__ void apply(const LaunchArgs &a, uint32_t Vs, uint32_t yb,
-                                                 const uint32_t (&ell)[RPL][MAXNNZ], const int (&row_of)[RPL],
-                                                 const Vec &yreg, Vec &k, Hook hook = Hook()) {
+                                                 const uint32_t (&ell)[RPL][MAXNNZ], const double (&vstat)[RPL][MAXNNZ],
+                                                 const int (&row_of)[RPL], const Vec &yreg, Vec &k, Hook hook = Hook()) {
 #pragma unroll
         for (int i = 0; i < RPL; i++) {
             double2 acc[CPL];
@@ -603,7 +608,9 @@ struct Kern {
 #pragma unroll
                 for (int j = 0; j < MAXNNZ; j++) {
                     const uint32_t e = ell[i][j];
-                    if (IM)
+                    if (SV && j > 0)
+                        vv[j].y = vstat[i][j];  // time-independent off-diagonal value, loaded once per trajectory
+                    else if (IM)
                         vv[j].y = lds1(Vs + (e >> 16));
                     else
                         vv[j] = lds2(Vs + (e >> 16));
@@ -758,6 +765,11 @@ struct Kern {
         }
         team_sync(a.team_warps, g.bar_id);
         compute_tables<5>(a, g, smem_gen, t0, 0.0, true, 0);
+        double vstat[RPL][MAXNNZ];
+#pragma unroll
+        for (int i = 0; i < RPL; i++)
+#pragma unroll
+            for (int j = 0; j < MAXNNZ; j++) vstat[i][j] = (SV && j > 0) ? lds1(g.sm_V + (ell[i][j] >> 16)) : 0.0;
 
         Vec u, k1, k2, k3, k4, k5, k6, k7, tmp;
         int cur = 0;
@@ -776,7 +788,7 @@ struct Kern {
                 initial_state(a, traj, col0, row_of, row_ok, u);
                 for (int ks = 0; ks < nsave; ks++) write_out(a, traj, ks, col0, row_of, row_ok, u);
                 put_stage(a, g, u, yb0, my_off, row_ok);
-                apply(a, V0, yb0, ell, row_of, u, k1);
+                apply(a, V0, yb0, ell, vstat, row_of, u, k1);
                 if (a.streamed) {
                     store_batch(sc_u0, n, col0, row_of, row_ok, u);
                     store_batch(sc_k0, n, col0, row_of, row_ok, k1);
@@ -804,7 +816,7 @@ struct Kern {
 #pragma unroll
                 for (int e = 0; e < E; e++) tmp[e] = make_double2(u[e].x + dt0 * k1[e].x, u[e].y + dt0 * k1[e].y);
                 put_stage(a, g, tmp, yb1, my_off, row_ok);
-                apply(a, V1, yb1, ell, row_of, tmp, k2);
+                apply(a, V1, yb1, ell, vstat, row_of, tmp, k2);
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     const double sk = a.abstol + sqrt(u[e].x * u[e].x + u[e].y * u[e].y) * a.reltol;
@@ -916,7 +928,7 @@ struct Kern {
                     }
                     put_stage(a, g, tmp, yb0, my_off, row_ok);
                     QSIM_TICK(4)
-                    apply(a, V0, yb0, ell, row_of, tmp, k2, [&] {
+                    apply(a, V0, yb0, ell, vstat, row_of, tmp, k2, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++) part[e] = make_double2(A31 * k1[e].x, A31 * k1[e].y);
                     });
@@ -927,7 +939,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
-                    apply(a, V1, yb1, ell, row_of, tmp, k3, [&] {
+                    apply(a, V1, yb1, ell, vstat, row_of, tmp, k3, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++)
                             part[e] = make_double2(fma(A42, k2[e].x, A41 * k1[e].x), fma(A42, k2[e].y, A41 * k1[e].y));
@@ -938,7 +950,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb0, my_off, row_ok);
-                    apply(a, V2, yb0, ell, row_of, tmp, k4, [&] {
+                    apply(a, V2, yb0, ell, vstat, row_of, tmp, k4, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++)
                             part[e] = make_double2(fma(A53, k3[e].x, fma(A52, k2[e].x, A51 * k1[e].x)),
@@ -950,7 +962,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
-                    apply(a, V3, yb1, ell, row_of, tmp, k5, [&] {
+                    apply(a, V3, yb1, ell, vstat, row_of, tmp, k5, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++)
                             part[e] = make_double2(
@@ -963,7 +975,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb0, my_off, row_ok);
-                    apply(a, V4, yb0, ell, row_of, tmp, k6, [&] {
+                    apply(a, V4, yb0, ell, vstat, row_of, tmp, k6, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++)
                             part[e] = make_double2(
@@ -978,7 +990,7 @@ struct Kern {
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
                     // while stage 7's operands load: the k1..k6 part of the error combination
                     double ex[E], ey[E];
-                    apply(a, V4, yb1, ell, row_of, tmp, k7, [&] {
+                    apply(a, V4, yb1, ell, vstat, row_of, tmp, k7, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++) {
                             ex[e] = fma(BT6, k6[e].x, fma(BT5, k5[e].x, fma(BT4, k4[e].x, fma(BT3, k3[e].x, fma(BT2, k2[e].x, BT1 * k1[e].x)))));
@@ -1124,10 +1136,11 @@ struct Kern {
 // up to 255 registers so nothing spills; 288: teams of up to 9 warps, 168 registers).
 // MINB: minimum resident CTAs per SM the register allocation must allow; IM: purely imaginary generator
 // (unitary evolution under a real Hamiltonian): value slots hold Im(A) only, 2 DFMA per multiply-add.
-template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM, bool RS>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS>
 __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant__ LaunchArgs a) {
     extern __shared__ __align__(16) double smem[];
-    typedef Kern<RPL, CPL, MAXNNZ, IM, RS> K;
+    typedef Kern<RPL, CPL, MAXNNZ, VM, RS> K;
+    constexpr bool IM = VM >= 1;
     const int n = a.g.n;
     Geo g;
     g.lane = threadIdx.x & 31;
@@ -1252,22 +1265,22 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
 // Host-side launcher for one (RPL, CPL, MAXNNZ) instantiation.
 typedef cudaError_t (*launch_fn)(const LaunchArgs &, int grid, int block, size_t smem, cudaStream_t);
 
-template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM, bool RS>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS>
 cudaError_t launch_solver(const LaunchArgs &a, int grid, int block, size_t smem, cudaStream_t stream) {
     if (block > MAXT) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM, RS>,
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM, RS><<<grid, block, smem, stream>>>(a);
+    solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS><<<grid, block, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, bool IM, bool RS>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS>
 cudaError_t occupancy_solver(int block, size_t smem, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM, RS>,
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, IM, RS>,
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS>,
                                                          block, smem);
 }
 
