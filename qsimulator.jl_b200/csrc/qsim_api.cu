@@ -777,6 +777,18 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.reltol = o.reltol; a.abstol = o.abstol; a.gamma = o.gamma; a.qmin = o.qmin; a.qmax = o.qmax;
     a.beta1 = o.beta1; a.beta2 = o.beta2; a.qoldinit = o.qoldinit; a.dtmax = o.dtmax;
     a.maxiters = o.maxiters > 0 ? o.maxiters : 1000000;
+    for (int w = 0; w < 2; w++) {
+        const double pw = w == 0 ? -0.5 * o.beta1 : 0.5 * o.beta2;
+        for (int idx = 0; idx < 16; idx++) {
+            const double cc = 1.03125 + 0.0625 * idx;
+            double coef = std::pow(cc, pw);
+            for (int k = 0; k < QSIM_POW_K; k++) {
+                a.pow_coef[w][idx][k] = coef;
+                coef = coef * (pw - k) / ((k + 1) * cc);  // binom(p, k+1) c^(p-k-1)
+            }
+        }
+        for (int e = 0; e < QSIM_POW_NE; e++) a.pow_exp2[w][e] = std::exp2(pw * (double)(e + QSIM_POW_EMIN));
+    }
 
     CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), stream));
     CU(pl.kv->launch(a, pl.grid, pl.block, pl.smem, stream));

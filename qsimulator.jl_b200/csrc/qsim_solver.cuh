@@ -76,6 +76,11 @@ struct LaunchArgs {
     int fast_chA, fast_chB;
     int off_dptr, off_dw, off_drec;  // byte offsets inside the common region (after tables, Chebyshev, power tables)
     const double *dyn_rec;           // [n_dyn_slots][8] records {w0, w1, w2 (double2), ch0, ch1, ch2, pad (int)}
+    // Controller power tables (kernel parameters live in the constant bank; the index is warp-uniform):
+    // Taylor coefficients of m^p about the centres of 16 sub-intervals of [1,2) and 2^(pE), for
+    // p = -beta1/2 (first) and p = +beta2/2 (second).  Filled on the host per call.
+    double pow_coef[2][16][10];
+    double pow_exp2[2][128];
     int team_bytes;       // shared bytes per team
     double reltol, abstol, gamma, qmin, qmax, beta1, beta2, qoldinit, dtmax;
     long long maxiters;
@@ -228,6 +233,7 @@ __device__ __forceinline__ double team_max(double v, uint32_t red, int team_warp
 #define QSIM_POW_EMIN (-80)     // controller power tables cover EEst^2 in [2^-80, 2^48)
 #define QSIM_POW_NE 128
 #define QSIM_POW_K 10          // Taylor coefficients per mantissa sub-interval (16 sub-intervals of [1,2))
+static_assert(QSIM_POW_NE == 128 && QSIM_POW_K == 10, "LaunchArgs::pow_coef / pow_exp2 are sized for these");
 #ifdef QSIM_TIMING   // development build: per-phase cycle counts of trajectory 0 (printed from the kernel)
 #define QSIM_TICK(i) { const long long c_ = clock64(); tk_[i] += c_ - tl_; tl_ = c_; }
 #else
@@ -277,22 +283,21 @@ struct Kern {
     // x^(-beta1/2) and x^(beta2/2) for x = EEst^2: split x = m 2^E, a degree-9 Taylor polynomial of m^p about the
     // centre of m's sub-interval (16 per octave; remainder < 1e-17 relative) times a tabulated 2^(pE).  Replaces a
     // log and an exp on the per-step critical path; false outside the tabulated exponent range (0, inf, nan too).
-    static __device__ __forceinline__ bool pow_pair(const Geo &g, double x, double &ra, double &rb) {
+    static __device__ __forceinline__ bool pow_pair(const LaunchArgs &a, double x, double &ra, double &rb) {
         const long long b = __double_as_longlong(x);
         const int ex = (int)((b >> 52) & 0x7ff) - 1023;
         if (b < 0 || ex < QSIM_POW_EMIN || ex >= QSIM_POW_EMIN + QSIM_POW_NE) return false;
         const int idx = (int)((b >> 48) & 15);
         const double m = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
         const double t = m - (1.03125 + 0.0625 * idx);
-        const uint32_t pa = g.sm_pow + 8u * QSIM_POW_K * idx, pb = pa + 8u * QSIM_POW_K * 16;
-        const uint32_t te = g.sm_pow + 8u * QSIM_POW_K * 32 + 8u * (ex - QSIM_POW_EMIN);
+
         double ca[QSIM_POW_K], cb[QSIM_POW_K];
 #pragma unroll
-        for (int k = 0; k < QSIM_POW_K; k++) {  // all loads in flight before the first use
-            ca[k] = lds1(pa + 8 * k);
-            cb[k] = lds1(pb + 8 * k);
+        for (int k = 0; k < QSIM_POW_K; k++) {  // constant-bank loads with a warp-uniform index
+            ca[k] = a.pow_coef[0][idx][k];
+            cb[k] = a.pow_coef[1][idx][k];
         }
-        const double ta = lds1(te), tb = lds1(te + 8u * QSIM_POW_NE);
+        const double ta = a.pow_exp2[0][ex - QSIM_POW_EMIN], tb = a.pow_exp2[1][ex - QSIM_POW_EMIN];
         // Estrin evaluation of the two degree-9 polynomials (dependency depth 5 instead of 9)
         static_assert(QSIM_POW_K == 10, "Estrin scheme below is written for 10 coefficients");
         const double t2 = t * t, t4 = t2 * t2, t8 = t4 * t4;
@@ -1063,7 +1068,7 @@ struct Kern {
                 if (!isfinite(e2)) { st.retcode = QSIM_RET_NONFINITE; break; }
                 // ra = EEst^-beta1, rb = EEst^beta2 (EEst = sqrt(e2)) from the power tables; libm outside their range
                 double ra, rb;
-                if (!pow_pair(g, e2, ra, rb)) {
+                if (!pow_pair(a, e2, ra, rb)) {
                     if (e2 == 0.0) {
                         ra = 1e300;   // "q = 1/qmax": largest growth after the clamp
                         rb = 0.0;
@@ -1190,20 +1195,6 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         const double *src = reinterpret_cast<const double *>(a.g.tab);
         for (int i = threadIdx.x; i < (int)(sizeof(SeriesTables) / 8); i += blockDim.x) sts1(g.sm_tab + 8 * i, src[i]);
         for (int i = threadIdx.x; i < QSIM_NN * QSIM_NN + QSIM_NN + 3; i += blockDim.x) sts1(g.sm_cheb + 8 * i, a.cheb[i]);
-        // controller power tables: p = -beta1/2 (first) and +beta2/2 (second)
-        for (int i = threadIdx.x; i < 32; i += blockDim.x) {
-            const int idx = i & 15;
-            const double p = i < 16 ? -0.5 * a.beta1 : 0.5 * a.beta2, c = 1.03125 + 0.0625 * idx;
-            double coef = pow(c, p);
-            for (int k = 0; k < QSIM_POW_K; k++) {
-                sts1(g.sm_pow + 8u * (QSIM_POW_K * i + k), coef);
-                coef = coef * (p - k) / ((k + 1) * c);  // binom(p, k+1) c^(p-k-1)
-            }
-        }
-        for (int i = threadIdx.x; i < 2 * QSIM_POW_NE; i += blockDim.x) {
-            const double p = i < QSIM_POW_NE ? -0.5 * a.beta1 : 0.5 * a.beta2;
-            sts1(g.sm_pow + 8u * (QSIM_POW_K * 32 + i), exp2(p * (double)((i % QSIM_POW_NE) + QSIM_POW_EMIN)));
-        }
         if (a.dyn_fast)
             for (int i = threadIdx.x; i < 8 * a.g.n_dyn_slots; i += blockDim.x) sts1(g.sm_drec + 8 * i, a.dyn_rec[i]);
         int *dptr = reinterpret_cast<int *>(smem) + a.off_dptr / 4;
