@@ -119,7 +119,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = max(cores, min(4096, 4 * cores))
+    n_sample = max(cores, min(4096, 12 * cores))   # ~8 s of CPU work per step (0.7 s per trajectory per core)
     for _ in range(args.warmup):
         cpu_reference_run(min(n_sample, cores), cores)
     times = []
@@ -258,7 +258,7 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_sample = max(cores, min(4096, 4 * cores))
+        n_sample = max(cores, min(4096, 24 * cores))   # ~15-20 s of CPU work
         secs, _ = cpu_reference_run(n_sample, cores)
         cpu_base = {"value": n_sample / secs, "unit": "propagators/s", "cores": cores, "kind": "port",
                     "sample": f"{n_sample} of the 4096 sweep points (evenly spaced), full ts=0:200, {secs:.1f} s; "
@@ -282,8 +282,10 @@ def main():
                          "frac": achieved / peak_tflops if peak_tflops > 0 else None, "traffic": None,
                          "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                         "nominal 37.2)",
-                         "flop_counted": "executed sparse generator MACs only (8 flop each); RK stage combinations, "
-                                         "error norm and drive transcendentals not counted",
+                         "flop_counted": "executed sparse generator multiply-adds only (%d flop each: the generator is "
+                                         "%s); RK stage combinations, error norm and drive evaluation not counted"
+                                         % ((4, "purely imaginary, 2 DFMA per entry") if "_vm0" not in prob.kernel_name(which)
+                                            else (8, "complex, 4 DFMA per entry")),
                          "dense_equivalent_tflops": dense_flops_per_launch / (total_ms / args.steps * 1e-3) / 1e12,
                          "hbm_out_gbs": d_out.numel() * 16 / (total_ms / args.steps * 1e-3) / 1e9},
             "gpu_launches": int(launches), "clocks": clocks,
