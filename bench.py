@@ -142,6 +142,19 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def recorded_traffic(kernel, n_traj, n_ts):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+    capture of this kernel on this workload (profiles/traffic.json), or None when no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            for rec in json.load(f):
+                if rec["kernel"] == kernel and rec["points"] == n_traj and rec["n_ts"] == n_ts:
+                    return rec["dram_bytes_read"] + rec["dram_bytes_write"], rec["source"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,6 +281,7 @@ def main():
         ms_per_step = total_ms_max / args.steps
         value = n_traj * world / (ms_per_step * 1e-3)
         achieved = flops_per_launch / (total_ms / args.steps * 1e-3) / 1e12
+        traffic, traffic_src = recorded_traffic(prob.kernel_name(which), n_traj, len(ts))
         line = {
             "metric": METRIC, "value": value, "unit": "propagators/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -279,7 +293,8 @@ def main():
                        "streams 1.07 GB of results", "attempted_steps_per_launch": attempts,
                        "unitarity_err_final": unit_err},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops if peak_tflops > 0 else None, "traffic": None,
+                         "frac": achieved / peak_tflops if peak_tflops > 0 else None,
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch", "traffic_source": traffic_src,
                          "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                         "nominal 37.2)",
                          "flop_counted": "executed sparse generator multiply-adds only (%d flop each: the generator is "

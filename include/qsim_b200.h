@@ -246,6 +246,21 @@ int qsim_me_state(qsim_ctx *ctx, qsim_problem *prob, int64_t n_traj,
                   const qsim_solver_opts *opts, double *out,
                   qsim_traj_stats *stats);
 
+/* Reduced output: the same solves, but only selected entries of each saved
+ * result leave the device -- what every sweep in the reference's notebooks keeps of a propagator
+ * (populations abs2(u[i,j]), the qubit-subspace block; doc/Examples.ipynb cells 14-15, 31, 34-38,
+ * test/test_time_evolution.jl:56-57,72).  which: 0 unitary_propagator, 1 unitary_state, 2 me_propagator,
+ * 3 me_state.  Entry i is (sel_rows[i], sel_cols[i]) of the saved matrix (0-based; which = 1 saves a
+ * vector and ignores sel_cols; which = 3 addresses the d*d density matrix, or, with sel_cols == NULL,
+ * its column-major linear index).  sel_rows / sel_cols are HOST arrays even with
+ * QSIM_FLAG_DEVICE_PTRS.  out[traj][k][n_sel]: complex (interleaved) when abs2 == 0, real |entry|^2
+ * otherwise.  init / init_stride as in the state solvers (ignored for propagators).                  */
+int qsim_solve_selected(qsim_ctx *ctx, qsim_problem *prob, int which, int64_t n_traj,
+                        const double *params, const double *ts, int n_ts, int64_t ts_stride,
+                        const double *init, int64_t init_stride, const qsim_solver_opts *opts,
+                        int n_sel, const int32_t *sel_rows, const int32_t *sel_cols, int abs2,
+                        double *out, qsim_traj_stats *stats);
+
 /* Executed FP64 flop of the generator application per right-hand-side call of
  * one trajectory (8 flop per complex multiply-add actually issued; 4 when the
  * generator is purely imaginary, i.e. a real Hamiltonian), for the roofline

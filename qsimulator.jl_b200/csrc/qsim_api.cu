@@ -63,7 +63,7 @@ struct qsim_ctx {
     SeriesTables *d_tab = nullptr;
     double *d_cheb = nullptr;  // Chebyshev transform / nodes / check points for the drive windows
     unsigned long long *d_counter = nullptr;
-    DevBuf params, ts, init, out, stats, scratch;
+    DevBuf params, ts, init, out, stats, scratch, sel;
     int64_t launches = 0;
 };
 
@@ -150,7 +150,7 @@ int qsim_destroy(qsim_ctx *c) {
     if (!c) return QSIM_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->params.release(); c->ts.release(); c->init.release(); c->out.release(); c->stats.release(); c->scratch.release();
+    c->params.release(); c->ts.release(); c->init.release(); c->out.release(); c->stats.release(); c->scratch.release(); c->sel.release();
     cudaFree(c->d_tab);
     cudaFree(c->d_cheb);
     cudaFree(c->d_counter);
@@ -404,10 +404,10 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
 }
 
 static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int vm, int rs) {
-    const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c1_t288, variants_r1c3_t128,
-                                              variants_r1c3_t288, variants_r2c1_t128, variants_r2c1_t288,
-                                              variants_r2c2_t128, variants_r2c2_t288, variants_r3c1_t128,
-                                              variants_r3c1_t288, variants_rowsplit};
+    const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c3_t128, variants_r1c3_t256,
+                                              variants_r1c3_t288, variants_r2c1_t128, variants_r2c2_t128,
+                                              variants_r2c2_t256, variants_r3c1_t128, variants_r3c1_t256,
+                                              variants_rowsplit};
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
         int cnt = 0;
@@ -462,8 +462,9 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.streamed = 0;
         pl.team_warps = pl.n_batches;
     } else {
+        // streamed: eight warps share the batches (256 threads keep 255 registers per thread: no spills)
         pl.streamed = 1;
-        pl.team_warps = 9;
+        pl.team_warps = 8;
     }
     // one-warp teams: 4 per CTA (128 threads, 2 CTAs = 8 warps per SM when the kernel needs > 168 registers:
     // no spills; spilled variants at 10-12 warps per SM are ~1.7x slower per warp)
@@ -621,9 +622,15 @@ static int ensure_device_copy(qsim_ctx *c, qsim_problem *p, int w) {
     return QSIM_OK;
 }
 
+struct Selection {
+    int n_sel = 0, abs2 = 0;
+    const int32_t *rows = nullptr, *cols = nullptr;
+};
+
 static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj, const double *params,
                         const double *ts, int n_ts, int64_t ts_stride, const double *init, int64_t init_stride,
-                        const qsim_solver_opts *opts_in, double *out, qsim_traj_stats *stats) {
+                        const qsim_solver_opts *opts_in, double *out, qsim_traj_stats *stats,
+                        const Selection *sel = nullptr) {
     if (!c) return fail(QSIM_ERR_NO_DEVICE, "ctx is NULL: create one with qsim_create (needs a CUDA device; no CPU fallback)");
     if (!p) return fail(QSIM_ERR_ARG, "prob is NULL");
     if (n_traj < 0) return fail(QSIM_ERR_ARG, "n_traj < 0");
@@ -688,11 +695,28 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     const size_t b_params = sizeof(double) * (size_t)std::max(p->n_params, 1) * n_traj;
     const size_t b_ts = sizeof(double) * (size_t)(ts_stride ? ts_stride * n_traj : n_ts);
     const size_t b_init = init ? sizeof(double2) * (size_t)(init_stride ? init_stride * n_traj : g.n) : 0;
-    const size_t b_out = sizeof(double2) * n_state * n_ts * n_traj;
+    size_t b_out = sizeof(double2) * n_state * n_ts * n_traj;
     const size_t b_stats = sizeof(qsim_traj_stats) * n_traj;
 
     LaunchArgs a;
     std::memset(&a, 0, sizeof(a));
+    if (sel) {
+        // position table of the selected entries (column-major state index -> position, -1 elsewhere)
+        std::vector<int> index(n_state, -1);
+        for (int i = 0; i < sel->n_sel; i++) {
+            const int r = sel->rows[i], cc = sel->cols ? sel->cols[i] : 0;
+            if (r < 0 || r >= g.n || cc < 0 || cc >= pl.ncols) return fail(QSIM_ERR_ARG, "selected entry out of range");
+            if (index[(size_t)cc * g.n + r] >= 0) return fail(QSIM_ERR_ARG, "selected entries must be distinct");
+            index[(size_t)cc * g.n + r] = i;
+        }
+        CU(c->sel.reserve(sizeof(int) * n_state));
+        CU(cudaMemcpyAsync(c->sel.p, index.data(), sizeof(int) * n_state, cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));  // `index` is pageable and goes out of scope
+        a.sel_index = (const int *)c->sel.p;
+        a.n_sel = sel->n_sel;
+        a.sel_abs2 = sel->abs2;
+        b_out = (sel->abs2 ? sizeof(double) : sizeof(double2)) * (size_t)sel->n_sel * n_ts * n_traj;
+    }
     if (dev_ptrs) {
         a.params = params;
         a.ts = ts;
@@ -822,6 +846,33 @@ int qsim_me_state(qsim_ctx *ctx, qsim_problem *prob, int64_t n_traj, const doubl
                   int n_ts, int64_t ts_stride, const double *rho0, int64_t init_stride, const qsim_solver_opts *opts,
                   double *out, qsim_traj_stats *stats) {
     return solve_common(ctx, prob, 3, n_traj, params, ts, n_ts, ts_stride, rho0, init_stride, opts, out, stats);
+}
+int qsim_solve_selected(qsim_ctx *ctx, qsim_problem *prob, int which, int64_t n_traj, const double *params,
+                        const double *ts, int n_ts, int64_t ts_stride, const double *init, int64_t init_stride,
+                        const qsim_solver_opts *opts, int n_sel, const int32_t *sel_rows, const int32_t *sel_cols,
+                        int abs2, double *out, qsim_traj_stats *stats) {
+    if (which < 0 || which > 3) return fail(QSIM_ERR_ARG, "which must be 0..3");
+    if (n_sel < 1 || !sel_rows) return fail(QSIM_ERR_ARG, "need at least one selected entry");
+    if ((which == 0 || which == 2) && !sel_cols) return fail(QSIM_ERR_ARG, "propagator selections need sel_cols");
+    if (!prob) return fail(QSIM_ERR_ARG, "prob is NULL");
+    Selection sel;
+    sel.n_sel = n_sel;
+    sel.abs2 = abs2 ? 1 : 0;
+    sel.rows = sel_rows;
+    sel.cols = (which == 0 || which == 2) ? sel_cols : nullptr;
+    std::vector<int32_t> lin;
+    if (which == 3 && sel_cols) {
+        // entries of the d x d density matrix: the solver's state is vec(rho), column-major
+        lin.resize((size_t)n_sel);
+        for (int i = 0; i < n_sel; i++) {
+            if (sel_rows[i] < 0 || sel_rows[i] >= prob->d || sel_cols[i] < 0 || sel_cols[i] >= prob->d)
+                return fail(QSIM_ERR_ARG, "selected entry out of range");
+            lin[(size_t)i] = sel_cols[i] * prob->d + sel_rows[i];
+        }
+        sel.rows = lin.data();
+    }
+    return solve_common(ctx, prob, which, n_traj, params, ts, n_ts, ts_stride, (which == 1 || which == 3) ? init : nullptr,
+                        init_stride, opts, out, stats, &sel);
 }
 
 }  // extern "C"

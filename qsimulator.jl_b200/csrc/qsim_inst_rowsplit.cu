@@ -2,8 +2,9 @@
 #include "qsim_registry.h"
 namespace qsim {
 const KernelVariant *variants_rowsplit(int *count) {
-    static const KernelVariant v[] = {QSIM_VARIANT_RS(0), QSIM_VARIANT_RS(1)};
-    *count = 2;
+    static const KernelVariant v[] = {QSIM_VARIANT_RS(256, 0), QSIM_VARIANT_RS(256, 1), QSIM_VARIANT_RS(288, 0),
+                                      QSIM_VARIANT_RS(288, 1)};
+    *count = 4;
     return v;
 }
 }

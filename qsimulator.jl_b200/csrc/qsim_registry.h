@@ -13,11 +13,13 @@ struct KernelVariant {
 
 // defined one per translation unit (qsim_inst_*.cu) so the variants compile in parallel
 #define QSIM_DECLARE(FN) const KernelVariant *FN(int *count);
-QSIM_DECLARE(variants_r1c1_t128) QSIM_DECLARE(variants_r1c1_t288)
-QSIM_DECLARE(variants_r1c3_t128) QSIM_DECLARE(variants_r1c3_t288)
-QSIM_DECLARE(variants_r2c1_t128) QSIM_DECLARE(variants_r2c1_t288)
-QSIM_DECLARE(variants_r2c2_t128) QSIM_DECLARE(variants_r2c2_t288)
-QSIM_DECLARE(variants_r3c1_t128) QSIM_DECLARE(variants_r3c1_t288)
+// t128: four one-warp teams per CTA, two CTAs per SM.  t256: teams of 2-8 warps, one CTA per SM.  Both leave
+// 255 registers per thread (two warps per scheduler).  t288: nine-warp teams (27-level propagators), 168 registers.
+QSIM_DECLARE(variants_r1c1_t128)
+QSIM_DECLARE(variants_r1c3_t128) QSIM_DECLARE(variants_r1c3_t256) QSIM_DECLARE(variants_r1c3_t288)
+QSIM_DECLARE(variants_r2c1_t128)
+QSIM_DECLARE(variants_r2c2_t128) QSIM_DECLARE(variants_r2c2_t256)
+QSIM_DECLARE(variants_r3c1_t128) QSIM_DECLARE(variants_r3c1_t256)
 QSIM_DECLARE(variants_rowsplit)
 
 #define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \
@@ -26,10 +28,10 @@ QSIM_DECLARE(variants_rowsplit)
             launch_solver<R, C, M, T, B, I, false>, occupancy_solver<R, C, M, T, B, I, false>               \
     }
 // row-split variants: rows spread over the team's warps, sparse rows streamed from global memory
-#define QSIM_VARIANT_RS(I)                                                                                \
+#define QSIM_VARIANT_RS(T, I)                                                                             \
     {                                                                                                     \
-        3, 1, 1, 288, 1, I, 1, "tsit5_rowsplit_r3c1_t288_vm" #I, launch_solver<3, 1, 1, 288, 1, I, true>,    \
-            occupancy_solver<3, 1, 1, 288, 1, I, true>                                                    \
+        3, 1, 1, T, 1, I, 1, "tsit5_rowsplit_r3c1_t" #T "_vm" #I, launch_solver<3, 1, 1, T, 1, I, true>,      \
+            occupancy_solver<3, 1, 1, T, 1, I, true>                                                      \
     }
 
 // Row capacities 5 / 9 / 12 / 16: the generator rows are padded to the variant's capacity and applied

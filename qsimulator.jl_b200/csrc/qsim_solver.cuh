@@ -58,6 +58,10 @@ struct LaunchArgs {
     const double *params, *ts;
     const double2 *init;
     double2 *out;
+    // selected-entry output (qsim_solve_selected): sel_index[col*n + row] = position of the entry in the
+    // selection or -1; out is then [traj][k][n_sel] complex, or real |.|^2 when sel_abs2
+    const int *sel_index;
+    int n_sel, sel_abs2;
     qsim_traj_stats *stats;
     unsigned long long *work_counter;
     double2 *scratch;     // streamed mode: [n_teams_total][4][n_batches*cpb*n]
@@ -607,38 +611,69 @@ struct Kern {
 #pragma unroll 4
                 for (int j = 1; j < nnz; j++) mac(Vs, yb, __ldg(er + (size_t)j * stride), false, &yreg[i * CPL], acc);
             } else {
-                // no per-entry branch (short rows are padded with the zero slot): every operand of the row is
-                // requested before the first multiply-add, so a stage exposes one shared-memory latency
-                double2 vv[MAXNNZ], yy[MAXNNZ][CPL];
-#pragma unroll
-                for (int j = 0; j < MAXNNZ; j++) {
-                    const uint32_t e = ell[i][j];
-                    if (SV && j > 0)
-                        vv[j].y = vstat[i][j];  // time-independent off-diagonal value, loaded once per trajectory
-                    else if (IM)
-                        vv[j].y = lds1(Vs + (e >> 16));
+                // no per-entry branch (short rows are padded with the zero slot).  Operands are requested in
+                // chunks of up to four off-diagonal entries, all loads of a chunk ahead of its multiply-adds, so a
+                // row of five exposes one shared-memory latency and longer rows stay within the register budget.
+                {
+                    // diagonal entry: operand from the lane's own registers
+                    const uint32_t e = ell[i][0];
+                    double2 vd;
+                    if (IM)
+                        vd = make_double2(0.0, lds1(Vs + (e >> 16)));
                     else
-                        vv[j] = lds2(Vs + (e >> 16));
-                    if (j > 0) {
-#pragma unroll
-                        for (int c = 0; c < CPL; c++) yy[j][c] = lds2(yb + (e & 0xFFFFu) + 16 * c);
-                    }
-                }
-                if (i == RPL - 1) hook();
-#pragma unroll
-                for (int j = 0; j < MAXNNZ; j++) {
+                        vd = lds2(Vs + (e >> 16));
+                    if (i == RPL - 1 && MAXNNZ <= 1) hook();
 #pragma unroll
                     for (int c = 0; c < CPL; c++) {
-                        const double2 y = j == 0 ? yreg[i * CPL + c] : yy[j][c];
+                        const double2 y = yreg[i * CPL + c];
                         if (IM) {
                             // A = i B with B real: (iB)(yr + i yi) = -B yi + i B yr
-                            acc[c].x = fma(-vv[j].y, y.y, acc[c].x);
-                            acc[c].y = fma(vv[j].y, y.x, acc[c].y);
+                            acc[c].x = fma(-vd.y, y.y, acc[c].x);
+                            acc[c].y = fma(vd.y, y.x, acc[c].y);
                         } else {
-                            acc[c].x = fma(vv[j].x, y.x, acc[c].x);
-                            acc[c].y = fma(vv[j].x, y.y, acc[c].y);
-                            acc[c].x = fma(-vv[j].y, y.y, acc[c].x);
-                            acc[c].y = fma(vv[j].y, y.x, acc[c].y);
+                            acc[c].x = fma(vd.x, y.x, acc[c].x);
+                            acc[c].y = fma(vd.x, y.y, acc[c].y);
+                            acc[c].x = fma(-vd.y, y.y, acc[c].x);
+                            acc[c].y = fma(vd.y, y.x, acc[c].y);
+                        }
+                    }
+                }
+                constexpr int CH = 4;
+#pragma unroll
+                for (int j0 = 1; j0 < MAXNNZ; j0 += CH) {
+                    double2 vv[CH], yy[CH][CPL];
+#pragma unroll
+                    for (int q = 0; q < CH; q++) {
+                        const int j = j0 + q;
+                        if (j < MAXNNZ) {
+                            const uint32_t e = ell[i][j];
+                            if (SV)
+                                vv[q] = make_double2(0.0, vstat[i][j]);  // time-independent, loaded once per trajectory
+                            else if (IM)
+                                vv[q] = make_double2(0.0, lds1(Vs + (e >> 16)));
+                            else
+                                vv[q] = lds2(Vs + (e >> 16));
+#pragma unroll
+                            for (int c = 0; c < CPL; c++) yy[q][c] = lds2(yb + (e & 0xFFFFu) + 16 * c);
+                        }
+                    }
+                    if (i == RPL - 1 && j0 == 1) hook();
+#pragma unroll
+                    for (int q = 0; q < CH; q++) {
+                        if (j0 + q < MAXNNZ) {
+#pragma unroll
+                            for (int c = 0; c < CPL; c++) {
+                                const double2 y = yy[q][c];
+                                if (IM) {
+                                    acc[c].x = fma(-vv[q].y, y.y, acc[c].x);
+                                    acc[c].y = fma(vv[q].y, y.x, acc[c].y);
+                                } else {
+                                    acc[c].x = fma(vv[q].x, y.x, acc[c].x);
+                                    acc[c].y = fma(vv[q].x, y.y, acc[c].y);
+                                    acc[c].x = fma(-vv[q].y, y.y, acc[c].x);
+                                    acc[c].y = fma(vv[q].y, y.x, acc[c].y);
+                                }
+                            }
                         }
                     }
                 }
@@ -651,6 +686,29 @@ struct Kern {
     static __device__ __forceinline__ void write_out(const LaunchArgs &a, long long traj, int ksave, int col0,
                                                      const int (&row_of)[RPL], const bool (&row_ok)[RPL], const Vec &x) {
         const int n = a.g.n;
+        if (a.sel_index) {
+            // reduced output: only the selected entries leave the chip
+            const size_t base = ((size_t)traj * a.n_ts + ksave) * (size_t)a.n_sel;
+#pragma unroll
+            for (int i = 0; i < RPL; i++)
+                if (row_ok[i]) {
+#pragma unroll
+                    for (int c = 0; c < CPL; c++) {
+                        const int col = col0 + c;
+                        if (col < a.ncols) {
+                            const int si = __ldg(a.sel_index + (size_t)col * n + row_of[i]);
+                            const double2 v = x[i * CPL + c];
+                            if (si >= 0) {
+                                if (a.sel_abs2)
+                                    reinterpret_cast<double *>(a.out)[base + si] = fma(v.x, v.x, v.y * v.y);
+                                else
+                                    a.out[base + si] = v;
+                            }
+                        }
+                    }
+                }
+            return;
+        }
         double2 *dst = a.out + ((size_t)traj * a.n_ts + ksave) * (size_t)a.ncols * n;
 #pragma unroll
         for (int i = 0; i < RPL; i++)

@@ -22,7 +22,8 @@ EXPORTS = [
     "qsim_synchronize", "qsim_alloc_pinned", "qsim_free_pinned", "qsim_problem_create", "qsim_problem_destroy",
     "qsim_problem_set_h0", "qsim_problem_add_term", "qsim_problem_add_lindblad", "qsim_problem_finalize",
     "qsim_problem_eval", "qsim_unitary_propagator", "qsim_unitary_state", "qsim_me_propagator", "qsim_me_state",
-    "qsim_problem_flops_per_rhs", "qsim_problem_kernel_name", "qsim_launch_count", "qsim_peak_fp64",
+    "qsim_solve_selected", "qsim_problem_flops_per_rhs", "qsim_problem_kernel_name", "qsim_launch_count",
+    "qsim_peak_fp64",
 ]
 
 
@@ -69,6 +70,8 @@ def lib():
     L.qsim_me_propagator.argtypes = sig_prop
     L.qsim_unitary_state.argtypes = sig_state
     L.qsim_me_state.argtypes = sig_state
+    L.qsim_solve_selected.argtypes = [vp, vp, C.c_int, C.c_int64, vp, vp, C.c_int, C.c_int64, vp, C.c_int64,
+                                      C.POINTER(_abi.SolverOpts), C.c_int, vp, vp, C.c_int, vp, vp]
     L.qsim_problem_flops_per_rhs.argtypes = [vp, C.c_int, dp]
     L.qsim_problem_kernel_name.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
     L.qsim_launch_count.argtypes = [vp]
@@ -240,9 +243,14 @@ class Problem:
                                  C.byref(o), out_ptr, stats_ptr)
         check(rc)
 
-    def solve(self, which, ts, params=None, init=None, opts=None, ctx: Optional[Context] = None, out=None):
+    def solve(self, which, ts, params=None, init=None, opts=None, ctx: Optional[Context] = None, out=None,
+              select=None, abs2: bool = False):
         """Batched solve through the C ABI with host buffers.  Returns (out, stats) with
-        out[n_traj, n_ts, ...] complex, inner matrices indexed [row, col]."""
+        out[n_traj, n_ts, ...] complex, inner matrices indexed [row, col].
+
+        select = [(row, col), ...] (or [row, ...] for unitary_state): only those entries of every saved result
+        are produced (qsim_solve_selected); out is then [n_traj, n_ts, len(select)], complex or, with abs2,
+        real squared moduli -- the populations the reference's sweeps keep of a propagator."""
         which = WHICH.get(which, which)
         ctx = ctx or default_context()
         ts = np.ascontiguousarray(ts, dtype=np.float64)
@@ -273,11 +281,29 @@ class Problem:
                     raise ValueError(f"initial state must have shape {shape}")
                 keep_init = np.ascontiguousarray(init.ravel(order="F"))
             init_ptr = keep_init.ctypes.data
+        stats = np.zeros(n_traj, dtype=_abi.STATS_DTYPE)
+        if select is not None:
+            sel = np.asarray(select, dtype=np.int32)
+            if sel.ndim == 1:
+                rows, cols = np.ascontiguousarray(sel), None
+            else:
+                rows, cols = np.ascontiguousarray(sel[:, 0]), np.ascontiguousarray(sel[:, 1])
+            want = (n_traj, n_ts, len(rows))
+            dtype = np.float64 if abs2 else np.complex128
+            if out is None:
+                out = np.empty(want, dtype=dtype)
+            elif out.shape != want or out.dtype != dtype or not out.flags.c_contiguous:
+                raise ValueError("out buffer has the wrong shape / dtype / layout")
+            o = opts if opts is not None else _abi.default_opts()
+            check(lib().qsim_solve_selected(ctx._h, self._h, which, n_traj, params.ctypes.data, ts.ctypes.data, n_ts,
+                                            ts_stride, init_ptr, init_stride, C.byref(o), len(rows), rows.ctypes.data,
+                                            cols.ctypes.data if cols is not None else None, 1 if abs2 else 0,
+                                            out.ctypes.data, stats.ctypes.data))
+            return out, stats
         if out is None:
             out = np.empty((n_traj, n_ts, n), dtype=np.complex128)
         elif out.shape != (n_traj, n_ts, n) or out.dtype != np.complex128 or not out.flags.c_contiguous:
             raise ValueError("out buffer has the wrong shape / dtype / layout")
-        stats = np.zeros(n_traj, dtype=_abi.STATS_DTYPE)
         self.solve_raw(ctx, which, n_traj, params.ctypes.data, ts.ctypes.data, n_ts, ts_stride, init_ptr, init_stride,
                        out.ctypes.data, stats.ctypes.data, opts)
         res = out

@@ -112,15 +112,40 @@ class PerturbativeTransmon(QSystem):
     num_terms: int = PERTURBATIVE_NUM_TERMS
 
 
-@dataclass(frozen=True)
 class RotatingFrameSystem(QSystem):
-    label: str
-    system: QSystem
-    rotation_rate: float
+    """A system viewed in a frame rotating at `rotation_rate` (systems.jl:155-165).  Constructed like the
+    reference, `RotatingFrameSystem(system, rotation_rate)` (the label is the wrapped system's), or with an
+    explicit label, `RotatingFrameSystem(label, system, rotation_rate)`."""
+    __slots__ = ("label", "system", "rotation_rate")
+
+    def __init__(self, *args):
+        if len(args) == 2:
+            system, rotation_rate = args
+            lbl = system.label
+        elif len(args) == 3:
+            lbl, system, rotation_rate = args
+        else:
+            raise TypeError("RotatingFrameSystem(system, rotation_rate) or (label, system, rotation_rate)")
+        object.__setattr__(self, "label", lbl)
+        object.__setattr__(self, "system", system)
+        object.__setattr__(self, "rotation_rate", float(rotation_rate))
+
+    def __setattr__(self, name, value):
+        raise AttributeError("RotatingFrameSystem is immutable")
+
+    def __eq__(self, other):
+        return (isinstance(other, RotatingFrameSystem) and self.label == other.label and self.system == other.system
+                and self.rotation_rate == other.rotation_rate)
+
+    def __hash__(self):
+        return hash((self.label, self.system, self.rotation_rate))
+
+    def __repr__(self):
+        return f"RotatingFrameSystem({self.label!r}, {self.system!r}, {self.rotation_rate!r})"
 
     @staticmethod
     def wrap(q: QSystem, rotation_rate: float) -> "RotatingFrameSystem":
-        return RotatingFrameSystem(q.label, q, rotation_rate)
+        return RotatingFrameSystem(q, rotation_rate)
 
     @property
     def dimension(self) -> int:
