@@ -45,11 +45,11 @@ def _check_ts(ts):
     return ts, False
 
 
-def _solve(name, cqs, ts, init, params, opts, ctx, return_stats):
+def _solve(name, cqs, ts, init, params, opts, ctx, return_stats, select=None, abs2=False):
     ts, scalar = _check_ts(ts)
     n_params = None if params is None else np.atleast_2d(params).shape[1]
     prob = _problem_for(cqs, n_params)
-    out, stats = prob.solve(name, ts, params=params, init=init, opts=opts, ctx=ctx)
+    out, stats = prob.solve(name, ts, params=params, init=init, opts=opts, ctx=ctx, select=select, abs2=abs2)
     if params is None:
         out = out[0]
         res = out[-1] if scalar else out
@@ -59,23 +59,33 @@ def _solve(name, cqs, ts, init, params, opts, ctx, return_stats):
 
 
 def unitary_propagator(cqs: CompositeQSystem, ts, params=None, opts: Optional[_abi.SolverOpts] = None,
-                       ctx: Optional[Context] = None, return_stats: bool = False):
+                       ctx: Optional[Context] = None, return_stats: bool = False, select=None, abs2: bool = False):
     """Solve dU/dt = -2 pi i H(t) U, U(ts[0]) = I.  Returns U at every ts[k]: array [n_ts, d, d]
-    (or [n_traj, n_ts, d, d] with `params`)."""
-    return _solve("unitary_propagator", cqs, ts, None, params, opts, ctx, return_stats)
+    (or [n_traj, n_ts, d, d] with `params`).
+
+    select=[(row, col), ...] keeps only those entries of every U(ts[k]) on the device side (result
+    [..., n_ts, len(select)]); with abs2=True their squared moduli -- the transition populations
+    abs2(u[i, j]) that the reference's sweeps reduce each propagator to (test_time_evolution.jl:72)."""
+    return _solve("unitary_propagator", cqs, ts, None, params, opts, ctx, return_stats, select, abs2)
 
 
-def unitary_state(cqs: CompositeQSystem, ts, psi0, params=None, opts=None, ctx=None, return_stats: bool = False):
-    """Solve d psi/dt = -2 pi i H(t) psi from psi0.  Returns [n_ts, d]."""
-    return _solve("unitary_state", cqs, ts, np.asarray(psi0, dtype=np.complex128), params, opts, ctx, return_stats)
+def unitary_state(cqs: CompositeQSystem, ts, psi0, params=None, opts=None, ctx=None, return_stats: bool = False,
+                  select=None, abs2: bool = False):
+    """Solve d psi/dt = -2 pi i H(t) psi from psi0.  Returns [n_ts, d]; select=[i, ...] keeps components."""
+    return _solve("unitary_state", cqs, ts, np.asarray(psi0, dtype=np.complex128), params, opts, ctx, return_stats,
+                  select, abs2)
 
 
-def me_propagator(cqs: CompositeQSystem, ts, params=None, opts=None, ctx=None, return_stats: bool = False):
+def me_propagator(cqs: CompositeQSystem, ts, params=None, opts=None, ctx=None, return_stats: bool = False,
+                  select=None, abs2: bool = False):
     """Solve the vectorised Lindblad master equation for the d^2 x d^2 propagator (column-major vec).
     Returns [n_ts, d^2, d^2]."""
-    return _solve("me_propagator", cqs, ts, None, params, opts, ctx, return_stats)
+    return _solve("me_propagator", cqs, ts, None, params, opts, ctx, return_stats, select, abs2)
 
 
-def me_state(cqs: CompositeQSystem, ts, rho0, params=None, opts=None, ctx=None, return_stats: bool = False):
-    """Solve d rho/dt = -2 pi i [H, rho] + 2 pi sum (L rho L' - 1/2 {L'L, rho}) from rho0.  Returns [n_ts, d, d]."""
-    return _solve("me_state", cqs, ts, np.asarray(rho0, dtype=np.complex128), params, opts, ctx, return_stats)
+def me_state(cqs: CompositeQSystem, ts, rho0, params=None, opts=None, ctx=None, return_stats: bool = False,
+             select=None, abs2: bool = False):
+    """Solve d rho/dt = -2 pi i [H, rho] + 2 pi sum (L rho L' - 1/2 {L'L, rho}) from rho0.  Returns [n_ts, d, d];
+    select=[(row, col), ...] keeps those entries of rho."""
+    return _solve("me_state", cqs, ts, np.asarray(rho0, dtype=np.complex128), params, opts, ctx, return_stats,
+                  select, abs2)
