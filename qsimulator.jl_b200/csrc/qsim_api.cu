@@ -405,7 +405,7 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
 
 static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int vm, int rs) {
     const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c3_t128, variants_r1c3_t256,
-                                              variants_r1c3_t288, variants_r2c1_t128, variants_r2c2_t128,
+                                              variants_r1c4_t256, variants_r2c1_t128, variants_r2c2_t128,
                                               variants_r2c2_t256, variants_r3c1_t128, variants_r3c1_t256,
                                               variants_rowsplit};
     const KernelVariant *best = nullptr;
@@ -437,8 +437,9 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.groups = std::min(32 / n, pl.ncols);
         cpl = (pl.ncols + pl.groups - 1) / pl.groups > 1 ? 3 : 1;
     } else if (n <= 32) {
+        // three columns per lane up to 24 rows, four above: at most eight warps per trajectory
         rpl = 1;
-        cpl = pl.ncols > 1 ? 3 : 1;
+        cpl = pl.ncols > 1 ? (n <= 24 ? 3 : 4) : 1;
     } else if (n <= 64) {
         rpl = 2;
         cpl = pl.ncols > 1 ? 2 : 1;
@@ -458,7 +459,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     if (pl.rowsplit) {
         pl.team_warps = (n + 95) / 96;
         pl.streamed = pl.n_batches > 1 ? 1 : 0;
-    } else if (pl.n_batches <= 9) {
+    } else if (pl.n_batches <= 8) {
         pl.streamed = 0;
         pl.team_warps = pl.n_batches;
     } else {
@@ -483,7 +484,8 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
                 const uint32_t sl = g.ell[(size_t)j * n + r] >> 16;
                 if (sl != 0xFFFFu && (int)sl < g.n_dyn_slots) static_off = false;
             }
-        if (static_off && find_variant(rpl, cpl, g.max_nnz, pl.block, 2, 0)) vm = 2;
+        // (with four entries per lane the extra value registers would spill: stay in mode 1)
+        if (static_off && rpl * cpl <= 3 && find_variant(rpl, cpl, g.max_nnz, pl.block, 2, 0)) vm = 2;
     }
     pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block, vm, pl.rowsplit);
     if (!pl.kv)

@@ -14,9 +14,10 @@ struct KernelVariant {
 // defined one per translation unit (qsim_inst_*.cu) so the variants compile in parallel
 #define QSIM_DECLARE(FN) const KernelVariant *FN(int *count);
 // t128: four one-warp teams per CTA, two CTAs per SM.  t256: teams of 2-8 warps, one CTA per SM.  Both leave
-// 255 registers per thread (two warps per scheduler).  t288: nine-warp teams (27-level propagators), 168 registers.
+// 255 registers per thread (two warps per scheduler); nine warps would be held to 168 and spill.
 QSIM_DECLARE(variants_r1c1_t128)
-QSIM_DECLARE(variants_r1c3_t128) QSIM_DECLARE(variants_r1c3_t256) QSIM_DECLARE(variants_r1c3_t288)
+QSIM_DECLARE(variants_r1c3_t128) QSIM_DECLARE(variants_r1c3_t256)
+QSIM_DECLARE(variants_r1c4_t256)
 QSIM_DECLARE(variants_r2c1_t128)
 QSIM_DECLARE(variants_r2c2_t128) QSIM_DECLARE(variants_r2c2_t256)
 QSIM_DECLARE(variants_r3c1_t128) QSIM_DECLARE(variants_r3c1_t256)

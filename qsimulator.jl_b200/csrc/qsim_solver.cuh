@@ -638,7 +638,10 @@ struct Kern {
                         }
                     }
                 }
-                constexpr int CH = 4;
+#ifndef QSIM_CH
+#define QSIM_CH 4
+#endif
+                constexpr int CH = QSIM_CH;
 #pragma unroll
                 for (int j0 = 1; j0 < MAXNNZ; j0 += CH) {
                     double2 vv[CH], yy[CH][CPL];
