@@ -771,7 +771,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
                 if (e.out_chan + q < 32) a.dyn_chan_mask |= 1u << (e.out_chan + q);
         }
     a.use_windows = (any_dyn && g.n_chan <= 32 && !(o.flags & QSIM_FLAG_DIRECT_DRIVES)) ? 1 : 0;
-    a.fast_tables = (a.use_windows && pl.team_warps == 1 && dc->fast_ok) ? 1 : 0;
+    a.fast_tables = (a.use_windows && dc->fast_ok) ? 1 : 0;
     a.fast_chA = dc->fast_chA;
     a.fast_chB = dc->fast_chB;
     a.ell_packed = dc->ell_packed;

@@ -75,7 +75,7 @@ struct LaunchArgs {
     unsigned dyn_chan_mask;  // channels produced by time-dependent evaluators
     int use_windows;      // 1: drive channels through windowed Chebyshev interpolants (see build_window)
     int dyn_fast;         // 1: every time-dependent slot has <= 3 pairs (64-byte records)
-    int fast_tables;      // 1: one-warp teams whose time-dependent slots are w0 + wA cA(t) + wB cB(t) with at most two
+    int fast_tables;      // 1: the time-dependent slots are w0 + wA cA(t) + wB cB(t) with at most two
                           //    time-dependent channels A, B (records hold w0, wA, wB in that order): see fast_tables()
     int fast_chA, fast_chB;
     int off_dptr, off_dw, off_drec;  // byte offsets inside the common region (after tables, Chebyshev, power tables)
@@ -219,6 +219,22 @@ __device__ __forceinline__ void team_sum(double (&v)[NV], uint32_t red, int team
         v[i] = s;
     }
     team_sync(team_warps, bar_id);
+}
+
+// Team-wide sum of one value with a single barrier: the partial sums alternate between two buffers (`par`
+// flips per call, identically in every warp), so a warp that runs ahead into the next call writes the other
+// buffer and cannot reach the call after that before everyone has left this one.
+__device__ __forceinline__ double team_sum_alt(double v, uint32_t red, int team_warps, int warp_in_team, int lane,
+                                               int bar_id, int &par) {
+    v = warp_sum(v);
+    if (team_warps == 1) return v;
+    const uint32_t buf = red + 8u * (uint32_t)((2 + par) * team_warps);
+    par ^= 1;
+    if (lane == 0) sts1(buf + 8 * warp_in_team, v);
+    team_sync(team_warps, bar_id);
+    double s = 0.0;
+    for (int w = 0; w < team_warps; w++) s += lds1(buf + 8 * w);
+    return s;
 }
 
 // Deterministic team-wide maximum.
@@ -401,11 +417,13 @@ struct Kern {
         return team_max(bad, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
     }
 
-    // Stage tables for the common case (one-warp team, <= 2 time-dependent channels, drive window valid):
+    // Stage tables for the common case (<= 2 time-dependent channels, drive window valid):
     // lane s < 5 evaluates both channels' Chebyshev interpolants at stage time s (basis by the double-step
     // recurrence T_{k+2} = 2 T_2 T_k - T_{k-2}: two independent chains), the values are broadcast by shuffle,
     // and every lane combines them with its slots' weights.  No shared-memory round trip, no barrier: the
-    // stage exchange's __syncwarp orders the table stores before the first gather.
+    // stage exchange's __syncwarp orders the table stores before the first gather.  In a multi-warp team every
+    // warp writes the whole (identical) table itself before it reads any of it, and the error-norm barrier of
+    // the previous step separates these stores from that step's reads, so no team barrier is needed either.
     static __device__ __forceinline__ void fast_tables(const LaunchArgs &a, const Geo &g, double t, double dt,
                                                        double win_t, double win_sc) {
         double cA = 0.0, cB = 0.0;
@@ -919,7 +937,7 @@ struct Kern {
             CTL_ST(C_QOLDPOW, pow(a.qoldinit, a.beta2));
             __syncwarp();
             long long iters = 0;
-            int n_attempt = 0;
+            int n_attempt = 0, red_par = 0;
             int win_state = a.use_windows ? 0 : -1;  // -1 direct evaluation, 0 no window yet, 1 window valid
 #ifdef QSIM_TIMING
             long long tk_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tl_ = clock64();
@@ -1118,7 +1136,7 @@ struct Kern {
                 }
                 n_attempt++;
                 QSIM_TICK(7)
-                team_sum<1>(err, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
+                err[0] = team_sum_alt(err[0], g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id, red_par);
                 QSIM_TICK(8)
                 // EEst^2 = mean |r_i|^2.  PI controller (stepsize_controller! / step_accept_controller! /
                 // step_reject_controller!): q = EEst^beta1 / qold^beta2 / gamma clamped to [1/qmax, 1/qmin];
