@@ -261,6 +261,17 @@ int qsim_solve_selected(qsim_ctx *ctx, qsim_problem *prob, int which, int64_t n_
                         int n_sel, const int32_t *sel_rows, const int32_t *sel_cols, int abs2,
                         double *out, qsim_traj_stats *stats);
 
+/* One sweep over several devices from a single call: trajectories [0, n_traj) are split into n_ctx
+ * contiguous blocks, block i is integrated through ctxs[i] (one ctx per device, each on its own host
+ * thread inside the library) and written straight into the caller's out / stats at its offsets; there is
+ * no collective and no ordering between blocks.  Host buffers only (QSIM_FLAG_DEVICE_PTRS and opts->stream
+ * are rejected).  which / init / init_stride as in qsim_solve_selected.  The reference's sweep is a
+ * user-level loop over unitary_propagator calls (doc/Examples.ipynb); this is that loop, sharded.       */
+int qsim_solve_multi(qsim_ctx **ctxs, int n_ctx, qsim_problem *prob, int which, int64_t n_traj,
+                     const double *params, const double *ts, int n_ts, int64_t ts_stride,
+                     const double *init, int64_t init_stride, const qsim_solver_opts *opts,
+                     double *out, qsim_traj_stats *stats);
+
 /* Executed FP64 flop of the generator application per right-hand-side call of
  * one trajectory (8 flop per complex multiply-add actually issued; 4 when the
  * generator is purely imaginary, i.e. a real Hamiltonian), for the roofline

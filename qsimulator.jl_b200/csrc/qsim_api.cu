@@ -9,9 +9,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -68,7 +70,7 @@ struct qsim_ctx {
 };
 
 struct qsim_problem::DeviceCopy {
-    qsim_ctx *owner = nullptr;
+    int device = -1;
     uint32_t *ell = nullptr;
     uint8_t *row_len = nullptr;
     int32_t *slot_ptr = nullptr, *pair_chan = nullptr;
@@ -78,6 +80,7 @@ struct qsim_problem::DeviceCopy {
     int fast_ok = 0, fast_chA = 0, fast_chB = 0;  // records are in (constant, channel A, channel B) order
     uint32_t *ell_packed = nullptr;  // row-split kernels
     int packed_stride = -1;
+    ~DeviceCopy() { free_all(); }  // the owning device must be current
     void free_all() {
         cudaFree(ell_packed);
         ell_packed = nullptr;
@@ -209,10 +212,9 @@ int qsim_problem_create(int d, int n_params, qsim_problem **out) {
 int qsim_problem_destroy(qsim_problem *p) {
     if (!p) return QSIM_OK;
     for (int w = 0; w < 2; w++)
-        if (p->dev[w]) {
-            cudaSetDevice(p->dev[w]->owner->device);
-            p->dev[w]->free_all();
-            delete p->dev[w];
+        for (auto *dc : p->dev[w]) {
+            cudaSetDevice(dc->device);
+            delete dc;
         }
     delete p;
     return QSIM_OK;
@@ -561,18 +563,19 @@ static cudaError_t upload(T **dst, const std::vector<T> &src) {
     return e;
 }
 
-static int ensure_device_copy(qsim_ctx *c, qsim_problem *p, int w) {
-    if (p->dev[w] && p->dev[w]->owner == c) return QSIM_OK;
-    if (p->dev[w]) {
-        cudaSetDevice(p->dev[w]->owner->device);
-        p->dev[w]->free_all();
-        delete p->dev[w];
-        p->dev[w] = nullptr;
-        cudaSetDevice(c->device);
-    }
+// The generator's device-resident tables on the ctx's device (uploaded on first use, then shared by every
+// ctx on that device).  Called with the CUDA device already set.
+static int ensure_device_copy(qsim_ctx *c, qsim_problem *p, int w, qsim_problem::DeviceCopy **out) {
+    std::lock_guard<std::mutex> lock(p->dev_mutex);
+    for (auto *have : p->dev[w])
+        if (have->device == c->device) {
+            *out = have;
+            return QSIM_OK;
+        }
     const Generator &g = p->gen[w];
-    auto *dc = new qsim_problem::DeviceCopy();
-    dc->owner = c;
+    std::unique_ptr<qsim_problem::DeviceCopy> holder(new qsim_problem::DeviceCopy());
+    qsim_problem::DeviceCopy *dc = holder.get();
+    dc->device = c->device;
     std::vector<double2> w2(g.pair_w.size());
     for (size_t i = 0; i < w2.size(); i++) w2[i] = make_double2(g.pair_w[i].real(), g.pair_w[i].imag());
     CU(upload(&dc->ell, g.ell));
@@ -620,7 +623,8 @@ static int ensure_device_copy(qsim_ctx *c, qsim_problem *p, int w) {
         dc->fast_chA = chA;
         dc->fast_chB = chB;
     }
-    p->dev[w] = dc;
+    p->dev[w].push_back(holder.release());
+    *out = dc;
     return QSIM_OK;
 }
 
@@ -661,9 +665,10 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     Plan pl;
     if (int rc = make_plan(p, which, pl)) return rc;
     CU(cudaSetDevice(c->device));
-    if (int rc = ensure_device_copy(c, p, pl.w)) return rc;
+    qsim_problem::DeviceCopy *dc = nullptr;
+    if (int rc = ensure_device_copy(c, p, pl.w, &dc)) return rc;
     const Generator &g = p->gen[pl.w];
-    qsim_problem::DeviceCopy *dc = p->dev[pl.w];
+    std::unique_lock<std::mutex> packed_lock(p->dev_mutex);
     if (pl.rowsplit && (!dc->ell_packed || dc->packed_stride != pl.y_row_stride)) {
         // translated sparse rows for the row-split kernels: byte offsets into the stage buffer / value table,
         // plus eight zero-slot padding rows for the lanes past the last row
@@ -685,6 +690,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         CU(upload(&dc->ell_packed, packed));
         dc->packed_stride = pl.y_row_stride;
     }
+    packed_lock.unlock();
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : c->stream;
 
     int ctas_per_sm = 0;
@@ -875,6 +881,53 @@ int qsim_solve_selected(qsim_ctx *ctx, qsim_problem *prob, int which, int64_t n_
     }
     return solve_common(ctx, prob, which, n_traj, params, ts, n_ts, ts_stride, (which == 1 || which == 3) ? init : nullptr,
                         init_stride, opts, out, stats, &sel);
+}
+
+// One sweep over several devices from one call (SURVEY.md section 8b "Threading": the fan-out happens inside
+// the library so a Julia caller needs no threads).  Trajectories are split into contiguous blocks, block i
+// runs through ctxs[i] on its own host thread and copies its results straight into the caller's buffers.
+int qsim_solve_multi(qsim_ctx **ctxs, int n_ctx, qsim_problem *prob, int which, int64_t n_traj, const double *params,
+                     const double *ts, int n_ts, int64_t ts_stride, const double *init, int64_t init_stride,
+                     const qsim_solver_opts *opts, double *out, qsim_traj_stats *stats) {
+    if (!ctxs || n_ctx < 1) return fail(QSIM_ERR_NO_DEVICE, "need at least one ctx (no CPU fallback)");
+    for (int i = 0; i < n_ctx; i++) {
+        if (!ctxs[i]) return fail(QSIM_ERR_NO_DEVICE, "ctx is NULL: create one per device with qsim_create");
+        for (int j = 0; j < i; j++)
+            if (ctxs[j] == ctxs[i]) return fail(QSIM_ERR_ARG, "the same ctx appears twice");
+    }
+    if (which < 0 || which > 3) return fail(QSIM_ERR_ARG, "which must be 0..3");
+    if (!prob) return fail(QSIM_ERR_ARG, "prob is NULL");
+    if (opts && ((opts->flags & QSIM_FLAG_DEVICE_PTRS) || opts->stream))
+        return fail(QSIM_ERR_ARG, "qsim_solve_multi takes host buffers and uses each ctx's own stream");
+    if (n_traj < 0) return fail(QSIM_ERR_ARG, "n_traj < 0");
+    const bool has_init = which == 1 || which == 3;
+    if (n_ctx == 1 || n_traj <= 1)
+        return solve_common(ctxs[0], prob, which, n_traj, params, ts, n_ts, ts_stride, has_init ? init : nullptr, init_stride,
+                            opts, out, stats);
+    // build the generator and check the plan once, on this thread (the workers then only read the problem)
+    Plan pl;
+    if (int rc = make_plan(prob, which, pl)) return rc;
+    const size_t n_state = (size_t)prob->gen[pl.w].n * pl.ncols;
+    const int64_t per = (n_traj + n_ctx - 1) / n_ctx;
+    std::vector<int> rcs((size_t)n_ctx, QSIM_OK);
+    std::vector<std::string> msgs((size_t)n_ctx);
+    std::vector<std::thread> workers;
+    for (int i = 0; i < n_ctx; i++) {
+        const int64_t lo = std::min<int64_t>(n_traj, per * i), hi = std::min<int64_t>(n_traj, per * (i + 1));
+        if (hi <= lo) continue;
+        workers.emplace_back([=, &rcs, &msgs]() {
+            const double *par_i = params ? params + (size_t)lo * std::max(prob->n_params, 1) : nullptr;
+            const double *ts_i = ts_stride ? ts + (size_t)lo * ts_stride : ts;
+            const double *init_i = has_init ? (init_stride ? init + 2 * (size_t)lo * init_stride : init) : nullptr;
+            rcs[(size_t)i] = solve_common(ctxs[i], prob, which, hi - lo, par_i, ts_i, n_ts, ts_stride, init_i, init_stride, opts,
+                                          out + 2 * (size_t)lo * n_ts * n_state, stats ? stats + lo : nullptr);
+            if (rcs[(size_t)i] != QSIM_OK) msgs[(size_t)i] = g_err;  // g_err is per thread
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int i = 0; i < n_ctx; i++)
+        if (rcs[(size_t)i] != QSIM_OK) return fail(rcs[(size_t)i], "ctx " + std::to_string(i) + ": " + msgs[(size_t)i]);
+    return QSIM_OK;
 }
 
 }  // extern "C"

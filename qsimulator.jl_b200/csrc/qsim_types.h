@@ -10,6 +10,7 @@
 // Channels are produced by evaluators: one per time-dependent term (qsim_term) or Lindblad rate.
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <vector>
 #include <complex>
 
@@ -82,7 +83,9 @@ struct qsim_problem {
     std::vector<Lind> linds;
     qsim::Generator gen[2];  // [0] unitary (n = d), [1] Lindblad (n = d^2)
     bool gen_built[2] = {false, false};
-    // device copies, owned by the ctx that uploaded them
+    // device copies of the generators, one per CUDA device that has solved this problem (shared by the
+    // contexts on that device); created under `dev_mutex`
     struct DeviceCopy;
-    DeviceCopy *dev[2] = {nullptr, nullptr};
+    std::vector<DeviceCopy *> dev[2];
+    std::mutex dev_mutex;
 };

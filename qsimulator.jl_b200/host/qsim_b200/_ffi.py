@@ -22,7 +22,7 @@ EXPORTS = [
     "qsim_synchronize", "qsim_alloc_pinned", "qsim_free_pinned", "qsim_problem_create", "qsim_problem_destroy",
     "qsim_problem_set_h0", "qsim_problem_add_term", "qsim_problem_add_lindblad", "qsim_problem_finalize",
     "qsim_problem_eval", "qsim_unitary_propagator", "qsim_unitary_state", "qsim_me_propagator", "qsim_me_state",
-    "qsim_solve_selected", "qsim_problem_flops_per_rhs", "qsim_problem_kernel_name", "qsim_launch_count",
+    "qsim_solve_selected", "qsim_solve_multi", "qsim_problem_flops_per_rhs", "qsim_problem_kernel_name", "qsim_launch_count",
     "qsim_peak_fp64",
 ]
 
@@ -72,6 +72,8 @@ def lib():
     L.qsim_me_state.argtypes = sig_state
     L.qsim_solve_selected.argtypes = [vp, vp, C.c_int, C.c_int64, vp, vp, C.c_int, C.c_int64, vp, C.c_int64,
                                       C.POINTER(_abi.SolverOpts), C.c_int, vp, vp, C.c_int, vp, vp]
+    L.qsim_solve_multi.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_int, C.c_int64, vp, vp, C.c_int, C.c_int64, vp,
+                                   C.c_int64, C.POINTER(_abi.SolverOpts), vp, vp]
     L.qsim_problem_flops_per_rhs.argtypes = [vp, C.c_int, dp]
     L.qsim_problem_kernel_name.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
     L.qsim_launch_count.argtypes = [vp]
@@ -250,9 +252,15 @@ class Problem:
 
         select = [(row, col), ...] (or [row, ...] for unitary_state): only those entries of every saved result
         are produced (qsim_solve_selected); out is then [n_traj, n_ts, len(select)], complex or, with abs2,
-        real squared moduli -- the populations the reference's sweeps keep of a propagator."""
+        real squared moduli -- the populations the reference's sweeps keep of a propagator.
+
+        ctx may be a list of Contexts (one per device): the sweep is then split into contiguous blocks, one per
+        device, inside the library (qsim_solve_multi)."""
         which = WHICH.get(which, which)
-        ctx = ctx or default_context()
+        multi = list(ctx) if isinstance(ctx, (list, tuple)) else None
+        if multi is not None and select is not None:
+            raise ValueError("select= is not available together with a list of contexts")
+        ctx = None if multi is not None else (ctx or default_context())
         ts = np.ascontiguousarray(ts, dtype=np.float64)
         if params is None:
             params = np.zeros((1, max(self.n_params, 1)))
@@ -304,8 +312,15 @@ class Problem:
             out = np.empty((n_traj, n_ts, n), dtype=np.complex128)
         elif out.shape != (n_traj, n_ts, n) or out.dtype != np.complex128 or not out.flags.c_contiguous:
             raise ValueError("out buffer has the wrong shape / dtype / layout")
-        self.solve_raw(ctx, which, n_traj, params.ctypes.data, ts.ctypes.data, n_ts, ts_stride, init_ptr, init_stride,
-                       out.ctypes.data, stats.ctypes.data, opts)
+        if multi is not None:
+            handles = (C.c_void_p * len(multi))(*[c._h.value for c in multi])
+            o = opts if opts is not None else _abi.default_opts()
+            check(lib().qsim_solve_multi(handles, len(multi), self._h, which, n_traj, params.ctypes.data, ts.ctypes.data,
+                                         n_ts, ts_stride, init_ptr, init_stride, C.byref(o), out.ctypes.data,
+                                         stats.ctypes.data))
+        else:
+            self.solve_raw(ctx, which, n_traj, params.ctypes.data, ts.ctypes.data, n_ts, ts_stride, init_ptr,
+                           init_stride, out.ctypes.data, stats.ctypes.data, opts)
         res = out
         if len(shape) == 2:
             res = out.reshape(n_traj, n_ts, shape[1], shape[0]).transpose(0, 1, 3, 2)
