@@ -302,6 +302,11 @@ def main():
                                          % ((4, "purely imaginary, 2 DFMA per entry") if "_vm0" not in prob.kernel_name(which)
                                             else (8, "complex, 4 DFMA per entry")),
                          "dense_equivalent_tflops": dense_flops_per_launch / (total_ms / args.steps * 1e-3) / 1e12,
+                         # informational: + the Runge-Kutta vector arithmetic any Tsit5 must do per attempted step and
+                         # complex state entry (21 stage-combination and 7 error-estimate real-by-complex multiply-adds
+                         # at 4 flop, 6 stage arguments u + dt*(...) at 4 flop, ~10 flop of scaled error norm = 146 flop)
+                         "tsit5_total_tflops": (flops_per_launch + 146.0 * d * d * attempts)
+                                               / (total_ms / args.steps * 1e-3) / 1e12,
                          "hbm_out_gbs": d_out.numel() * 16 / (total_ms / args.steps * 1e-3) / 1e9},
             "gpu_launches": int(launches), "clocks": clocks,
         }
