@@ -74,7 +74,7 @@ typedef struct {
 } qsim_slot;
 
 enum { QSIM_CARRIER_NONE = 0, QSIM_CARRIER_COS = 1, QSIM_CARRIER_SIN = 2 };
-enum { QSIM_ENV_NONE = 0, QSIM_ENV_GAUSSIAN = 1, QSIM_ENV_ERF_SQUARED = 2 };
+enum { QSIM_ENV_NONE = 0, QSIM_ENV_GAUSSIAN = 1, QSIM_ENV_ERF_SQUARED = 2, QSIM_ENV_TABLE = 3 };
 enum { QSIM_BLEND_NONE = 0, QSIM_BLEND_REST = 1 };
 
 /*
@@ -83,6 +83,7 @@ enum { QSIM_BLEND_NONE = 0, QSIM_BLEND_REST = 1 };
  *   env(t)     = 1
  *              | exp(-0.5*((t - t1)/sigma)^2)                        (gaussian)
  *              | 0.5*(erf((t - t1)/sigma) - erf((t - t2)/sigma))     (erf_squared)
+ *              | p(t), a tabulated piecewise polynomial                (table; see qsim_problem_add_table)
  * blend == NONE:  s = offset + amp * env * carrier
  * blend == REST:  s = env * (offset + amp * carrier) + (1 - env) * rest
  * These are the drive shapes of benchmark/benchmarks.jl:111,138,185,
@@ -93,7 +94,7 @@ typedef struct {
     int32_t carrier;
     int32_t envelope;
     int32_t blend;
-    int32_t _pad;
+    int32_t table;   /* QSIM_ENV_TABLE: id returned by qsim_problem_add_table; 0 otherwise */
     qsim_slot offset, amp, freq, phase, t1, t2, sigma, rest;
 } qsim_signal;
 
@@ -204,6 +205,15 @@ int qsim_problem_add_term(qsim_problem *prob, const qsim_term *term,
  * scale == NULL means 1 (fixed_Ls; add_lindblad!, composite_systems.jl:53-62). */
 int qsim_problem_add_lindblad(qsim_problem *prob, const double *lind,
                               const qsim_signal *scale);
+/* A tabulated envelope for QSIM_ENV_TABLE signals: the generic path for drives that are opaque closures in
+ * the reference (arbitrary pulse shapes, add_hamiltonian!(cqs, t -> ..., q), composite_systems.jl:40-50;
+ * SURVEY.md section 8f rank 3).  The host samples the closure into a piecewise polynomial: n_seg equal
+ * segments over [t_start, t_end], segment k holding n_coef (2..16) Chebyshev coefficients c_j of
+ * p(t) = sum_j c_j T_j(x), x = 2 (t - t_k)/h - 1, evaluated with the Clenshaw recurrence; outside
+ * [t_start, t_end] the end values continue.  coef is [n_seg][n_coef].  The accuracy of the table is the
+ * host's responsibility (the Python mirror refines n_seg until the closure is matched to 1e-13).      */
+int qsim_problem_add_table(qsim_problem *prob, double t_start, double t_end, int n_seg, int n_coef,
+                           const double *coef, int32_t *table_id);
 int qsim_problem_finalize(qsim_problem *prob);
 
 /* Introspection used by the tests: evaluate the assembled generator at time t

@@ -47,6 +47,8 @@ def lib():
         L.qso_problem_set_h0.argtypes = [C.c_void_p, dp]
         L.qso_problem_add_term.argtypes = [C.c_void_p, C.POINTER(_abi.TermStruct), dp, dp, C.POINTER(C.c_int32)]
         L.qso_problem_add_lindblad.argtypes = [C.c_void_p, dp, C.POINTER(_abi.SignalStruct)]
+        L.qso_problem_add_table.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, dp]
+        L.qso_problem_add_table.restype = C.c_int
         L.qso_problem_eval.argtypes = [C.c_void_p, C.c_int, C.c_double, dp, dp]
         L.qso_tsit5_constants.argtypes = [dp, dp, dp, dp]
         L.qso_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, dp, dp, C.c_int, C.c_int64, dp, C.c_int64,
@@ -65,8 +67,12 @@ class OracleProblem:
         self._h = L.qso_problem_create(spec.d, spec.n_params)
         p, keep = _abi.cplx_ptr(spec.h0)
         L.qso_problem_set_h0(self._h, p)
+        table_ids = {}
+        for tb in spec.tables or []:
+            table_ids[id(tb)] = L.qso_problem_add_table(self._h, tb.t_start, tb.t_end, tb.n_seg, tb.n_coef,
+                                                        tb.coef.ctypes.data_as(C.POINTER(C.c_double)))
         for lt, a, b, levels in spec.terms:
-            ts = _abi.make_term(lt)
+            ts = _abi.make_term(lt, table_ids)
             pa, ka = _abi.cplx_ptr(a)
             pb, kb = _abi.cplx_ptr(b)
             pl = None
@@ -79,7 +85,7 @@ class OracleProblem:
             if scale is None:
                 L.qso_problem_add_lindblad(self._h, po, None)
             else:
-                ss = _abi.make_signal(scale)
+                ss = _abi.make_signal(scale, table_ids)
                 L.qso_problem_add_lindblad(self._h, po, C.byref(ss))
 
     def __del__(self):

@@ -99,6 +99,9 @@ typedef struct qso_problem {
     int n_terms, n_lind;
     o_term *terms;
     o_lind *linds;
+    /* tabulated envelopes (qsim_problem_add_table): per table {t_start, 1/h, n_seg, n_coef, coef...} */
+    int n_tables;
+    double **tables;
 } qso_problem;
 
 qso_problem *qso_problem_create(int d, int n_params) {
@@ -117,10 +120,24 @@ void qso_problem_destroy(qso_problem *p) {
         free(p->terms[i].levels);
     }
     for (int i = 0; i < p->n_lind; i++) free(p->linds[i].op);
+    for (int i = 0; i < p->n_tables; i++) free(p->tables[i]);
+    free(p->tables);
     free(p->terms);
     free(p->linds);
     free(p->h0);
     free(p);
+}
+/* include/qsim_b200.h qsim_problem_add_table: returns the 1-based table id */
+int qso_problem_add_table(qso_problem *p, double t_start, double t_end, int n_seg, int n_coef, const double *coef) {
+    double *T = (double *)malloc(sizeof(double) * (4 + (size_t)n_seg * n_coef));
+    T[0] = t_start;
+    T[1] = (double)n_seg / (t_end - t_start);
+    T[2] = (double)n_seg;
+    T[3] = (double)n_coef;
+    memcpy(T + 4, coef, sizeof(double) * (size_t)n_seg * n_coef);
+    p->tables = (double **)realloc(p->tables, sizeof(double *) * (p->n_tables + 1));
+    p->tables[p->n_tables++] = T;
+    return p->n_tables;
 }
 static double *dup_mat(const double *m, int d) {
     if (!m) return NULL;
@@ -158,7 +175,25 @@ int qso_problem_add_lindblad(qso_problem *p, const double *op, const qsim_signal
 /* ------------------------------------------------------- drive evaluation */
 static inline double slot(const qsim_slot *s, const double *row) { return s->param >= 0 ? row[s->param] : s->value; }
 
-static double eval_signal(const qsim_signal *s, double t, const double *row) {
+/* piecewise Chebyshev series, Clenshaw recurrence; end values continue outside the table */
+static double eval_table(const double *T, double t) {
+    const int n_seg = (int)T[2], nc = (int)T[3];
+    const double u = (t - T[0]) * T[1];
+    int k = (int)floor(u);
+    k = k < 0 ? 0 : (k >= n_seg ? n_seg - 1 : k);
+    double x = 2.0 * (u - (double)k) - 1.0;
+    x = x < -1.0 ? -1.0 : (x > 1.0 ? 1.0 : x);
+    const double *c = T + 4 + (size_t)k * nc;
+    double b1 = 0.0, b2 = 0.0;
+    for (int j = nc - 1; j >= 1; j--) {
+        double b0 = fma(2.0 * x, b1, c[j] - b2);
+        b2 = b1;
+        b1 = b0;
+    }
+    return fma(x, b1, c[0] - b2);
+}
+
+static double eval_signal(const qso_problem *p, const qsim_signal *s, double t, const double *row) {
     double car = 1.0, env = 1.0;
     if (s->carrier != QSIM_CARRIER_NONE) {
         double arg = (TWO_PI * slot(&s->freq, row)) * t + slot(&s->phase, row);
@@ -170,6 +205,8 @@ static double eval_signal(const qsim_signal *s, double t, const double *row) {
     } else if (s->envelope == QSIM_ENV_ERF_SQUARED) {
         double sg = slot(&s->sigma, row);
         env = 0.5 * (erf((t - slot(&s->t1, row)) / sg) - erf((t - slot(&s->t2, row)) / sg));
+    } else if (s->envelope == QSIM_ENV_TABLE) {
+        env = (s->table >= 1 && s->table <= p->n_tables) ? eval_table(p->tables[s->table - 1], t) : 0.0;
     }
     if (s->blend == QSIM_BLEND_NONE) return slot(&s->offset, row) + slot(&s->amp, row) * env * car;
     return env * (slot(&s->offset, row) + slot(&s->amp, row) * car) + (1 - env) * slot(&s->rest, row);
@@ -197,7 +234,7 @@ static void assemble_h(const qso_problem *p, double t, const double *row, double
     for (int k = 0; k < p->n_terms; k++) {
         const o_term *ot = &p->terms[k];
         const qsim_term *td = &ot->desc;
-        double s = eval_signal(&td->signal, t, row);
+        double s = eval_signal(p, &td->signal, t, row);
         if (td->kind == QSIM_TERM_SCALAR) {
             for (int i = 0; i < dd; i++) {
                 ham[2 * i] += s * ot->atom_a[2 * i];
@@ -307,7 +344,7 @@ typedef struct {
 static void lind_matrix(const rhs_ctx *c, int i, double t, double *lm) {
     const o_lind *ol = &c->p->linds[i];
     const int dd = c->d * c->d;
-    double s = ol->has_scale ? eval_signal(&ol->scale, t, c->row) : 1.0;
+    double s = ol->has_scale ? eval_signal(c->p, &ol->scale, t, c->row) : 1.0;
     for (int q = 0; q < dd; q++) {
         lm[2 * q] = s * ol->op[2 * q];
         lm[2 * q + 1] = s * ol->op[2 * q + 1];

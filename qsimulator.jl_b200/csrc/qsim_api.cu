@@ -77,6 +77,7 @@ struct qsim_problem::DeviceCopy {
     double2 *pair_w = nullptr;
     EvalDesc *evals = nullptr;
     double *dyn_rec = nullptr;       // 64-byte records of the time-dependent slots
+    double *tables = nullptr;        // tabulated envelopes (nullptr when the problem has none)
     int fast_ok = 0, fast_chA = 0, fast_chB = 0;  // records are in (constant, channel A, channel B) order
     uint32_t *ell_packed = nullptr;  // row-split kernels
     int packed_stride = -1;
@@ -86,6 +87,8 @@ struct qsim_problem::DeviceCopy {
         ell_packed = nullptr;
         cudaFree(dyn_rec);
         dyn_rec = nullptr;
+        cudaFree(tables);
+        tables = nullptr;
         cudaFree(ell); cudaFree(row_len); cudaFree(slot_ptr); cudaFree(pair_chan); cudaFree(pair_w); cudaFree(evals);
         ell = nullptr; row_len = nullptr; slot_ptr = nullptr; pair_chan = nullptr; pair_w = nullptr; evals = nullptr;
     }
@@ -230,11 +233,33 @@ static int check_slot(const qsim_problem *p, const qsim_slot &s, const char *wha
     return QSIM_OK;
 }
 static int check_signal(const qsim_problem *p, const qsim_signal &s) {
-    if (s.carrier < 0 || s.carrier > 2 || s.envelope < 0 || s.envelope > 2 || s.blend < 0 || s.blend > 1)
+    if (s.carrier < 0 || s.carrier > 2 || s.envelope < 0 || s.envelope > 3 || s.blend < 0 || s.blend > 1)
         return fail(QSIM_ERR_ARG, "signal: unknown carrier / envelope / blend");
+    if (s.envelope == QSIM_ENV_TABLE && (s.table < 1 || s.table > (int)p->table_offset.size()))
+        return fail(QSIM_ERR_ARG, "signal: table id does not name a table added with qsim_problem_add_table");
     const qsim_slot *sl[8] = {&s.offset, &s.amp, &s.freq, &s.phase, &s.t1, &s.t2, &s.sigma, &s.rest};
     for (auto q : sl)
         if (int rc = check_slot(p, *q, "signal")) return rc;
+    return QSIM_OK;
+}
+
+int qsim_problem_add_table(qsim_problem *p, double t_start, double t_end, int n_seg, int n_coef, const double *coef,
+                           int32_t *table_id) {
+    if (int rc = check_open(p)) return rc;
+    if (!coef || !table_id) return fail(QSIM_ERR_ARG, "NULL argument");
+    if (!(t_end > t_start) || !std::isfinite(t_start) || !std::isfinite(t_end))
+        return fail(QSIM_ERR_ARG, "table: need t_start < t_end");
+    if (n_seg < 1 || n_seg > (1 << 20) || n_coef < 2 || n_coef > 16)
+        return fail(QSIM_ERR_ARG, "table: n_seg must be in [1, 2^20] and n_coef in [2, 16]");
+    for (size_t i = 0; i < (size_t)n_seg * n_coef; i++)
+        if (!std::isfinite(coef[i])) return fail(QSIM_ERR_ARG, "table: non-finite coefficient");
+    p->table_offset.push_back((int32_t)p->tables.size());
+    p->tables.push_back(t_start);
+    p->tables.push_back((double)n_seg / (t_end - t_start));
+    p->tables.push_back((double)n_seg);
+    p->tables.push_back((double)n_coef);
+    p->tables.insert(p->tables.end(), coef, coef + (size_t)n_seg * n_coef);
+    *table_id = (int32_t)p->table_offset.size();  // ids start at 1; 0 means "no table"
     return QSIM_OK;
 }
 
@@ -584,6 +609,7 @@ static int ensure_device_copy(qsim_ctx *c, qsim_problem *p, int w, qsim_problem:
     CU(upload(&dc->pair_chan, g.pair_chan));
     CU(upload(&dc->pair_w, w2));
     CU(upload(&dc->evals, g.evals));
+    if (!g.tables.empty()) CU(upload(&dc->tables, g.tables));
     {
         // {w0, w1, w2 (re, im), ch0, ch1, ch2, pad}: unused pairs carry weight 0 on the constant channel.
         // When the time-dependent slots involve only the constant channel and at most two time-dependent
@@ -766,6 +792,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.g.pair_w = dc->pair_w;
     a.g.evals = dc->evals;
     a.g.tab = c->d_tab;
+    a.g.tables = dc->tables;
     a.cheb = c->d_cheb;
     a.dyn_chan_mask = 0;
     bool any_dyn = false;

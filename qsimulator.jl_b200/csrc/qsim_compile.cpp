@@ -281,6 +281,17 @@ void build_generator(const qsim_problem &p, int which, Generator &g) {
     g.n_dyn_slots = n_dyn;
     g.n_chan = (int)ca.chan_dynamic.size();
     g.evals = ca.evals;
+    // tabulated envelopes: table id (1-based) -> 1 + offset into the flat table array
+    g.tables = p.tables;
+    for (auto &e : g.evals) {
+        if (e.sig.envelope == QSIM_ENV_TABLE) {
+            if (e.sig.table < 1 || e.sig.table > (int)p.table_offset.size())
+                throw std::runtime_error("signal refers to a table that was not added");
+            e.sig.table = 1 + p.table_offset[(size_t)e.sig.table - 1];
+        } else {
+            e.sig.table = 0;
+        }
+    }
     g.slot_ptr.push_back(0);
     for (int i = 0; i < ns; i++) {
         for (auto &kv : slot_expr[order[i]]) {
@@ -353,7 +364,7 @@ void host_eval_generator(const Generator &g, double t, const double *row, cplx *
     chan[0] = 1.0;
     for (const auto &e : g.evals) {
         ResolvedEval r;
-        resolve_eval(e, row, r);
+        resolve_eval(e, row, g.tables.empty() ? nullptr : g.tables.data(), r);
         double o0, o1;
         run_resolved(r, tab.freq, tab.anh, t, &o0, &o1);
         chan[r.out_chan] = o0;

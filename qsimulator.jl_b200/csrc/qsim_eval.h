@@ -24,14 +24,36 @@ struct SeriesTables {
     double anh[31];
 };
 
-// One evaluator with its slots resolved for a trajectory (18 doubles; lives in shared memory).
+// One evaluator with its slots resolved for a trajectory (20 doubles; lives in shared memory).
 struct ResolvedEval {
     int32_t kind, carrier, envelope, blend, num_terms, out_chan, dynamic, _pad;
     double offset, amp, w, phase, t1, t2, sigma, rest;  // w = 2*pi*freq
     double rate;                                        // ROTATING
     double EC, EC2, EJs, EJp;                           // TRANSMON: EC, 2*EC, EJ1^2+EJ2^2, 2*EJ1*EJ2
     double slot;                                        // SLOT
+    const double *tab;                                  // ENV_TABLE: {t_start, 1/h, n_seg, n_coef, coef...}
+    double _pad2;
 };
+static_assert(sizeof(ResolvedEval) == 160, "ResolvedEval is copied as ten 16-byte words");
+
+// Tabulated envelope: segment lookup + Clenshaw (qsim_problem_add_table).
+QSIM_HD double eval_table(const double *T, double t) {
+    const int n_seg = (int)T[2], nc = (int)T[3];
+    const double u = (t - T[0]) * T[1];
+    int k = (int)floor(u);
+    k = k < 0 ? 0 : (k >= n_seg ? n_seg - 1 : k);
+    double x = 2.0 * (u - (double)k) - 1.0;
+    x = x < -1.0 ? -1.0 : (x > 1.0 ? 1.0 : x);   // constant continuation outside [t_start, t_end]
+    const double *c = T + 4 + (size_t)k * nc;
+    double b1 = 0.0, b2 = 0.0;
+    const double x2 = 2.0 * x;
+    for (int j = nc - 1; j >= 1; j--) {
+        const double b0 = fma(x2, b1, c[j] - b2);
+        b2 = b1;
+        b1 = b0;
+    }
+    return fma(x, b1, c[0] - b2);
+}
 
 QSIM_HD double slot_value(const qsim_slot &s, const double *row) { return s.param >= 0 ? row[s.param] : s.value; }
 
@@ -39,7 +61,7 @@ QSIM_HD bool signal_is_dynamic(const qsim_signal &s) {
     return s.carrier != QSIM_CARRIER_NONE || s.envelope != QSIM_ENV_NONE;
 }
 
-QSIM_HD void resolve_eval(const EvalDesc &e, const double *row, ResolvedEval &r) {
+QSIM_HD void resolve_eval(const EvalDesc &e, const double *row, const double *tables, ResolvedEval &r) {
     r.kind = e.kind;
     r.carrier = e.sig.carrier;
     r.envelope = e.sig.envelope;
@@ -63,6 +85,8 @@ QSIM_HD void resolve_eval(const EvalDesc &e, const double *row, ResolvedEval &r)
     r.EJs = EJ1 * EJ1 + EJ2 * EJ2;
     r.EJp = 2.0 * EJ1 * EJ2;
     r.slot = slot_value(e.slot, row);
+    r.tab = (e.sig.envelope == QSIM_ENV_TABLE && e.sig.table > 0 && tables) ? tables + (e.sig.table - 1) : nullptr;
+    r._pad2 = 0.0;
 }
 
 QSIM_HD double eval_signal(const ResolvedEval &s, double t) {
@@ -76,6 +100,8 @@ QSIM_HD double eval_signal(const ResolvedEval &s, double t) {
         env = exp(-0.5 * (x * x));
     } else if (s.envelope == QSIM_ENV_ERF_SQUARED) {
         env = 0.5 * (erf((t - s.t1) / s.sigma) - erf((t - s.t2) / s.sigma));
+    } else if (s.envelope == QSIM_ENV_TABLE) {
+        env = s.tab ? eval_table(s.tab, t) : 0.0;
     }
     if (s.blend == QSIM_BLEND_NONE) return s.offset + s.amp * env * car;
     return env * (s.offset + s.amp * car) + (1.0 - env) * s.rest;

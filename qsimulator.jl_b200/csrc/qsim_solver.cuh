@@ -35,7 +35,6 @@
 
 namespace qsim {
 
-static_assert(sizeof(ResolvedEval) == 18 * sizeof(double), "ResolvedEval layout");
 
 struct DevGenerator {
     int n, max_nnz, n_slots, n_dyn_slots, n_chan, n_evals;
@@ -47,6 +46,7 @@ struct DevGenerator {
     const double2 *pair_w;
     const EvalDesc *evals;
     const SeriesTables *tab;
+    const double *tables;     // tabulated envelopes (flat; see Generator::tables) or nullptr
 };
 
 struct LaunchArgs {
@@ -335,10 +335,10 @@ struct Kern {
     static __device__ __forceinline__ void load_resolved(uint32_t addr, ResolvedEval &r) {
         union {
             ResolvedEval r;
-            double2 q[9];
+            double2 q[10];
         } ld;
 #pragma unroll
-        for (int i = 0; i < 9; i++) ld.q[i] = lds2(addr + 16 * i);
+        for (int i = 0; i < 10; i++) ld.q[i] = lds2(addr + 16 * i);
         r = ld.r;
     }
 
@@ -842,7 +842,7 @@ struct Kern {
                 reinterpret_cast<const ResolvedEval *>(smem_gen + (g.sm_rev - g.sm_tab) / 8));
             for (int e = g.team_thread; e < a.g.n_evals; e += g.team_threads) {
                 ResolvedEval r;
-                resolve_eval(a.g.evals[e], prow, r);
+                resolve_eval(a.g.evals[e], prow, a.g.tables, r);
                 rev[e] = r;
             }
             for (int s = g.team_thread; s < 5; s += g.team_threads) sts1(g.sm_chan + 8u * (s * a.ncp), 1.0);

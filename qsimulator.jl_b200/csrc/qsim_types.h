@@ -59,6 +59,9 @@ struct Generator {
     std::vector<int32_t> pair_chan;
     std::vector<cplx> pair_w;
     std::vector<EvalDesc> evals;
+    // tabulated envelopes, flat: per table {t_start, 1/h, n_seg, n_coef, coef[n_seg][n_coef]}; an evaluator's
+    // sig.table holds 1 + the offset of its table in this array (0: none)
+    std::vector<double> tables;
     int64_t nnz = 0;           // total stored entries (executed complex MACs per column per RHS)
     bool imag_only = false;    // every value slot is purely imaginary (A = i B, B real): real H, no dissipator
 };
@@ -81,6 +84,8 @@ struct qsim_problem {
     };
     std::vector<Term> terms;
     std::vector<Lind> linds;
+    std::vector<double> tables;          // flat table storage (layout as Generator::tables)
+    std::vector<int32_t> table_offset;   // table id -> offset into `tables`
     qsim::Generator gen[2];  // [0] unitary (n = d), [1] Lindblad (n = d^2)
     bool gen_built[2] = {false, false};
     // device copies of the generators, one per CUDA device that has solved this problem (shared by the

@@ -5,7 +5,7 @@ systems (systems.jl), operators and drive factories (operators.jl), CompositeQSy
 assembly (composite_systems.jl) and the four solvers (time_evolution.jl:29-164), which call
 the CUDA shared library through the C ABI of include/qsim_b200.h.  There is no CPU fallback.
 """
-from .signals import Param, Signal, ComplexSignal, Const, Cos, Sin
+from .signals import Param, Signal, ComplexSignal, Const, Cos, Sin, Table, tabulated
 from .systems import (HermitianSpec, ResonatorSpec, TransmonSpec, DuffingSpec, QSystem, LiteralHermitian,
                       Resonator, DuffingTransmon, PerturbativeTransmon, RotatingFrameSystem, label, dimension,
                       spec, hamiltonian, duffing_hamiltonian)

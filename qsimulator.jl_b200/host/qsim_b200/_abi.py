@@ -21,7 +21,7 @@ class Slot(C.Structure):
 
 
 class SignalStruct(C.Structure):
-    _fields_ = [("carrier", C.c_int32), ("envelope", C.c_int32), ("blend", C.c_int32), ("_pad", C.c_int32),
+    _fields_ = [("carrier", C.c_int32), ("envelope", C.c_int32), ("blend", C.c_int32), ("table", C.c_int32),
                 ("offset", Slot), ("amp", Slot), ("freq", Slot), ("phase", Slot),
                 ("t1", Slot), ("t2", Slot), ("sigma", Slot), ("rest", Slot)]
 
@@ -65,15 +65,21 @@ def make_slot(x) -> Slot:
     return Slot(param=-1, value=float(x))
 
 
-def make_signal(s: Signal) -> SignalStruct:
-    return SignalStruct(carrier=s.carrier, envelope=s.envelope, blend=s.blend,
+def make_signal(s: Signal, table_ids=None) -> SignalStruct:
+    """table_ids: {id(Table) -> 1-based id in the problem being built} for tabulated envelopes."""
+    table = 0
+    if s.table is not None:
+        if table_ids is None or id(s.table) not in table_ids:
+            raise ValueError("tabulated envelope was not registered with the problem")
+        table = table_ids[id(s.table)]
+    return SignalStruct(carrier=s.carrier, envelope=s.envelope, blend=s.blend, table=table,
                         offset=make_slot(s.offset), amp=make_slot(s.amp), freq=make_slot(s.freq),
                         phase=make_slot(s.phase), t1=make_slot(s.t1), t2=make_slot(s.t2),
                         sigma=make_slot(s.sigma), rest=make_slot(s.rest))
 
 
-def make_term(t: LoweredTerm) -> TermStruct:
-    return TermStruct(kind=t.kind, num_terms=int(t.num_terms), signal=make_signal(t.signal),
+def make_term(t: LoweredTerm, table_ids=None) -> TermStruct:
+    return TermStruct(kind=t.kind, num_terms=int(t.num_terms), signal=make_signal(t.signal, table_ids),
                       rate=make_slot(t.rate), anharm=make_slot(t.anharm), rot=make_slot(t.rot),
                       EC=make_slot(t.EC), EJ1=make_slot(t.EJ1), EJ2=make_slot(t.EJ2))
 

@@ -20,7 +20,8 @@ LIB_PATH = os.environ.get("QSIM_B200_LIB", os.path.join(PKG_ROOT, "lib", "libqsi
 EXPORTS = [
     "qsim_version", "qsim_last_error", "qsim_default_opts", "qsim_create", "qsim_destroy", "qsim_device_info",
     "qsim_synchronize", "qsim_alloc_pinned", "qsim_free_pinned", "qsim_problem_create", "qsim_problem_destroy",
-    "qsim_problem_set_h0", "qsim_problem_add_term", "qsim_problem_add_lindblad", "qsim_problem_finalize",
+    "qsim_problem_set_h0", "qsim_problem_add_term", "qsim_problem_add_lindblad", "qsim_problem_add_table",
+    "qsim_problem_finalize",
     "qsim_problem_eval", "qsim_unitary_propagator", "qsim_unitary_state", "qsim_me_propagator", "qsim_me_state",
     "qsim_solve_selected", "qsim_solve_multi", "qsim_problem_flops_per_rhs", "qsim_problem_kernel_name", "qsim_launch_count",
     "qsim_peak_fp64",
@@ -62,6 +63,7 @@ def lib():
     L.qsim_problem_set_h0.argtypes = [vp, dp]
     L.qsim_problem_add_term.argtypes = [vp, C.POINTER(_abi.TermStruct), dp, dp, C.POINTER(C.c_int32)]
     L.qsim_problem_add_lindblad.argtypes = [vp, dp, C.POINTER(_abi.SignalStruct)]
+    L.qsim_problem_add_table.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int, dp, C.POINTER(C.c_int32)]
     L.qsim_problem_finalize.argtypes = [vp]
     L.qsim_problem_eval.argtypes = [vp, C.c_int, C.c_double, dp, dp]
     sig_prop = [vp, vp, C.c_int64, vp, vp, C.c_int, C.c_int64, C.POINTER(_abi.SolverOpts), vp, vp]
@@ -160,6 +162,7 @@ class PinnedArray:
             pass
 
 
+dp_t = C.POINTER(C.c_double)
 WHICH = {"unitary_propagator": 0, "unitary_state": 1, "me_propagator": 2, "me_state": 3}
 
 
@@ -176,8 +179,14 @@ class Problem:
         check(L.qsim_problem_create(spec.d, spec.n_params, C.byref(self._h)))
         p, keep = _abi.cplx_ptr(spec.h0)
         check(L.qsim_problem_set_h0(self._h, p))
+        table_ids = {}
+        for tb in spec.tables or []:
+            tid = C.c_int32()
+            check(L.qsim_problem_add_table(self._h, tb.t_start, tb.t_end, tb.n_seg, tb.n_coef,
+                                           tb.coef.ctypes.data_as(dp_t), C.byref(tid)))
+            table_ids[id(tb)] = tid.value
         for lt, a, b, levels in spec.terms:
-            ts = _abi.make_term(lt)
+            ts = _abi.make_term(lt, table_ids)
             pa, ka = _abi.cplx_ptr(a)
             pb, kb = _abi.cplx_ptr(b)
             pl, lv = None, None
@@ -190,7 +199,7 @@ class Problem:
             if scale is None:
                 check(L.qsim_problem_add_lindblad(self._h, po, None))
             else:
-                ss = _abi.make_signal(scale)
+                ss = _abi.make_signal(scale, table_ids)
                 check(L.qsim_problem_add_lindblad(self._h, po, C.byref(ss)))
         check(L.qsim_problem_finalize(self._h))
 

@@ -187,6 +187,7 @@ class ProblemSpec:
     h0: np.ndarray
     terms: List[Tuple[LoweredTerm, Optional[np.ndarray], Optional[np.ndarray], Optional[np.ndarray]]]
     lindblads: List[Tuple[np.ndarray, Optional[Signal]]]
+    tables: List = None     # distinct signals.Table objects referenced by the terms (qsim_problem_add_table order)
 
 
 def _levels(cqs: CompositeQSystem, pos: int) -> np.ndarray:
@@ -228,4 +229,9 @@ def lower(cqs: CompositeQSystem, n_params: Optional[int] = None) -> ProblemSpec:
         n_params = max_p + 1
     if n_params <= max_p:
         raise ValueError(f"n_params={n_params} but a term uses Param({max_p})")
-    return ProblemSpec(d=d, n_params=n_params, h0=composite_hamiltonian(cqs), terms=terms, lindblads=lind)
+    tables = []
+    for sig in [t[0].signal for t in terms] + [sc for _, sc in lind if sc is not None]:
+        if sig.table is not None and all(sig.table is not tb for tb in tables):
+            tables.append(sig.table)
+    return ProblemSpec(d=d, n_params=n_params, h0=composite_hamiltonian(cqs), terms=terms, lindblads=lind,
+                       tables=tables)

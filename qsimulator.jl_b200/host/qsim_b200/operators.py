@@ -166,7 +166,8 @@ def _as_signal(drive) -> Signal:
     if isinstance(drive, (int, float, Param)):
         return Const(drive)
     raise TypeError(
-        "drive must be a qsim_b200 Signal (Cos/Sin/Const/...): opaque callables cannot cross the C ABI")
+        "drive must be a qsim_b200 Signal (Cos/Sin/Const/...): opaque callables cannot cross the C ABI; "
+        "wrap an arbitrary closure with tabulated(fn, t_start, t_end)")
 
 
 def dipole_drive(q, drive, rotation_rate: Scalar = 0.0) -> ParametricHamiltonian:

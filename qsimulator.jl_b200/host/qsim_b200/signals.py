@@ -9,6 +9,7 @@ per-trajectory parameter row of a sweep.
 
   carrier = 1 | cos((2*pi*freq)*t + phase) | sin((2*pi*freq)*t + phase)
   env     = 1 | exp(-0.5*((t-t1)/sigma)**2) | 0.5*(erf((t-t1)/sigma) - erf((t-t2)/sigma))
+              | a tabulated closure (piecewise Chebyshev series, `tabulated(fn, t0, t1)`)
   blend NONE: s = offset + amp*env*carrier
   blend REST: s = env*(offset + amp*carrier) + (1-env)*rest
 
@@ -19,10 +20,12 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field, replace
-from typing import Optional, Sequence, Union
+from typing import Callable, Optional, Sequence, Union
+
+import numpy as np
 
 CARRIER_NONE, CARRIER_COS, CARRIER_SIN = 0, 1, 2
-ENV_NONE, ENV_GAUSSIAN, ENV_ERF_SQUARED = 0, 1, 2
+ENV_NONE, ENV_GAUSSIAN, ENV_ERF_SQUARED, ENV_TABLE = 0, 1, 2, 3
 BLEND_NONE, BLEND_REST = 0, 1
 
 
@@ -54,6 +57,77 @@ def max_param_index(*xs) -> int:
     return m
 
 
+class Table:
+    """A real function of time sampled into a piecewise Chebyshev series (qsim_problem_add_table): n_seg equal
+    segments over [t_start, t_end], n_coef coefficients each, end values continued outside.  This is how an
+    opaque closure `t -> Real` of the reference (composite_systems.jl:40-50) reaches the device.  `fn` is kept
+    so that the host mirror still calls the closure itself, like the reference does."""
+
+    def __init__(self, t_start: float, t_end: float, coef: np.ndarray, fn: Optional[Callable] = None):
+        self.t_start, self.t_end = float(t_start), float(t_end)
+        self.coef = np.ascontiguousarray(coef, dtype=np.float64)
+        if self.coef.ndim != 2 or not (2 <= self.coef.shape[1] <= 16) or not (self.t_end > self.t_start):
+            raise ValueError("Table needs coef[n_seg, 2..16] and t_start < t_end")
+        self.fn = fn
+
+    @property
+    def n_seg(self) -> int:
+        return self.coef.shape[0]
+
+    @property
+    def n_coef(self) -> int:
+        return self.coef.shape[1]
+
+    def eval(self, t):
+        """The piecewise polynomial itself (same lookup and Clenshaw recurrence as the device and the oracle)."""
+        t = np.asarray(t, dtype=np.float64)
+        u = (t - self.t_start) * (self.n_seg / (self.t_end - self.t_start))
+        k = np.clip(np.floor(u).astype(np.int64), 0, self.n_seg - 1)
+        x = np.clip(2.0 * (u - k) - 1.0, -1.0, 1.0)
+        c = self.coef[k]                       # [..., n_coef]
+        b1 = np.zeros_like(x)
+        b2 = np.zeros_like(x)
+        for j in range(self.n_coef - 1, 0, -1):
+            b1, b2 = 2.0 * x * b1 + (c[..., j] - b2), b1
+        return x * b1 + (c[..., 0] - b2)
+
+    @staticmethod
+    def from_function(fn: Callable, t_start: float, t_end: float, n_coef: int = 12, tol: float = 1e-14,
+                      max_seg: int = 1 << 16) -> "Table":
+        """Sample `fn` on [t_start, t_end]: the segment count doubles until the series matches `fn` at 2*n_coef
+        off-node points per segment to tol * max|fn|."""
+        def f(ts):
+            try:
+                v = np.asarray(fn(ts), dtype=np.float64)
+                if v.shape == ts.shape:
+                    return v
+            except Exception:
+                pass
+            return np.array([float(fn(float(x))) for x in ts.ravel()]).reshape(ts.shape)
+
+        N = n_coef
+        j = np.arange(N)
+        nodes = np.cos(np.pi * (j + 0.5) / N)                              # x_j
+        dct = (2.0 / N) * np.cos(np.pi * np.outer(np.arange(N), j + 0.5) / N)
+        dct[0] *= 0.5
+        chk = np.cos(np.pi * (np.arange(2 * N) + 0.25) / (2 * N))
+        n_seg = 1
+        while True:
+            h = (t_end - t_start) / n_seg
+            left = t_start + h * np.arange(n_seg)
+            coef = f(left[:, None] + 0.5 * h * (1.0 + nodes[None, :])) @ dct.T
+            tab = Table(t_start, t_end, coef, fn)
+            tc = left[:, None] + 0.5 * h * (1.0 + chk[None, :])
+            want = f(tc)
+            err = np.max(np.abs(tab.eval(tc) - want))
+            scale = max(np.max(np.abs(want)), 1e-300)
+            if err <= tol * scale or n_seg >= max_seg:
+                if err > 1e-9 * scale:
+                    raise ValueError(f"could not tabulate the function to 1e-9 with {n_seg} segments (error {err / scale:.1e})")
+                return tab
+            n_seg *= 2
+
+
 @dataclass(frozen=True)
 class Signal:
     carrier: int = CARRIER_NONE
@@ -67,6 +141,7 @@ class Signal:
     t2: Scalar = 0.0
     sigma: Scalar = 1.0
     rest: Scalar = 0.0
+    table: Optional[Table] = None      # ENV_TABLE
 
     FIELDS = ("offset", "amp", "freq", "phase", "t1", "t2", "sigma", "rest")
 
@@ -85,6 +160,10 @@ class Signal:
         elif self.envelope == ENV_GAUSSIAN:
             x = (t - r(self.t1)) / r(self.sigma)
             env = math.exp(-0.5 * (x * x))
+        elif self.envelope == ENV_TABLE:
+            # the closure itself when there is one (what the reference would call), else the table
+            tb = self.table
+            env = float(tb.fn(min(max(t, tb.t_start), tb.t_end))) if tb.fn is not None else float(tb.eval(t))
         else:
             s = r(self.sigma)
             env = 0.5 * (math.erf((t - r(self.t1)) / s) - math.erf((t - r(self.t2)) / s))
@@ -103,6 +182,15 @@ class Signal:
         if rest is None:
             return replace(self, envelope=ENV_ERF_SQUARED, t1=t1, t2=t2, sigma=sigma)
         return replace(self, envelope=ENV_ERF_SQUARED, blend=BLEND_REST, t1=t1, t2=t2, sigma=sigma, rest=rest)
+
+
+def tabulated(fn: Callable, t_start: float, t_end: float, amp: Scalar = 1.0, offset: Scalar = 0.0,
+              n_coef: int = 12, tol: float = 1e-14) -> Signal:
+    """t -> offset + amp*fn(t) for an arbitrary real closure `fn` on [t_start, t_end] (constant continuation
+    outside): the generic path for the reference's opaque drive closures.  Combine with a carrier through
+    dataclasses.replace(sig, carrier=..., freq=...) for shaped microwave pulses."""
+    return Signal(envelope=ENV_TABLE, amp=amp, offset=offset,
+                  table=Table.from_function(fn, t_start, t_end, n_coef=n_coef, tol=tol))
 
 
 def Const(value: Scalar) -> Signal:

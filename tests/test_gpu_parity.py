@@ -336,3 +336,24 @@ def test_drive_windows_vs_direct_evaluation():
     a, _, _ = check_parity(cqs4, "me_propagator", np.array([0.0, 2.0]), p4[[5, 8000]])
     b, _, _ = check_parity(cqs4, "me_propagator", np.array([0.0, 2.0]), p4[[5, 8000]], opts=direct)
     assert max_rel_err(a, b) < 1e-10
+
+
+@pytest.mark.gpu
+def test_repeated_runs_are_bitwise_identical():
+    """Reductions are fixed-order and inter-warp exchanges are barrier-ordered, so every kernel mode must
+    reproduce itself bit for bit (a data race would show up as run-to-run differences): resident one-warp,
+    resident multi-warp team, streamed, row-split."""
+    from qsim_b200 import workloads as W
+    from qsim_b200._ffi import Problem
+    for name, n, tf in (("cfg2", 300, 3.0), ("cfg3", 150, 2.0), ("cfg4", 150, 0.5), ("cfg5", 4, 0.05)):
+        cqs, params, _, fn = W.config(name)
+        idx = np.linspace(0, len(params) - 1, n).astype(int)
+        pr = np.ascontiguousarray(params[idx])
+        ts = np.linspace(0.0, tf, 4)
+        P = Problem(cqs)
+        first, st0 = P.solve(fn, ts, params=pr)
+        assert np.all(st0["retcode"] == 0)
+        for _ in range(3):
+            again, st = P.solve(fn, ts, params=pr)
+            assert np.array_equal(first, again), name
+            assert np.array_equal(st0, st), name
