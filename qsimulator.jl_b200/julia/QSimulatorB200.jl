@@ -42,7 +42,7 @@ Slot(p::Param) = Slot(Int32(p.index - 1), Int32(0), 0.0)
 const Scalar = Union{Real,Param}
 
 struct CSignal
-    carrier::Int32; envelope::Int32; blend::Int32; _pad::Int32
+    carrier::Int32; envelope::Int32; blend::Int32; table::Int32   # table: id from qsim_problem_add_table (0: none)
     offset::Slot; amp::Slot; freq::Slot; phase::Slot; t1::Slot; t2::Slot; sigma::Slot; rest::Slot
 end
 struct CTerm
@@ -111,6 +111,8 @@ csignal(s::Signal) = CSignal(s.carrier, s.envelope, s.blend, 0, Slot(s.offset), 
                              Slot(s.phase), Slot(s.t1), Slot(s.t2), Slot(s.sigma), Slot(s.rest))
 as_signal(s::Signal) = s
 as_signal(x::Scalar) = ConstSignal(x)
+# Arbitrary closures reach the library as tabulated envelopes (qsim_problem_add_table + ENV_TABLE = 3; the Python
+# mirror's `tabulated(f, t0, t1)` shows the sampling).  This shim does not wire that path yet.
 as_signal(::Function) = error("opaque closures cannot cross the C ABI: pass a Signal (CosSignal/SinSignal/...)")
 
 # One lowered qsim_term before embedding
