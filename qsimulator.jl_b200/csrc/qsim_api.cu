@@ -432,7 +432,7 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
 
 static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int vm, int rs) {
     const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c3_t128, variants_r1c3_t256,
-                                              variants_r1c4_t256, variants_r2c1_t128, variants_r2c2_t128,
+                                              variants_r1c4_t256, variants_r2c1_t128,
                                               variants_r2c2_t256, variants_r3c1_t128, variants_r3c1_t256,
                                               variants_rowsplit};
     const KernelVariant *best = nullptr;

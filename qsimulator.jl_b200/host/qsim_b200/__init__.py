@@ -12,7 +12,7 @@ from .systems import (HermitianSpec, ResonatorSpec, TransmonSpec, DuffingSpec, Q
 from .transmon_series import (PERTURBATIVE_NUM_TERMS, xi_effective, perturbative_transmon_freq,
                               perturbative_transmon_anharm)
 from .operators import (raising, lowering, number, X, Y, X_Y, XY, flip_flop, decay, dephasing, dipole_drive,
-                        rwa_dipole, parametric_drive, xy_exchange_drive, ParametricHamiltonian,
+                        rwa_dipole, parametric_drive, xy_exchange_drive, scaled_operator, ParametricHamiltonian,
                         ParametricLindblad)
 from .composite import (CompositeQSystem, add_hamiltonian, add_lindblad, embed, embed_indices, embed_add,
                         find_indices, add_parametric_hamiltonians, lower, ProblemSpec)
@@ -20,5 +20,6 @@ from . import _abi
 from ._ffi import Context, Problem, QsimError, PinnedArray, default_context
 from .time_evolution import unitary_propagator, unitary_state, me_propagator, me_state
 from .sweep import shard_indices, shard_params, scatter_back, gather_results
+from .postprocess import populations, subspace_indices, subspace_block, average_gate_fidelity
 from .floquet import (floquet_propagator, floquet_rise_fall_propagator, choose_times_floquet,
                       decompose_times_floquet, unique_tol)

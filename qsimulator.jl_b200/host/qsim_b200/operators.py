@@ -203,6 +203,20 @@ def rwa_dipole(q, drive) -> ParametricHamiltonian:
     return ParametricHamiltonian(ham, terms)
 
 
+def scaled_operator(op: np.ndarray, drive) -> ParametricHamiltonian:
+    """t -> drive(t) * op for a fixed operator `op` on the subsystems the term is added to: the generic raw
+    closure `add_hamiltonian!(cqs, t -> f(t) * M, qs)` (composite_systems.jl:40-50).  With drive = Param(i)
+    (or Const(Param(i))) this is a *static* term whose strength is swept per trajectory, e.g. a coupling
+    g * X([q0, q1]) with g a sweep column."""
+    sig = _as_signal(drive)
+    mat = np.asarray(op, dtype=complex)
+
+    def ham(t, params=None):
+        return sig(t, params) * mat
+
+    return ParametricHamiltonian(ham, [LoweredTerm(TERM_SCALAR, sig, atom_a=mat)])
+
+
 def parametric_drive(q, drive) -> ParametricHamiltonian:
     """t -> hamiltonian(q, drive(t)) (operators.jl:265-268): a frequency drive on a
     DuffingTransmon (systems.jl:205-206) or a flux drive on a PerturbativeTransmon
