@@ -81,10 +81,16 @@ struct qsim_problem::DeviceCopy {
     int fast_ok = 0, fast_chA = 0, fast_chB = 0;  // records are in (constant, channel A, channel B) order
     uint32_t *ell_packed = nullptr;  // row-split kernels
     int packed_stride = -1;
+    uint32_t *blk_ell = nullptr;     // blocked kernels: row table and value slot ids (built by make_plan)
+    uint16_t *blk_slot = nullptr;
     ~DeviceCopy() { free_all(); }  // the owning device must be current
     void free_all() {
         cudaFree(ell_packed);
         ell_packed = nullptr;
+        cudaFree(blk_ell);
+        cudaFree(blk_slot);
+        blk_ell = nullptr;
+        blk_slot = nullptr;
         cudaFree(dyn_rec);
         dyn_rec = nullptr;
         cudaFree(tables);
@@ -380,24 +386,87 @@ struct Plan {
     int y_row_stride = 1, y_grp_stride = 1, rowsplit = 0;
     int off_dptr = 0, off_dw = 0, off_drec = 0, dyn_fast = 0;
     size_t smem = 0, scratch_per_team = 0;
+    // blocked variant (value mode 3): block rows, row table [1 + max blocks][n] and value slot ids
+    int blk_rows = 0, blk_nnz = 0;
+    std::vector<uint32_t> blk_ell;
+    std::vector<uint16_t> blk_slot;
 };
+
+// Blocked form of a generator for the value-mode-3 kernels: rows grouped R at a time, every off-diagonal entry
+// inside an R x R block (block row I, block column J != I) whose values are per-trajectory constants.
+// Returns false when the generator does not have that shape.
+static bool build_blocked(const Generator &g, int R, int capacity, Plan &pl) {
+    const int n = g.n;
+    if (n % R != 0 || !g.imag_only) return false;
+    const int nb = n / R;
+    std::vector<std::vector<int>> nbr((size_t)nb);
+    for (int r = 0; r < n; r++)
+        for (int j = 1; j < g.max_nnz; j++) {
+            const uint32_t e = g.ell[(size_t)j * n + r];
+            if ((e >> 16) == 0xFFFFu) continue;
+            if ((int)(e >> 16) < g.n_dyn_slots) return false;       // time-dependent off-diagonal entry
+            const int J = (int)(e & 0xFFFFu) / R, I = r / R;
+            if (J == I) return false;                               // off-diagonal entry inside the diagonal block
+            auto &v = nbr[(size_t)I];
+            if (std::find(v.begin(), v.end(), J) == v.end()) v.push_back(J);
+        }
+    int mb = 0;
+    for (auto &v : nbr) {
+        std::sort(v.begin(), v.end());
+        mb = std::max(mb, (int)v.size());
+    }
+    if (mb < 1 || mb + 1 > capacity) return false;
+    const int nnz = capacity, MB = capacity - 1;
+    pl.blk_rows = nb;
+    pl.blk_nnz = nnz;
+    pl.blk_ell.assign((size_t)nnz * n, 0);
+    pl.blk_slot.assign((size_t)nb * MB * R * R, (uint16_t)g.n_slots);  // default: the zero slot
+    for (int r = 0; r < n; r++) {
+        const int I = r / R, k = r % R;
+        pl.blk_ell[r] = g.ell[r];  // diagonal entry (own row, its slot)
+        for (int b = 0; b < MB; b++) {
+            const int J = b < (int)nbr[(size_t)I].size() ? nbr[(size_t)I][(size_t)b] : I;
+            pl.blk_ell[(size_t)(1 + b) * n + r] = (uint32_t)(R * J + k) | (0xFFFFu << 16);
+        }
+        for (int j = 1; j < g.max_nnz; j++) {
+            const uint32_t e = g.ell[(size_t)j * n + r];
+            if ((e >> 16) == 0xFFFFu) continue;
+            const int src = (int)(e & 0xFFFFu), J = src / R;
+            const int b = (int)(std::find(nbr[(size_t)I].begin(), nbr[(size_t)I].end(), J) - nbr[(size_t)I].begin());
+            pl.blk_slot[(((size_t)I * MB + b) * R + k) * R + (size_t)(src % R)] = (uint16_t)(e >> 16);
+        }
+    }
+    return true;
+}
 
 // Shared-memory wavefronts of the stage-vector gathers and stores for a candidate layout: the stage
 // buffer holds element (row, group g, column c) at 16-byte unit row*S + g*Cg + c.  A 128-bit shared
 // access is served a quarter warp (8 lanes) at a time; lanes hitting the same 16-byte bank group
 // (unit mod 8) at different addresses serialise.
-static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S, int Cg) {
+// blk_rows > 0: blocked variants (lane = block row + blk_rows * group, rows rpl*block_row + i) with their own
+// row table `ell` of `max_nnz` entries per row.
+static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S, int Cg, int blk_rows = 0,
+                        const uint32_t *ell = nullptr, int max_nnz = 0) {
     const int n = g.n;
+    if (!ell) {
+        ell = g.ell.data();
+        max_nnz = g.max_nnz;
+    }
     long cost = 0;
     for (int i = 0; i < rpl; i++) {
-        for (int j = 0; j <= g.max_nnz; j++) {  // j == max_nnz: the lane's own store
+        for (int j = 0; j <= max_nnz; j++) {  // j == max_nnz: the lane's own store
             for (int q = 0; q < 4; q++) {
                 int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 int seen[8][8];
                 for (int l = 8 * q; l < 8 * q + 8; l++) {
                     int gi = 0, r = l + 32 * i;
                     bool active = true;
-                    if (groups > 1) {
+                    if (blk_rows > 0) {
+                        active = l < groups * blk_rows;
+                        const int le = active ? l : groups * blk_rows - 1;
+                        gi = le / blk_rows;
+                        r = rpl * (le % blk_rows) + i;
+                    } else if (groups > 1) {
                         active = l < groups * n;
                         const int le = active ? l : groups * n - 1;
                         gi = le / n;
@@ -408,12 +477,12 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
                         r = n - 1;
                     }
                     int src = r;
-                    if (j == g.max_nnz) {
+                    if (j == max_nnz) {
                         if (!active) continue;  // inactive lanes do not store
                     } else if (j == 0) {
                         continue;  // diagonal operand comes from registers
                     } else {
-                        src = (int)(g.ell[(size_t)j * n + r] & 0xFFFFu);
+                        src = (int)(ell[(size_t)j * n + r] & 0xFFFFu);
                     }
                     const int unit = src * S + gi * Cg;
                     const int b = unit & 7;
@@ -434,7 +503,7 @@ static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int bloc
     const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c3_t128, variants_r1c3_t256,
                                               variants_r1c4_t256, variants_r2c1_t128,
                                               variants_r2c2_t256, variants_r3c1_t128, variants_r3c1_t256,
-                                              variants_rowsplit};
+                                              variants_rowsplit, variants_blocked};
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
         int cnt = 0;
@@ -481,8 +550,29 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     } else {
         return fail(QSIM_ERR_UNSUPPORTED, "state vectors longer than 864 entries have no kernel yet");
     }
-    const int cpb = pl.groups * cpl;
+    int cpb = pl.groups * cpl;
     pl.n_batches = (pl.ncols + cpb - 1) / cpb;
+    // Blocked variant (value mode 3) for small propagators whose couplings fall into 3 x 3 blocks (Kronecker
+    // structure with a 3-level last subsystem: the 2-transmon gates of cfg1/cfg2): every lane owns 3 consecutive
+    // rows of one column and each neighbour block is loaded once for its 9 multiply-adds, which cuts the
+    // shared-memory wavefronts per step by a quarter.  Measured on B200 it is only 1.7 % faster than the
+    // row-per-lane value-mode-2 kernel (the step is bound by its dependent chain, not by shared-memory
+    // throughput) and its 18 block values per lane push it to 255 registers, so it is opt-in: QSIM_BLOCKED=1.
+    bool blocked = false;
+    if (pl.identity && !pl.rowsplit && n % 3 == 0 && std::getenv("QSIM_BLOCKED")) {
+        const int nb = n / 3, gb = std::min(32 / nb, pl.ncols);
+        if (gb >= pl.ncols) {  // the whole propagator in one warp
+            for (int cap : {3, 5})
+                if (!blocked && find_variant(3, 1, cap, 128, 3, 0) && build_blocked(g, 3, cap, pl)) blocked = true;
+            if (blocked) {
+                rpl = 3;
+                cpl = 1;
+                pl.groups = gb;
+                cpb = gb;
+                pl.n_batches = 1;
+            }
+        }
+    }
     if (pl.rowsplit) {
         pl.team_warps = (n + 95) / 96;
         pl.streamed = pl.n_batches > 1 ? 1 : 0;
@@ -504,7 +594,9 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     pl.block = pl.team_warps * 32 * pl.teams_per_cta;
     // value mode: 2 when the generator is purely imaginary and only diagonal entries depend on time
     int vm = g.imag_only ? 1 : 0;
-    if (vm == 1 && !pl.rowsplit) {
+    if (blocked) {
+        vm = 3;
+    } else if (vm == 1 && !pl.rowsplit) {
         bool static_off = true;
         for (int j = 1; j < g.max_nnz && static_off; j++)
             for (int r = 0; r < n; r++) {
@@ -514,7 +606,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         // (with four entries per lane the extra value registers would spill: stay in mode 1)
         if (static_off && rpl * cpl <= 3 && find_variant(rpl, cpl, g.max_nnz, pl.block, 2, 0)) vm = 2;
     }
-    pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block, vm, pl.rowsplit);
+    pl.kv = find_variant(rpl, cpl, blocked ? pl.blk_nnz : g.max_nnz, pl.block, vm, pl.rowsplit);
     if (!pl.kv)
         return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
                                               std::to_string(g.max_nnz) + ")");
@@ -525,7 +617,8 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
             for (int S = (pl.groups - 1) * Cg + cpl; S <= (pl.groups - 1) * Cg + cpl + 16; S++) {
                 if (pl.groups == 1 && Cg > cpl) break;  // no groups: only the row stride matters
                 if (16 * n * S > 65535) continue;
-                const long c = layout_cost(g, rpl, cpl, pl.groups, S, Cg) * 64 + S;  // ties: smaller buffer
+                const long c = (blocked ? layout_cost(g, rpl, cpl, pl.groups, S, Cg, pl.blk_rows, pl.blk_ell.data(), pl.blk_nnz)
+                                        : layout_cost(g, rpl, cpl, pl.groups, S, Cg)) * 64 + S;  // ties: smaller buffer
                 if (best < 0 || c < best) {
                     best = c;
                     pl.y_row_stride = S;
@@ -536,7 +629,8 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         if (std::getenv("QSIM_DEBUG"))
             std::fprintf(stderr, "[qsim] n=%d groups=%d cpl=%d: stage layout S=%d Cg=%d wavefronts %ld (dense layout %ld)\n", n,
                          pl.groups, cpl, pl.y_row_stride, pl.y_grp_stride, best / 64,
-                         layout_cost(g, rpl, cpl, pl.groups, cpb, cpl));
+                         blocked ? layout_cost(g, rpl, cpl, pl.groups, cpb, cpl, pl.blk_rows, pl.blk_ell.data(), pl.blk_nnz)
+                                 : layout_cost(g, rpl, cpl, pl.groups, cpb, cpl));
     }
     if (g.n_slots > 4094)
         return fail(QSIM_ERR_UNSUPPORTED, "generator too large for the packed 16-bit slot offsets");
@@ -716,6 +810,10 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         CU(upload(&dc->ell_packed, packed));
         dc->packed_stride = pl.y_row_stride;
     }
+    if (pl.blk_rows > 0 && !dc->blk_ell) {
+        CU(upload(&dc->blk_ell, pl.blk_ell));
+        CU(upload(&dc->blk_slot, pl.blk_slot));
+    }
     packed_lock.unlock();
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : c->stream;
 
@@ -807,6 +905,12 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.fast_tables = (a.use_windows && dc->fast_ok) ? 1 : 0;
     a.fast_chA = dc->fast_chA;
     a.fast_chB = dc->fast_chB;
+    if (pl.blk_rows > 0) {
+        a.g.ell = dc->blk_ell;
+        a.g.max_nnz = pl.blk_nnz;
+        a.blk_slot = dc->blk_slot;
+        a.n_blk_rows = pl.blk_rows;
+    }
     a.ell_packed = dc->ell_packed;
     a.ell_rows = g.n + 8;
     a.ncols = pl.ncols;

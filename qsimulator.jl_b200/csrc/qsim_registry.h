@@ -22,6 +22,7 @@ QSIM_DECLARE(variants_r2c1_t128)
 QSIM_DECLARE(variants_r2c2_t256)  // 33-64 level propagators always stream their columns through an 8-warp team
 QSIM_DECLARE(variants_r3c1_t128) QSIM_DECLARE(variants_r3c1_t256)
 QSIM_DECLARE(variants_rowsplit)
+QSIM_DECLARE(variants_blocked)
 
 #define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \
     {                                                                                                     \

@@ -65,6 +65,8 @@ struct LaunchArgs {
     qsim_traj_stats *stats;
     unsigned long long *work_counter;
     double2 *scratch;     // streamed mode: [n_teams_total][4][n_batches*cpb*n]
+    const uint16_t *blk_slot;    // blocked variants: [n_blk_rows][(max_nnz-1)*RPL*RPL] slot ids of the block values
+    int n_blk_rows;              // blocked variants: block rows (= lanes per column)
     const uint32_t *ell_packed;  // row-split mode: [max_nnz][ell_rows] translated (source offset | slot offset << 16)
     int ell_rows;                // n + 8: eight zero-slot padding rows for lanes past the last row
     int team_warps, teams_per_cta, n_batches, groups, streamed;
@@ -273,6 +275,7 @@ struct Geo {
     uint32_t sm_y0, sm_y1;                      // this warp's two stage buffers (+ column offset)
     uint32_t sm_ctl;                            // this warp's control block: step-loop scalars parked in shared memory
     double stage_c;                             // kStageC[lane] for lanes 0..4 (fast_tables), set once per thread
+    int blk_row;                                // blocked variants: this lane's block row
     uint32_t v_stride;                          // bytes between value tables
 };
 
@@ -293,6 +296,14 @@ template <int RPL, int CPL, int MAXNNZ, int VM, bool RS>
 struct Kern {
     static constexpr bool IM = VM >= 1;
     static constexpr bool SV = VM == 2;
+    // VM == 3, "blocked": a lane owns RPL consecutive rows of one column and the off-diagonal part of the
+    // generator is stored as dense RPL x RPL blocks (static, purely imaginary, values in registers).  Entry
+    // 1 + b of row-slot k names row k of neighbour block b, so the RPL row-slots together load each
+    // neighbour block exactly once: RPL * (MAXNNZ - 1) operand loads serve RPL * RPL * (MAXNNZ - 1)
+    // multiply-adds (Kronecker-structured couplings reuse every operand RPL times).
+    static constexpr bool BLK = VM == 3;
+    static constexpr int NVS = BLK ? (MAXNNZ - 1) * RPL * RPL : RPL * MAXNNZ;  // static values held per lane
+    static_assert(!BLK || CPL == 1, "blocked variants hold one column per lane");
     static constexpr int E = RPL * CPL;
     static constexpr uint32_t VB = IM ? 8u : 16u;  // bytes per value slot (IM: imaginary part only)
     typedef double2 Vec[E];
@@ -612,8 +623,39 @@ struct Kern {
     // there (the next stage's partial combination) executes under the shared-memory latency.
     template <typename Hook = NoHook>
     static __device__ __forceinline__ void apply(const LaunchArgs &a, uint32_t Vs, uint32_t yb,
-                                                 const uint32_t (&ell)[RPL][MAXNNZ], const double (&vstat)[RPL][MAXNNZ],
+                                                 const uint32_t (&ell)[RPL][MAXNNZ], const double (&vstat)[NVS],
                                                  const int (&row_of)[RPL], const Vec &yreg, Vec &k, Hook hook = Hook()) {
+        if (BLK) {
+            constexpr int MB = MAXNNZ > 1 ? MAXNNZ - 1 : 1;  // (row-split variants instantiate MAXNNZ = 1; never blocked)
+            double vd[RPL];
+            double2 yy[MB][RPL], acc[RPL];
+#pragma unroll
+            for (int i = 0; i < RPL; i++) vd[i] = lds1(Vs + (ell[i][0] >> 16));
+#pragma unroll
+            for (int b = 0; b < MB; b++)
+#pragma unroll
+                for (int kk = 0; kk < RPL; kk++) yy[b][kk] = lds2(yb + (ell[kk][1 + b] & 0xFFFFu));
+            hook();
+#pragma unroll
+            for (int i = 0; i < RPL; i++) {
+                // A = i B with B real: (iB)(yr + i yi) = -B yi + i B yr
+                acc[i].x = -vd[i] * yreg[i].y;
+                acc[i].y = vd[i] * yreg[i].x;
+            }
+#pragma unroll
+            for (int b = 0; b < MB; b++)
+#pragma unroll
+                for (int kk = 0; kk < RPL; kk++)
+#pragma unroll
+                    for (int i = 0; i < RPL; i++) {
+                        const double v = vstat[(b * RPL + i) * RPL + kk];
+                        acc[i].x = fma(-v, yy[b][kk].y, acc[i].x);
+                        acc[i].y = fma(v, yy[b][kk].x, acc[i].y);
+                    }
+#pragma unroll
+            for (int i = 0; i < RPL; i++) k[i] = acc[i];
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < RPL; i++) {
             double2 acc[CPL];
@@ -669,7 +711,7 @@ struct Kern {
                         if (j < MAXNNZ) {
                             const uint32_t e = ell[i][j];
                             if (SV)
-                                vv[q] = make_double2(0.0, vstat[i][j]);  // time-independent, loaded once per trajectory
+                                vv[q] = make_double2(0.0, vstat[i * MAXNNZ + j]);  // time-independent, loaded once per trajectory
                             else if (IM)
                                 vv[q] = make_double2(0.0, lds1(Vs + (e >> 16)));
                             else
@@ -849,11 +891,19 @@ struct Kern {
         }
         team_sync(a.team_warps, g.bar_id);
         compute_tables<5>(a, g, smem_gen, t0, 0.0, true, 0);
-        double vstat[RPL][MAXNNZ];
+        double vstat[NVS];
+        if (BLK) {
+            // block values (per-trajectory constants): slot ids from the host-built table of this lane's block row
+            const uint16_t *bs = a.blk_slot + (size_t)g.blk_row * NVS;
 #pragma unroll
-        for (int i = 0; i < RPL; i++)
+            for (int q = 0; q < NVS; q++) vstat[q] = lds1(g.sm_V + VB * (uint32_t)__ldg(bs + q));
+        } else {
 #pragma unroll
-            for (int j = 0; j < MAXNNZ; j++) vstat[i][j] = (SV && j > 0) ? lds1(g.sm_V + (ell[i][j] >> 16)) : 0.0;
+            for (int i = 0; i < RPL; i++)
+#pragma unroll
+                for (int j = 0; j < MAXNNZ; j++)
+                    vstat[i * MAXNNZ + j] = (SV && j > 0) ? lds1(g.sm_V + (ell[i][j] >> 16)) : 0.0;
+        }
 
         Vec u, k1, k2, k3, k4, k5, k6, k7, tmp;
         int cur = 0;
@@ -1238,7 +1288,14 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     // that their (discarded) gathers broadcast instead of adding bank conflicts.
     int g_idx = 0, row0 = g.lane;
     bool lane_active = true;
-    if (a.groups > 1) {
+    g.blk_row = 0;
+    if (K::BLK) {
+        // lane -> (block row, column group): RPL consecutive rows of one column
+        lane_active = g.lane < a.groups * a.n_blk_rows;
+        const int le = lane_active ? g.lane : a.groups * a.n_blk_rows - 1;
+        g_idx = le / a.n_blk_rows;
+        g.blk_row = le - g_idx * a.n_blk_rows;
+    } else if (a.groups > 1) {
         lane_active = g.lane < a.groups * n;
         const int le = lane_active ? g.lane : a.groups * n - 1;
         g_idx = le / n;
@@ -1298,7 +1355,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     uint32_t ell[RPL][MAXNNZ];
 #pragma unroll
     for (int i = 0; i < RPL; i++) {
-        row_of[i] = row0 + 32 * i + (RS ? g.warp_in_team * 32 * RPL : 0);
+        row_of[i] = K::BLK ? g.blk_row * RPL + i : row0 + 32 * i + (RS ? g.warp_in_team * 32 * RPL : 0);
         row_ok[i] = lane_active && row_of[i] < n;
         const int row_eff = row_of[i] < n ? row_of[i] : n - 1;
         if (RS) row_of[i] = row_ok[i] ? row_of[i] : n + (row_of[i] - n) % 8;  // padding rows of the packed table

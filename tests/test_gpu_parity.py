@@ -357,3 +357,26 @@ def test_repeated_runs_are_bitwise_identical():
             again, st = P.solve(fn, ts, params=pr)
             assert np.array_equal(first, again), name
             assert np.array_equal(st0, st), name
+
+
+@pytest.mark.gpu
+def test_blocked_variant_opt_in(monkeypatch):
+    """QSIM_BLOCKED=1 selects the blocked kernels (3 consecutive rows per lane, dense 3 x 3 coupling blocks with
+    values in registers) for the 2-transmon propagators: same step sequence, results within rounding of the
+    default row-per-lane kernel and within 1e-8 of the oracle."""
+    from qsim_b200 import workloads as W
+    from qsim_b200._ffi import Problem
+    cqs, params, _, fn = W.config("cfg2")
+    pr = np.ascontiguousarray(params[np.linspace(0, len(params) - 1, 40).astype(int)])
+    ts = np.linspace(0.0, 5.0, 6)
+    P = Problem(cqs)
+    assert "_vm2_" in P.kernel_name(fn)
+    base, st0 = P.solve(fn, ts, params=pr)
+    monkeypatch.setenv("QSIM_BLOCKED", "1")
+    P2 = Problem(cqs)
+    assert "r3c1_nnz3" in P2.kernel_name(fn) and "_vm3_" in P2.kernel_name(fn)
+    blk, st1 = P2.solve(fn, ts, params=pr)
+    assert np.array_equal(st0["n_accept"], st1["n_accept"]) and np.array_equal(st0["n_reject"], st1["n_reject"])
+    assert np.max(np.abs(blk - base)) <= 1e-9
+    want, _ = co.OracleProblem(cqs).solve(co.UNITARY_PROPAGATOR, ts, pr, mode=0, n_threads=4)
+    assert np.max(np.abs(blk - want) / np.maximum(np.abs(want), 1e-3)) <= 1e-8
