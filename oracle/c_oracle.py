@@ -37,8 +37,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            build()
+        build()     # no-op when libqsim_oracle.so is newer than its sources
         L = C.CDLL(LIB_PATH)
         dp = C.POINTER(C.c_double)
         L.qso_problem_create.restype = C.c_void_p
