@@ -1,5 +1,7 @@
-"""Switching from QSimulator.jl: the reference's "lab frame parametric 2Q gate" benchmark system
-(/root/reference/benchmark/benchmarks.jl:125-146) swept over drive amplitude and frequency in ONE call.
+"""Switching from QSimulator.jl: a lab-frame parametric two-transmon gate (the system of
+/root/reference/benchmark/benchmarks.jl:125-146 with the transmon of test/integration_tests.jl:86, whose second
+flux-modulation sideband brings |01> and |10> into resonance near 118 MHz) swept over drive amplitude and
+frequency in ONE call.
 
 In the reference this is a Julia loop that rebuilds the CompositeQSystem and calls unitary_propagator per point:
 
@@ -27,16 +29,16 @@ from qsim_b200 import (CompositeQSystem, DuffingSpec, DuffingTransmon, Param, Pe
                        X, add_hamiltonian, average_gate_fidelity, parametric_drive, subspace_block, unitary_propagator)
 
 q0 = DuffingTransmon("q0", 3, DuffingSpec(3.94015, -0.1807))
-q1 = PerturbativeTransmon("q1", 3, TransmonSpec(0.172, 16.4, 0.55))
+q1 = PerturbativeTransmon("q1", 3, TransmonSpec(0.172, 12.71, 3.69))
 cqs = CompositeQSystem([q0, q1])
 add_hamiltonian(cqs, q0)
 add_hamiltonian(cqs, parametric_drive(q1, Sin(amp=Param(0), freq=Param(1))), q1)
 add_hamiltonian(cqs, 0.006 * X([q0, q1]), [q0, q1])
 
-amps = np.linspace(0.20, 0.45, 32)
-freqs = np.linspace(0.110, 0.134, 32)
+amps = np.linspace(0.28, 0.36, 32)
+freqs = np.linspace(0.112, 0.124, 32)
 params = np.array([(a, f) for a in amps for f in freqs])
-ts = np.arange(0.0, 201.0)
+ts = np.arange(0.0, 151.0)
 
 # full propagators: [n_points, n_ts, 9, 9]
 us = unitary_propagator(cqs, ts, params=params)
@@ -45,8 +47,9 @@ print("propagators:", us.shape)
 # or keep only what the sweep needs, reduced on the device: the |01> -> |10> population ...
 i01, i10 = 0 * 3 + 1, 1 * 3 + 0
 pop = unitary_propagator(cqs, ts, params=params, select=[(i10, i01)], abs2=True)[:, :, 0]
-best = np.unravel_index(np.argmax(pop[:, -1]), (len(amps), len(freqs)))
-print(f"largest 01->10 transfer at t=200 ns: {pop[:, -1].max():.4f} at amp={amps[best[0]]:.3f} Phi0, f={1e3 * freqs[best[1]]:.1f} MHz")
+point, k = np.unravel_index(np.argmax(pop), pop.shape)
+print(f"largest 01->10 transfer {pop[point, k]:.4f} at t = {ts[k]:.0f} ns, amp = {params[point, 0]:.3f} Phi0, "
+      f"f = {1e3 * params[point, 1]:.2f} MHz")
 
 # ... or the qubit-subspace block, for a gate fidelity against iSWAP (up to single-qubit phases this is only a
 # rough figure of merit; the point is that 16 numbers per propagator leave the GPU instead of 81)
