@@ -36,6 +36,15 @@ QSIM_DECLARE(variants_blocked)
             occupancy_solver<3, 1, 1, T, 1, I, true>                                                      \
     }
 
+#ifdef QSIM_FAST_BUILD
+// development builds (make EXTRA=-DQSIM_FAST_BUILD): only the capacity-5 value-mode-2 kernels (cfg1/cfg2)
+#define QSIM_DEFINE_VARIANTS(FN, R, C, T, B)                                                              \
+    const KernelVariant *FN(int *count) {                                                                 \
+        static const KernelVariant v[] = {QSIM_VARIANT(R, C, 5, T, B, 2)};                                \
+        *count = 1;                                                                                       \
+        return v;                                                                                         \
+    }
+#else
 // Row capacities 5 / 9 / 12 / 16: the generator rows are padded to the variant's capacity and applied
 // without per-entry branches (5 and 9 are the exact row lengths of the 2- and 3-transmon gate Hamiltonians).
 #define QSIM_DEFINE_VARIANTS(FN, R, C, T, B)                                                              \
@@ -48,5 +57,6 @@ QSIM_DECLARE(variants_blocked)
         *count = (int)(sizeof(v) / sizeof(v[0]));                                                         \
         return v;                                                                                         \
     }
+#endif
 
 }  // namespace qsim
