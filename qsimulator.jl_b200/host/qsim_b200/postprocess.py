@@ -40,3 +40,18 @@ def average_gate_fidelity(u_sub: np.ndarray, target: np.ndarray) -> np.ndarray:
     m = np.conj(target.T) @ u_sub
     tr = np.trace(m, axis1=-2, axis2=-1)
     return (np.real(np.sum(m * np.conj(m), axis=(-2, -1))) + np.abs(tr) ** 2) / (n * (n + 1))
+
+
+def superoperator(u: np.ndarray) -> np.ndarray:
+    """conj(U) (x) U: the column-major vec superoperator of rho -> U rho U' (the convention of me_propagator,
+    time_evolution.jl:85-87).  Broadcasts over leading axes."""
+    uc = np.conj(u)
+    return np.einsum("...ac,...bd->...abcd", uc, u).reshape(u.shape[:-2] + (u.shape[-2] ** 2, u.shape[-1] ** 2))
+
+
+def kraus_mix(us: np.ndarray, weights=None) -> np.ndarray:
+    """Average channel of a sweep over a noise parameter: sum_i w_i conj(U_i) (x) U_i over the first axis of
+    `us` (doc/Examples.ipynb cells 34-38: quasi-static flux noise as a mixture of unitaries)."""
+    us = np.asarray(us)
+    w = np.full(us.shape[0], 1.0 / us.shape[0]) if weights is None else np.asarray(weights, dtype=float)
+    return np.tensordot(w, superoperator(us), axes=(0, 0))

@@ -380,3 +380,24 @@ def test_blocked_variant_opt_in(monkeypatch):
     assert np.max(np.abs(blk - base)) <= 1e-9
     want, _ = co.OracleProblem(cqs).solve(co.UNITARY_PROPAGATOR, ts, pr, mode=0, n_threads=4)
     assert np.max(np.abs(blk - want) / np.maximum(np.abs(want), 1e-3)) <= 1e-8
+
+
+@pytest.mark.gpu
+def test_large_sweep_work_queue():
+    """50 000 short trajectories in one launch: every sweep point is fetched from the work queue exactly once
+    (results depend only on the point's parameters), nothing is skipped, and a sample agrees with the oracle."""
+    from qsim_b200 import workloads as W
+    from qsim_b200._ffi import Problem
+    cqs, params, _, fn = W.config("cfg2")
+    n = 50_000
+    pr = np.ascontiguousarray(params[np.arange(n) % len(params)])
+    ts = np.array([0.0, 0.25])
+    P = Problem(cqs)
+    got, st = P.solve(fn, ts, params=pr)
+    assert np.all(st["retcode"] == 0) and np.all(st["t_final"] == 0.25)
+    # rows n and n + 4096 carry the same parameters: identical results, bit for bit
+    assert np.array_equal(got[:4096], got[4096:8192]) and np.array_equal(got[:4096], got[40960:45056])
+    idx = np.array([0, 1, 4095, 4096, 17_123, 49_999])
+    want, ost = co.OracleProblem(cqs).solve(co.UNITARY_PROPAGATOR, ts, pr[idx], mode=0, n_threads=4)
+    assert np.array_equal(st["n_accept"][idx], ost["n_accept"])
+    assert np.max(np.abs(got[idx] - want) / np.maximum(np.abs(want), 1e-3)) <= 1e-8

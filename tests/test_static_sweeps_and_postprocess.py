@@ -45,6 +45,21 @@ def test_subspace_helpers():
     assert np.allclose(populations(np.array([3 + 4j])), [25.0])
 
 
+def test_superoperator_and_kraus_mix():
+    from qsim_b200 import kraus_mix, superoperator
+    rng = np.random.default_rng(20261019)
+    us = np.linalg.qr(rng.normal(size=(5, 3, 3)) + 1j * rng.normal(size=(5, 3, 3)))[0]
+    rho = rng.normal(size=(3, 3)) + 1j * rng.normal(size=(3, 3))
+    s = superoperator(us[0])
+    assert np.allclose((s @ rho.reshape(-1, order="F")).reshape(3, 3, order="F"), us[0] @ rho @ us[0].conj().T)
+    w = np.array([0.1, 0.2, 0.3, 0.25, 0.15])
+    mixed = (kraus_mix(us, w) @ rho.reshape(-1, order="F")).reshape(3, 3, order="F")
+    assert np.allclose(mixed, sum(wi * u @ rho @ u.conj().T for wi, u in zip(w, us)))
+    # trace preservation of the mixture: vec(I)' S = vec(I)'
+    eye = np.eye(3).reshape(-1, order="F")
+    assert np.allclose(eye @ kraus_mix(us, w), eye)
+
+
 @pytest.mark.gpu
 def test_static_sweep_gpu_parity_and_fidelity():
     cqs = _system()
