@@ -62,6 +62,39 @@ class DuffingSpec:
                            perturbative_transmon_anharm(t.EC, t.EJ1, t.EJ2, phi, num_terms))
 
 
+def fit_transmon(freq_max: float, freq_min: float, anharm_max: float,
+                 num_terms: int = PERTURBATIVE_NUM_TERMS) -> TransmonSpec:
+    """TransmonSpec whose perturbative model has 0-1 frequency `freq_max` and anharmonicity `anharm_max` at
+    phi = 0 and 0-1 frequency `freq_min` at phi = 1/2; `freq_max == freq_min` enforces EJ2 = 0
+    (systems.jl:288-323, PerturbativeTransmon model).  The reference minimises the L1 misfit with Optim's
+    Nelder-Mead from the guesses below; the same conditions are solved here as equations (scipy least_squares
+    from the same starting point), which meets the reference's test tolerances (test_systems.jl:49-92)."""
+    from scipy.optimize import least_squares
+
+    EC0 = -anharm_max
+    EJ_max0 = -(freq_max - anharm_max) ** 2 / (8 * anharm_max)
+    EJ_min0 = -(freq_min - anharm_max) ** 2 / (8 * anharm_max)
+    tol = dict(xtol=1e-15, ftol=1e-15, gtol=1e-15)
+    if freq_max == freq_min:
+        def res(p):
+            return [perturbative_transmon_freq(p[0], p[1], 0.0, 0.0, num_terms) - freq_max,
+                    perturbative_transmon_anharm(p[0], p[1], 0.0, 0.0, num_terms) - anharm_max]
+        sol = least_squares(res, [EC0, 0.5 * (EJ_max0 + EJ_min0)], **tol)
+        return TransmonSpec(float(sol.x[0]), float(sol.x[1]), 0.0)
+
+    def res(p):
+        return [perturbative_transmon_freq(p[0], p[1], p[2], 0.0, num_terms) - freq_max,
+                perturbative_transmon_anharm(p[0], p[1], p[2], 0.0, num_terms) - anharm_max,
+                perturbative_transmon_freq(p[0], p[1], p[2], 0.5, num_terms) - freq_min]
+    sol = least_squares(res, [EC0, 0.5 * (EJ_max0 + EJ_min0), 0.5 * abs(EJ_max0 - EJ_min0)], **tol)
+    return TransmonSpec(*(float(x) for x in sol.x))
+
+
+def transmon_spec_from_duffing(d: DuffingSpec, num_terms: int = PERTURBATIVE_NUM_TERMS) -> TransmonSpec:
+    """TransmonSpec(::DuffingSpec) (systems.jl:70-73): a fixed-frequency transmon fitted to (frequency, anharmonicity)."""
+    return fit_transmon(d.frequency, d.frequency, d.anharmonicity, num_terms)
+
+
 # ---- systems -------------------------------------------------------------
 class QSystem:
     label: str

@@ -148,3 +148,23 @@ def test_opaque_closure_rejected_by_lowering():
         lower(cqs)
     with pytest.raises(TypeError):
         dipole_drive(q, lambda t: 0.02 * math.cos(t))
+
+
+def test_fit_transmon_and_spec_conversions():
+    """test_systems.jl:15-22 (first part), :49-92 (PerturbativeTransmon model), :94-103."""
+    from qsim_b200 import duffing_hamiltonian, fit_transmon, hamiltonian, transmon_spec_from_duffing
+    # tunable: frequency and anharmonicity at phi = 0, frequency at phi = 1/2
+    t = fit_transmon(4.0, 3.0, -0.2)
+    h = hamiltonian(PerturbativeTransmon("q", 3, t), 0.0)
+    assert np.allclose(h, np.diag([0.0, 4.0, 2 * 4.0 - 0.2]), rtol=1e-8, atol=1e-10)
+    t = fit_transmon(5.0, 4.0, -0.2)
+    assert t.EJ2 != 0.0
+    assert np.allclose(hamiltonian(PerturbativeTransmon("q", 3, t), 0.0), duffing_hamiltonian(5.0, -0.2, 3), rtol=1e-7, atol=1e-10)
+    assert np.allclose(hamiltonian(PerturbativeTransmon("q", 2, t), 0.5), duffing_hamiltonian(4.0, 0.0, 2), rtol=1e-8, atol=1e-10)
+    # fixed frequency: EJ2 == 0
+    t = fit_transmon(5.0, 5.0, -0.2)
+    assert t.EJ2 == 0.0
+    assert np.allclose(hamiltonian(PerturbativeTransmon("q", 3, t), 0.0), duffing_hamiltonian(5.0, -0.2, 3), rtol=1e-7, atol=1e-10)
+    # DuffingSpec <-> TransmonSpec round trip
+    d1 = DuffingSpec.from_transmon(transmon_spec_from_duffing(DuffingSpec(4.0, -0.2)))
+    assert d1.frequency == pytest.approx(4.0, rel=1e-8) and d1.anharmonicity == pytest.approx(-0.2, rel=1e-8)
