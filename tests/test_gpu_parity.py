@@ -401,3 +401,37 @@ def test_large_sweep_work_queue():
     want, ost = co.OracleProblem(cqs).solve(co.UNITARY_PROPAGATOR, ts, pr[idx], mode=0, n_threads=4)
     assert np.array_equal(st["n_accept"][idx], ost["n_accept"])
     assert np.max(np.abs(got[idx] - want) / np.maximum(np.abs(want), 1e-3)) <= 1e-8
+
+
+@pytest.mark.gpu
+def test_cfg3_cfg4_cfg5_sweep_properties():
+    """Size-independent properties on sweeps too large for the oracle: unitarity and U(t0) = I for the 3-transmon
+    propagators (cfg3, 1184 points), trace preservation vec(I)' S = vec(I)' and S(t0) = I for the Lindblad
+    superoperators (cfg4: d^2 = 81, 592 points; cfg5: d^2 = 729, 8 points), every trajectory successful, and
+    independence of how the sweep is partitioned into launches (bitwise)."""
+    def subset(name, n):
+        cqs, params, _, fn = W.config(name)
+        return cqs, np.ascontiguousarray(params[np.linspace(0, len(params) - 1, n).astype(int)]), fn
+    # cfg3
+    cqs, pr, fn = subset("cfg3", 1184)
+    P = Problem(cqs)
+    ts = np.array([0.0, 5.0, 10.0])
+    u, st = P.solve(fn, ts, params=pr)
+    assert np.all(st["retcode"] == 0) and np.all(st["t_final"] == 10.0)
+    assert np.array_equal(u[:, 0], np.broadcast_to(np.eye(27), (len(pr), 27, 27)))
+    assert np.abs(np.einsum("tji,tjk->tik", u[:, -1].conj(), u[:, -1]) - np.eye(27)).max() < 2e-3
+    part, _ = P.solve(fn, ts, params=pr[500:900])
+    assert np.array_equal(part, u[500:900])
+    # cfg4 / cfg5: trace preservation of the superoperator
+    for name, n, tf in (("cfg4", 592, 1.0), ("cfg5", 8, 0.1)):
+        cqs, pr, fn = subset(name, n)
+        d = cqs.dimension
+        P = Problem(cqs)
+        ts = np.array([0.0, tf])
+        s, st = P.solve(fn, ts, params=pr)
+        assert np.all(st["retcode"] == 0)
+        assert np.array_equal(s[:, 0], np.broadcast_to(np.eye(d * d), (len(pr), d * d, d * d)))
+        vec_eye = np.eye(d).reshape(-1, order="F")
+        assert np.abs(np.einsum("i,tij->tj", vec_eye, s[:, -1]) - vec_eye).max() < 1e-6
+        part, _ = P.solve(fn, ts, params=pr[n // 4: n // 2])
+        assert np.array_equal(part, s[n // 4: n // 2])
