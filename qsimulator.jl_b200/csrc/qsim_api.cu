@@ -550,6 +550,14 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     } else {
         return fail(QSIM_ERR_UNSUPPORTED, "state vectors longer than 864 entries have no kernel yet");
     }
+    if (!pl.rowsplit && g.max_nnz > 16) {
+        // rows longer than the register-resident capacities (dense Hamiltonians of 17..96 levels): the row-split
+        // kernels read their rows from global memory and take any row length
+        rpl = 3;
+        cpl = 1;
+        pl.groups = 1;
+        pl.rowsplit = 1;
+    }
     int cpb = pl.groups * cpl;
     pl.n_batches = (pl.ncols + cpb - 1) / cpb;
     // Blocked variant (value mode 3) for small propagators whose couplings fall into 3 x 3 blocks (Kronecker
@@ -649,6 +657,12 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     pl.team_bytes = (((g.imag_only ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
                     (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride + 128 * pl.team_warps;
     pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
+    // large value tables (dense Hamiltonians): fewer teams per CTA until the CTA fits
+    while (pl.smem > 220 * 1024 && pl.teams_per_cta > 1) {
+        pl.teams_per_cta /= 2;
+        pl.block = pl.team_warps * 32 * pl.teams_per_cta;
+        pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
+    }
     pl.scratch_per_team = pl.streamed ? (size_t)4 * pl.n_batches * cpb * n * sizeof(double2) : 0;
     if (pl.smem > 220 * 1024) return fail(QSIM_ERR_UNSUPPORTED, "problem needs more shared memory than one SM has");
     return QSIM_OK;
