@@ -435,3 +435,24 @@ def test_cfg3_cfg4_cfg5_sweep_properties():
         assert np.abs(np.einsum("i,tij->tj", vec_eye, s[:, -1]) - vec_eye).max() < 1e-6
         part, _ = P.solve(fn, ts, params=pr[n // 4: n // 2])
         assert np.array_equal(part, s[n // 4: n // 2])
+
+
+@pytest.mark.gpu
+def test_failed_trajectory_is_isolated():
+    """A sweep point whose parameters are not finite fails on its own (retcode, NaN results) and leaves every
+    other trajectory of the launch untouched -- the same outcome the oracle reports."""
+    cqs, params, _, fn = W.config("cfg2")
+    pr = np.ascontiguousarray(params[np.linspace(0, len(params) - 1, 64).astype(int)])
+    ts = np.array([0.0, 1.0, 2.0])
+    P = Problem(cqs)
+    good, st_good = P.solve(fn, ts, params=pr)
+    bad = pr.copy()
+    bad[5, 0] = np.nan
+    bad[40, 1] = np.inf
+    got, st = P.solve(fn, ts, params=bad)
+    want, ost = co.OracleProblem(cqs).solve(co.UNITARY_PROPAGATOR, ts, bad, n_threads=8)
+    ok = np.ones(64, dtype=bool)
+    ok[[5, 40]] = False
+    assert np.array_equal(got[ok], good[ok]) and np.array_equal(st[ok], st_good[ok])
+    assert np.all(st["retcode"][~ok] != 0) and np.array_equal(st["retcode"], ost["retcode"])
+    assert np.isnan(got[~ok][:, -1]).all()
