@@ -456,3 +456,20 @@ def test_failed_trajectory_is_isolated():
     assert np.array_equal(got[ok], good[ok]) and np.array_equal(st[ok], st_good[ok])
     assert np.all(st["retcode"][~ok] != 0) and np.array_equal(st["retcode"], ost["retcode"])
     assert np.isnan(got[~ok][:, -1]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [
+    dict(reltol=1e-9, abstol=1e-11),
+    dict(reltol=1e-4, abstol=1e-6),
+    dict(beta1=0.2, beta2=0.05, gamma=0.8),
+    dict(qmin=0.5, qmax=3.0),
+    dict(dtmax=0.004),
+    dict(qoldinit=1e-2),
+])
+def test_solver_options_follow_the_oracle(kw):
+    """Non-default tolerances and controller constants (the per-call power tables of the kernel are rebuilt from
+    beta1, beta2): same accepted / rejected steps as the oracle and 1e-8 agreement."""
+    cqs, params, _, fn = W.config("cfg2")
+    pr = np.ascontiguousarray(params[[3, 2000, 4090]])
+    check_parity(cqs, fn, np.linspace(0.0, 3.0, 4), pr, opts=_abi.default_opts(**kw))
