@@ -67,8 +67,15 @@ struct LaunchArgs {
     double2 *scratch;     // streamed mode: [n_teams_total][4][n_batches*cpb*n]
     const uint16_t *blk_slot;    // blocked variants: [n_blk_rows][(max_nnz-1)*RPL*RPL] slot ids of the block values
     int n_blk_rows;              // blocked variants: block rows (= lanes per column)
-    const uint32_t *ell_packed;  // row-split mode: [max_nnz][ell_rows] translated (source offset | slot offset << 16)
-    int ell_rows;                // n + 8: eight zero-slot padding rows for lanes past the last row
+    // Row-split mode.  Rows are sorted by descending length and dealt out in chunks of 32: chunk c = slot * team_warps
+    // + warp holds sorted rows [32c, 32c + 32), so every (warp, slot) group is homogeneous in length and the
+    // warps of a team carry equal work.  ell_packed[j][q]: entry j of sorted row q, translated (source offset |
+    // slot offset << 16), diagonal first, no interior padding; ell_rows = n + 8 (eight zero-slot padding rows
+    // for lanes past the last row); rs_perm[q] = state row of sorted row q; rs_len[c] = entries per row of chunk c.
+    const uint32_t *ell_packed;
+    int ell_rows;
+    const int *rs_perm;
+    const int *rs_len;
     int team_warps, teams_per_cta, n_batches, groups, streamed;
     int y_row_stride, y_grp_stride;  // stage-buffer layout in 16-byte units (chosen on the host to avoid bank conflicts)
     int nvp, ncp;         // padded slot / channel counts (nvp > n_slots: slot n_slots is the zero slot)
@@ -664,10 +671,10 @@ struct Kern {
             if (RS) {
                 // rows come from global memory (translated on the host); rows past n read row n-1's
                 // entries with the zero slot substituted by the host-side table's padding row
-                const uint32_t *er = a.ell_packed + row_of[i];
-                const int nnz = a.g.max_nnz, stride = a.ell_rows;
+                const uint32_t *er = a.ell_packed + (ell[i][0] & 0xFFFFu);
+                const int nnz = (int)(ell[i][0] >> 16), stride = a.ell_rows;  // this (warp, slot) group's row length
                 if (i == RPL - 1) hook();
-                mac(Vs, yb, __ldg(er), true, &yreg[i * CPL], acc);
+                if (nnz > 0) mac(Vs, yb, __ldg(er), true, &yreg[i * CPL], acc);
 #pragma unroll 4
                 for (int j = 1; j < nnz; j++) mac(Vs, yb, __ldg(er + (size_t)j * stride), false, &yreg[i * CPL], acc);
             } else {
@@ -1355,10 +1362,20 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     uint32_t ell[RPL][MAXNNZ];
 #pragma unroll
     for (int i = 0; i < RPL; i++) {
-        row_of[i] = K::BLK ? g.blk_row * RPL + i : row0 + 32 * i + (RS ? g.warp_in_team * 32 * RPL : 0);
+        if (RS) {
+            // sorted row q of chunk (slot i, this warp); the stage buffer and the packed table are indexed by q,
+            // initial state / results / scratch by the state row rs_perm[q]
+            const int chunk = i * a.team_warps + g.warp_in_team;
+            const int q = chunk * 32 + g.lane;
+            row_ok[i] = q < n;
+            row_of[i] = row_ok[i] ? __ldg(a.rs_perm + q) : 0;
+            my_off[i] = 16u * ((q < n ? q : n - 1) * a.y_row_stride);
+            ell[i][0] = (uint32_t)(row_ok[i] ? q : n + (q - n) % 8) | ((uint32_t)__ldg(a.rs_len + chunk) << 16);
+            continue;
+        }
+        row_of[i] = K::BLK ? g.blk_row * RPL + i : row0 + 32 * i;
         row_ok[i] = lane_active && row_of[i] < n;
         const int row_eff = row_of[i] < n ? row_of[i] : n - 1;
-        if (RS) row_of[i] = row_ok[i] ? row_of[i] : n + (row_of[i] - n) % 8;  // padding rows of the packed table
         my_off[i] = 16u * (row_eff * a.y_row_stride);
 #pragma unroll
         for (int j = 0; j < MAXNNZ; j++) {
