@@ -81,7 +81,8 @@ struct qsim_problem::DeviceCopy {
     int fast_ok = 0, fast_chA = 0, fast_chB = 0;  // records are in (constant, channel A, channel B) order
     uint32_t *ell_packed = nullptr;  // row-split kernels: sorted, translated rows; row permutation; chunk lengths
     int *rs_perm = nullptr, *rs_len = nullptr;
-    int packed_stride = -1, packed_warps = -1;
+    int packed_stride = -1, packed_warps = -1, packed_vm = -1;
+    uint8_t *slot_imag = nullptr;    // value mode 4
     uint32_t *blk_ell = nullptr;     // blocked kernels: row table and value slot ids (built by make_plan)
     uint16_t *blk_slot = nullptr;
     ~DeviceCopy() { free_all(); }  // the owning device must be current
@@ -89,6 +90,8 @@ struct qsim_problem::DeviceCopy {
         cudaFree(ell_packed);
         cudaFree(rs_perm);
         cudaFree(rs_len);
+        cudaFree(slot_imag);
+        slot_imag = nullptr;
         ell_packed = nullptr;
         rs_perm = nullptr;
         rs_len = nullptr;
@@ -391,6 +394,8 @@ struct Plan {
     int y_row_stride = 1, y_grp_stride = 1, rowsplit = 0;
     int off_dptr = 0, off_dw = 0, off_drec = 0, dyn_fast = 0;
     size_t smem = 0, scratch_per_team = 0;
+    int vm = 0;                        // value mode of the chosen variant
+    std::vector<uint8_t> slot_imag;    // value mode 4: per slot, 1 = purely imaginary, 0 = purely real
     // blocked variant (value mode 3): block rows, row table [1 + max blocks][n] and value slot ids
     int blk_rows = 0, blk_nnz = 0;
     std::vector<uint32_t> blk_ell;
@@ -619,6 +624,29 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         // (with four entries per lane the extra value registers would spill: stay in mode 1)
         if (static_off && rpl * cpl <= 3 && find_variant(rpl, cpl, g.max_nnz, pl.block, 2, 0)) vm = 2;
     }
+    if (vm == 0) {
+        // value mode 4: every off-diagonal entry purely real or purely imaginary for all times and parameters
+        // (all channel weights of its slot real, or all imaginary); the diagonal may be complex
+        bool mixed = g.n_slots <= 2045;  // 8-byte offsets into both halves of the split table fit 15 bits
+        pl.slot_imag.assign((size_t)g.n_slots, 0);
+        std::vector<uint8_t> off_diag((size_t)g.n_slots, 0);
+        for (int j = 1; j < g.max_nnz; j++)
+            for (int r = 0; r < n; r++) {
+                const uint32_t sl = g.ell[(size_t)j * n + r] >> 16;
+                if (sl != 0xFFFFu) off_diag[sl] = 1;
+            }
+        for (int sl = 0; sl < g.n_slots && mixed; sl++) {
+            bool any_re = false, any_im = false;
+            for (int q = g.slot_ptr[sl]; q < g.slot_ptr[sl + 1]; q++) {
+                any_re = any_re || g.pair_w[(size_t)q].real() != 0.0;
+                any_im = any_im || g.pair_w[(size_t)q].imag() != 0.0;
+            }
+            if (off_diag[(size_t)sl] && any_re && any_im) mixed = false;
+            pl.slot_imag[(size_t)sl] = any_im ? 1 : 0;
+        }
+        if (mixed && find_variant(rpl, cpl, g.max_nnz, pl.block, 4, pl.rowsplit)) vm = 4;
+    }
+    pl.vm = vm;
     pl.kv = find_variant(rpl, cpl, blocked ? pl.blk_nnz : g.max_nnz, pl.block, vm, pl.rowsplit);
     if (!pl.kv)
         return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
@@ -659,7 +687,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     for (int sl = 0; sl < g.n_dyn_slots; sl++)
         if (g.slot_ptr[sl + 1] - g.slot_ptr[sl] > 3) pl.dyn_fast = 0;
     pl.common_bytes = pl.off_drec + (pl.dyn_fast ? 64 * std::max(g.n_dyn_slots, 1) : 16);
-    pl.team_bytes = (((g.imag_only ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
+    pl.team_bytes = ((((pl.vm >= 1 && pl.vm <= 3) ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
                     (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride + 128 * pl.team_warps;
     pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
     // large value tables (dense Hamiltonians): fewer teams per CTA until the CTA fits
@@ -683,12 +711,13 @@ extern "C" int qsim_problem_kernel_name(qsim_problem *p, int which, char *buf, i
 
 extern "C" int qsim_problem_flops_per_rhs(qsim_problem *p, int which, double *flops) {
     if (!p || !flops || which < 0 || which > 3) return fail(QSIM_ERR_ARG, "bad argument");
-    const int w = which >= 2 ? 1 : 0;
-    if (int rc = ensure_generator(p, w)) return rc;
-    const Generator &g = p->gen[w];
+    Plan pl;
+    if (int rc = make_plan(p, which, pl)) return rc;
+    const Generator &g = p->gen[pl.w];
     const double ncols = (which == 0 || which == 2) ? (double)g.n : 1.0;
-    // a complex multiply-add is 4 DFMA (8 flop); a purely imaginary generator needs 2 (4 flop)
-    *flops = (g.imag_only ? 4.0 : 8.0) * (double)g.nnz * ncols;
+    // a complex multiply-add is 4 DFMA (8 flop); value modes 1-4 (entries purely imaginary, or each purely
+    // real or purely imaginary) issue 2 (4 flop)
+    *flops = (pl.vm >= 1 ? 4.0 : 8.0) * (double)g.nnz * ncols;
     return QSIM_OK;
 }
 
@@ -808,7 +837,8 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     if (int rc = ensure_device_copy(c, p, pl.w, &dc)) return rc;
     const Generator &g = p->gen[pl.w];
     std::unique_lock<std::mutex> packed_lock(p->dev_mutex);
-    if (pl.rowsplit && (!dc->ell_packed || dc->packed_stride != pl.y_row_stride || dc->packed_warps != pl.team_warps)) {
+    if (pl.rowsplit && (!dc->ell_packed || dc->packed_stride != pl.y_row_stride || dc->packed_warps != pl.team_warps ||
+                        dc->packed_vm != pl.vm)) {
         // Row tables of the row-split kernels.  Rows are sorted by descending length and dealt out in chunks of 32
         // (chunk c = slot * team_warps + warp), so each (warp, slot) group runs exactly as many entries as its
         // longest row and the warps of a team carry equal work; without this every row would be padded to the
@@ -816,7 +846,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         // Entries are translated to byte offsets into the stage buffer (indexed by sorted position) and the
         // value table; eight zero-slot padding rows serve the lanes past the last row.
         const int n = g.n, rows = n + 8;
-        const uint32_t vb = g.imag_only ? 8u : 16u;
+        const uint32_t vb = pl.vm >= 1 ? 8u : 16u;
         std::vector<std::vector<uint32_t>> compact((size_t)n);
         for (int r = 0; r < n; r++) {
             compact[(size_t)r].push_back(g.ell[(size_t)r]);  // the diagonal entry (own row; slot 0xFFFF if absent)
@@ -840,7 +870,11 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
             for (size_t j = 0; j < row.size(); j++) {
                 const uint32_t src = (uint32_t)inv[(size_t)(row[j] & 0xFFFFu)];
                 const uint32_t sl = (row[j] >> 16) == 0xFFFFu ? (uint32_t)g.n_slots : (row[j] >> 16);
-                packed[j * rows + (size_t)q] = (16u * src * (uint32_t)pl.y_row_stride) | ((vb * sl) << 16);
+                uint32_t e = (16u * src * (uint32_t)pl.y_row_stride) | ((vb * sl) << 16);
+                // value mode 4: an imaginary off-diagonal entry reads the second half of the split value table
+                if (pl.vm == 4 && j > 0 && sl < (uint32_t)g.n_slots && pl.slot_imag[sl])
+                    e = (e + ((8u * (uint32_t)pl.nvp) << 16)) | 0x80000000u;
+                packed[j * rows + (size_t)q] = e;
             }
         }
         cudaFree(dc->ell_packed);
@@ -854,7 +888,9 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         CU(upload(&dc->rs_len, lens));
         dc->packed_stride = pl.y_row_stride;
         dc->packed_warps = pl.team_warps;
+        dc->packed_vm = pl.vm;
     }
+    if (pl.vm == 4 && !dc->slot_imag) CU(upload(&dc->slot_imag, pl.slot_imag));
     if (pl.blk_rows > 0 && !dc->blk_ell) {
         CU(upload(&dc->blk_ell, pl.blk_ell));
         CU(upload(&dc->blk_slot, pl.blk_slot));
@@ -960,6 +996,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.ell_rows = g.n + 8;
     a.rs_perm = dc->rs_perm;
     a.rs_len = dc->rs_len;
+    a.slot_imag = dc->slot_imag;
     a.ncols = pl.ncols;
     a.identity_init = pl.identity;
     a.n_params = p->n_params;

@@ -9,9 +9,9 @@ const KernelVariant *variants_rowsplit(int *count) {
 }
 #else
 const KernelVariant *variants_rowsplit(int *count) {
-    static const KernelVariant v[] = {QSIM_VARIANT_RS(256, 0), QSIM_VARIANT_RS(256, 1), QSIM_VARIANT_RS(288, 0),
-                                      QSIM_VARIANT_RS(288, 1)};
-    *count = 4;
+    static const KernelVariant v[] = {QSIM_VARIANT_RS(256, 0), QSIM_VARIANT_RS(256, 1), QSIM_VARIANT_RS(256, 4),
+                                      QSIM_VARIANT_RS(288, 0), QSIM_VARIANT_RS(288, 1), QSIM_VARIANT_RS(288, 4)};
+    *count = 6;
     return v;
 }
 #endif

@@ -5,7 +5,8 @@
 namespace qsim {
 
 struct KernelVariant {
-    int rpl, cpl, maxnnz, maxt, minb, vm, rs;  // vm: value mode (0 complex, 1 imaginary, 2 imaginary + static off-diagonals)
+    int rpl, cpl, maxnnz, maxt, minb, vm, rs;  // vm: value mode (0 complex, 1 imaginary, 2 imaginary + static off-diagonals,
+                                               // 3 blocked, 4 mixed real/imaginary entries)
     const char *name;
     launch_fn launch;
     cudaError_t (*occupancy)(int block, size_t smem, int *ctas_per_sm);
@@ -52,8 +53,9 @@ QSIM_DECLARE(variants_blocked)
         static const KernelVariant v[] = {                                                                \
             QSIM_VARIANT(R, C, 5, T, B, 0),  QSIM_VARIANT(R, C, 5, T, B, 1),  QSIM_VARIANT(R, C, 5, T, B, 2),   \
             QSIM_VARIANT(R, C, 9, T, B, 0),  QSIM_VARIANT(R, C, 9, T, B, 1),  QSIM_VARIANT(R, C, 9, T, B, 2),   \
-            QSIM_VARIANT(R, C, 12, T, B, 0), QSIM_VARIANT(R, C, 12, T, B, 1),                             \
-            QSIM_VARIANT(R, C, 16, T, B, 0), QSIM_VARIANT(R, C, 16, T, B, 1)};                            \
+            QSIM_VARIANT(R, C, 9, T, B, 4),                                                               \
+            QSIM_VARIANT(R, C, 12, T, B, 0), QSIM_VARIANT(R, C, 12, T, B, 1), QSIM_VARIANT(R, C, 12, T, B, 4), \
+            QSIM_VARIANT(R, C, 16, T, B, 0), QSIM_VARIANT(R, C, 16, T, B, 1), QSIM_VARIANT(R, C, 16, T, B, 4)}; \
         *count = (int)(sizeof(v) / sizeof(v[0]));                                                         \
         return v;                                                                                         \
     }

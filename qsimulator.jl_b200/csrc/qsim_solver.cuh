@@ -76,6 +76,7 @@ struct LaunchArgs {
     int ell_rows;
     const int *rs_perm;
     const int *rs_len;
+    const uint8_t *slot_imag;    // value mode 4: per slot, 1 when the slot is purely imaginary (0: purely real)
     int team_warps, teams_per_cta, n_batches, groups, streamed;
     int y_row_stride, y_grp_stride;  // stage-buffer layout in 16-byte units (chosen on the host to avoid bank conflicts)
     int nvp, ncp;         // padded slot / channel counts (nvp > n_slots: slot n_slots is the zero slot)
@@ -301,8 +302,16 @@ struct Geo {
 // the whole trajectory and only the diagonal is read from the per-stage table.
 template <int RPL, int CPL, int MAXNNZ, int VM, bool RS>
 struct Kern {
-    static constexpr bool IM = VM >= 1;
+    static constexpr bool IM = VM >= 1 && VM <= 3;
     static constexpr bool SV = VM == 2;
+    // VM == 4, "mixed": a complex generator whose every OFF-DIAGONAL entry is purely real or purely imaginary
+    // (Lindblad generators of real Hamiltonians and real collapse operators: couplings come from the commutator and
+    // are imaginary, the sandwich terms L rho L' are real; only the diagonal mixes both).  A value table is stored
+    // split -- real parts of all slots, then imaginary parts -- so an off-diagonal entry loads the one 8-byte part
+    // it has (its byte offset points into the right half, bit 31 of the entry says which half) and costs 2 DFMA
+    // instead of 4; the diagonal entry loads both halves.
+    static constexpr bool MX = VM == 4;
+    static constexpr uint32_t VSTRIDE = (VM >= 1 && VM <= 3) ? 8u : 16u;  // table bytes per slot
     // VM == 3, "blocked": a lane owns RPL consecutive rows of one column and the off-diagonal part of the
     // generator is stored as dense RPL x RPL blocks (static, purely imaginary, values in registers).  Entry
     // 1 + b of row-slot k names row k of neighbour block b, so the RPL row-slots together load each
@@ -312,7 +321,7 @@ struct Kern {
     static constexpr int NVS = BLK ? (MAXNNZ - 1) * RPL * RPL : RPL * MAXNNZ;  // static values held per lane
     static_assert(!BLK || CPL == 1, "blocked variants hold one column per lane");
     static constexpr int E = RPL * CPL;
-    static constexpr uint32_t VB = IM ? 8u : 16u;  // bytes per value slot (IM: imaginary part only)
+    static constexpr uint32_t VB = (IM || MX) ? 8u : 16u;  // bytes per value slot (IM / MX: one real number)
     typedef double2 Vec[E];
 
     // Refresh tables table0 + s, s < NTAB, for the times tbase + kStageC[s]*dtv.  all == false: only
@@ -486,7 +495,13 @@ struct Kern {
                     sts1(g.sm_V + s * g.v_stride + 8 * sl, vy);
                 } else {
                     const double vx = fma(w2.x, fB, fma(w1.x, fA, w0.x));
-                    sts2(g.sm_V + s * g.v_stride + 16 * sl, make_double2(vx, vy));
+                    if (MX)
+                        {
+                        sts1(g.sm_V + s * g.v_stride + 8 * sl, vx);
+                        sts1(g.sm_V + s * g.v_stride + 8 * (a.nvp + sl), vy);
+                    }
+                    else
+                        sts2(g.sm_V + s * g.v_stride + 16 * sl, make_double2(vx, vy));
                 }
             }
         }
@@ -541,7 +556,11 @@ struct Kern {
                         sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * sl, vy);
                     } else {
                         const double vx = fma(w2.x, c2, fma(w1.x, c1, w0.x * c0));
-                        sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
+                        if (MX) {
+                            sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * sl, vx);
+                            sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * (a.nvp + sl), vy);
+                        } else
+                            sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
                     }
                 }
             } else
@@ -558,7 +577,10 @@ struct Kern {
                 }
                 if (IM)
                     sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * sl, vy);
-                else
+                else if (MX) {
+                    sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * sl, vx);
+                    sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * (a.nvp + sl), vy);
+                } else
                     sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
             }
         } else {
@@ -575,7 +597,10 @@ struct Kern {
                 }
                 if (IM)
                     sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * sl, vy);
-                else
+                else if (MX) {
+                    sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * sl, vx);
+                    sts1(g.sm_V + (table0 + s) * g.v_stride + 8 * (a.nvp + sl), vy);
+                } else
                     sts2(g.sm_V + (table0 + s) * g.v_stride + 16 * sl, make_double2(vx, vy));
             }
         }
@@ -598,28 +623,58 @@ struct Kern {
 
     // k = A(t_s) * y : sparse row gather, value table Vs, stage vector yb (both shared-memory addresses).
     // Entry 0 of every row is its diagonal: that operand is the lane's own stage value `yreg`.
-    static __device__ __forceinline__ void mac(uint32_t Vs, uint32_t yb, uint32_t e, bool diag, const double2 *yreg,
-                                               double2 (&acc)[CPL]) {
-        const uint32_t ya = yb + (e & 0xFFFFu);
+    // value of a row entry (byte offset of its slot in bits 16..; MX: bit 31 is the "imaginary" flag)
+    static __device__ __forceinline__ double2 ldv(uint32_t Vs, uint32_t e) {
+        if (MX) return make_double2(0.0, lds1(Vs + ((e >> 16) & 0x7FFFu)));
+        if (IM) return make_double2(0.0, lds1(Vs + (e >> 16)));
+        return lds2(Vs + (e >> 16));
+    }
+    // the diagonal entry: complex in mixed mode (both halves of the split table)
+    static __device__ __forceinline__ double2 ldv_diag(const LaunchArgs &a, uint32_t Vs, uint32_t e) {
+        if (MX) return make_double2(lds1(Vs + (e >> 16)), lds1(Vs + (e >> 16) + 8u * a.nvp));
+        return ldv(Vs, e);
+    }
+    static __device__ __forceinline__ void cfma_diag(double2 &acc, double2 v, double2 y) {
         if (IM) {
-            // A = i B with B real: (iB)(yr + i yi) = -B yi + i B yr
-            const double v = lds1(Vs + (e >> 16));
-#pragma unroll
-            for (int c = 0; c < CPL; c++) {
-                const double2 y = diag ? yreg[c] : lds2(ya + 16 * c);
-                acc[c].x = fma(-v, y.y, acc[c].x);
-                acc[c].y = fma(v, y.x, acc[c].y);
-            }
+            acc.x = fma(-v.y, y.y, acc.x);
+            acc.y = fma(v.y, y.x, acc.y);
         } else {
-            const double2 v = lds2(Vs + (e >> 16));
+            acc.x = fma(v.x, y.x, acc.x);
+            acc.y = fma(v.x, y.y, acc.y);
+            acc.x = fma(-v.y, y.y, acc.x);
+            acc.y = fma(v.y, y.x, acc.y);
+        }
+    }
+    // acc += v * y for one row entry
+    static __device__ __forceinline__ void cfma(double2 &acc, double2 v, uint32_t e, double2 y) {
+        if (MX) {
+            const bool im = (e >> 31) != 0;
+            const double a0 = im ? -y.y : y.x, a1 = im ? y.x : y.y;
+            acc.x = fma(v.y, a0, acc.x);
+            acc.y = fma(v.y, a1, acc.y);
+        } else if (IM) {
+            // A = i B with B real: (iB)(yr + i yi) = -B yi + i B yr
+            acc.x = fma(-v.y, y.y, acc.x);
+            acc.y = fma(v.y, y.x, acc.y);
+        } else {
+            acc.x = fma(v.x, y.x, acc.x);
+            acc.y = fma(v.x, y.y, acc.y);
+            acc.x = fma(-v.y, y.y, acc.x);
+            acc.y = fma(v.y, y.x, acc.y);
+        }
+    }
+
+    static __device__ __forceinline__ void mac(const LaunchArgs &a, uint32_t Vs, uint32_t yb, uint32_t e, bool diag,
+                                               const double2 *yreg, double2 (&acc)[CPL]) {
+        const uint32_t ya = yb + (e & 0xFFFFu);
+        if (diag) {
+            const double2 v = ldv_diag(a, Vs, e);
 #pragma unroll
-            for (int c = 0; c < CPL; c++) {
-                const double2 y = diag ? yreg[c] : lds2(ya + 16 * c);
-                acc[c].x = fma(v.x, y.x, acc[c].x);
-                acc[c].y = fma(v.x, y.y, acc[c].y);
-                acc[c].x = fma(-v.y, y.y, acc[c].x);
-                acc[c].y = fma(v.y, y.x, acc[c].y);
-            }
+            for (int c = 0; c < CPL; c++) cfma_diag(acc[c], v, yreg[c]);
+        } else {
+            const double2 v = ldv(Vs, e);
+#pragma unroll
+            for (int c = 0; c < CPL; c++) cfma(acc[c], v, e, lds2(ya + 16 * c));
         }
     }
 
@@ -674,9 +729,9 @@ struct Kern {
                 const uint32_t *er = a.ell_packed + (ell[i][0] & 0xFFFFu);
                 const int nnz = (int)(ell[i][0] >> 16), stride = a.ell_rows;  // this (warp, slot) group's row length
                 if (i == RPL - 1) hook();
-                if (nnz > 0) mac(Vs, yb, __ldg(er), true, &yreg[i * CPL], acc);
+                if (nnz > 0) mac(a, Vs, yb, __ldg(er), true, &yreg[i * CPL], acc);
 #pragma unroll 4
-                for (int j = 1; j < nnz; j++) mac(Vs, yb, __ldg(er + (size_t)j * stride), false, &yreg[i * CPL], acc);
+                for (int j = 1; j < nnz; j++) mac(a, Vs, yb, __ldg(er + (size_t)j * stride), false, &yreg[i * CPL], acc);
             } else {
                 // no per-entry branch (short rows are padded with the zero slot).  Operands are requested in
                 // chunks of up to four off-diagonal entries, all loads of a chunk ahead of its multiply-adds, so a
@@ -684,26 +739,10 @@ struct Kern {
                 {
                     // diagonal entry: operand from the lane's own registers
                     const uint32_t e = ell[i][0];
-                    double2 vd;
-                    if (IM)
-                        vd = make_double2(0.0, lds1(Vs + (e >> 16)));
-                    else
-                        vd = lds2(Vs + (e >> 16));
+                    const double2 vd = ldv_diag(a, Vs, e);
                     if (i == RPL - 1 && MAXNNZ <= 1) hook();
 #pragma unroll
-                    for (int c = 0; c < CPL; c++) {
-                        const double2 y = yreg[i * CPL + c];
-                        if (IM) {
-                            // A = i B with B real: (iB)(yr + i yi) = -B yi + i B yr
-                            acc[c].x = fma(-vd.y, y.y, acc[c].x);
-                            acc[c].y = fma(vd.y, y.x, acc[c].y);
-                        } else {
-                            acc[c].x = fma(vd.x, y.x, acc[c].x);
-                            acc[c].y = fma(vd.x, y.y, acc[c].y);
-                            acc[c].x = fma(-vd.y, y.y, acc[c].x);
-                            acc[c].y = fma(vd.y, y.x, acc[c].y);
-                        }
-                    }
+                    for (int c = 0; c < CPL; c++) cfma_diag(acc[c], vd, yreg[i * CPL + c]);
                 }
 #ifndef QSIM_CH
 #define QSIM_CH 4
@@ -719,10 +758,8 @@ struct Kern {
                             const uint32_t e = ell[i][j];
                             if (SV)
                                 vv[q] = make_double2(0.0, vstat[i * MAXNNZ + j]);  // time-independent, loaded once per trajectory
-                            else if (IM)
-                                vv[q] = make_double2(0.0, lds1(Vs + (e >> 16)));
                             else
-                                vv[q] = lds2(Vs + (e >> 16));
+                                vv[q] = ldv(Vs, e);
 #pragma unroll
                             for (int c = 0; c < CPL; c++) yy[q][c] = lds2(yb + (e & 0xFFFFu) + 16 * c);
                         }
@@ -732,18 +769,7 @@ struct Kern {
                     for (int q = 0; q < CH; q++) {
                         if (j0 + q < MAXNNZ) {
 #pragma unroll
-                            for (int c = 0; c < CPL; c++) {
-                                const double2 y = yy[q][c];
-                                if (IM) {
-                                    acc[c].x = fma(-vv[q].y, y.y, acc[c].x);
-                                    acc[c].y = fma(vv[q].y, y.x, acc[c].y);
-                                } else {
-                                    acc[c].x = fma(vv[q].x, y.x, acc[c].x);
-                                    acc[c].y = fma(vv[q].x, y.y, acc[c].y);
-                                    acc[c].x = fma(-vv[q].y, y.y, acc[c].x);
-                                    acc[c].y = fma(vv[q].y, y.x, acc[c].y);
-                                }
-                            }
+                            for (int c = 0; c < CPL; c++) cfma(acc[c], vv[q], ell[i][j0 + q], yy[q][c]);
                         }
                     }
                 }
@@ -1281,7 +1307,7 @@ template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS>
 __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant__ LaunchArgs a) {
     extern __shared__ __align__(16) double smem[];
     typedef Kern<RPL, CPL, MAXNNZ, VM, RS> K;
-    constexpr bool IM = VM >= 1;
+    constexpr bool IM = K::IM;
     const int n = a.g.n;
     Geo g;
     g.lane = threadIdx.x & 31;
@@ -1321,7 +1347,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     g.sm_dw = sbase + a.off_dw;                          // double2[n_dyn_pairs]
     g.sm_drec = sbase + a.off_drec;                      // 64-byte records of the time-dependent slots
     const uint32_t tbase = sbase + a.common_bytes + team_in_cta * a.team_bytes;
-    g.v_stride = K::VB * a.nvp;
+    g.v_stride = K::VSTRIDE * a.nvp;
     g.sm_V = tbase;
     g.sm_chan = g.sm_V + ((5 * g.v_stride + 15u) & ~15u);
     g.sm_rev = g.sm_chan + 8u * 5 * a.ncp;
@@ -1348,7 +1374,10 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         }
         // the zero slot of every table (padding entries of short rows read it)
         for (int s = g.team_thread; s < 5; s += g.team_threads)
-            if (IM)
+            if (K::MX) {
+                sts1(g.sm_V + s * g.v_stride + 8 * a.g.n_slots, 0.0);
+                sts1(g.sm_V + s * g.v_stride + 8 * (a.nvp + a.g.n_slots), 0.0);
+            } else if (IM)
                 sts1(g.sm_V + s * g.v_stride + 8 * a.g.n_slots, 0.0);
             else
                 sts2(g.sm_V + s * g.v_stride + 16 * a.g.n_slots, make_double2(0.0, 0.0));
@@ -1385,6 +1414,9 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
             // slot 0xFFFF marks a zero entry (padding, or a row without a stored diagonal)
             const uint32_t sl = (!row_ok[i] || (e >> 16) == 0xFFFFu) ? (uint32_t)a.g.n_slots : (e >> 16);
             ell[i][j] = (16u * (e & 0xFFFFu) * a.y_row_stride) | ((K::VB * sl) << 16);
+            // mixed mode: an imaginary off-diagonal entry reads the second half of the split table
+            if (K::MX && j > 0 && sl < (uint32_t)a.g.n_slots && __ldg(a.slot_imag + sl))
+                ell[i][j] = (ell[i][j] + ((8u * a.nvp) << 16)) | 0x80000000u;
         }
     }
     double2 *sc_base = nullptr;

@@ -85,6 +85,13 @@ def test_kernel_dispatch_names_and_flops():
     # executed flop never exceed the dense count 8 d^3
     assert 0 < P.flops_per_rhs("unitary_propagator") <= 8 * 9 ** 3
     assert 0 < P.flops_per_rhs("unitary_state") <= 8 * 9 ** 2
+    # value modes: real Hamiltonian with static couplings -> 2 (imaginary generator, static off-diagonals in
+    # registers); Lindblad generator of real H and real collapse operators -> 4 (off-diagonal entries purely real
+    # or purely imaginary, complex diagonal); rotating-frame exchange terms are complex -> 0
+    assert "_vm2_" in P.kernel_name("unitary_propagator")
+    c4 = Problem(W.config("cfg4")[0])
+    assert "_vm4_" in c4.kernel_name("me_propagator") and "_vm4_" in c4.kernel_name("me_state")
+    assert "_vm0_" in Problem(W.config("cfg5")[0]).kernel_name("me_propagator")
 
 
 def test_argument_errors():
