@@ -19,11 +19,15 @@
 //   * resident mode: one batch per warp, state never leaves registers (unitary d <= 32, me_state).
 //     streamed mode: more batches than warps (me_propagator): u/k1 are read and u_new/k7 written
 //     once per step per column through L2-resident scratch; everything else stays on chip.
+//     row-split mode: state vectors longer than 96 entries (or rows longer than 16 entries): the rows
+//     of a column are spread over the team's warps, rows come from global memory sorted by length.
 //   * A(t): per trajectory the drive descriptors are resolved against the parameter row into
-//     shared memory; per step the team evaluates the drive channels (FP64 sin/cos/sqrt/Horner) for
-//     the five distinct stage times in parallel across lanes and refreshes only the time-dependent
-//     value slots.
-//   * step controller: EEst^b1 / qold^b2 as exp(b1 log EEst - b2 log qold), log qold carried over.
+//     shared memory.  Each time-dependent channel is kept as a windowed Chebyshev interpolant
+//     (12 nodes, built from the direct FP64 sin/cos/sqrt/Horner evaluator and checked against it);
+//     per step the five distinct stage times are evaluated from the interpolants and only the
+//     time-dependent value slots are refreshed (QSIM_FLAG_DIRECT_DRIVES: direct evaluation instead).
+//   * step controller: EEst^b1 and qold^b2 from mantissa-interval Taylor tables passed in the
+//     kernel parameters (constant bank); libm only outside the tables' range.
 //   * work distribution: persistent CTAs, dynamic queue over trajectories (atomic counter).
 // No reductions use atomics, so results are bitwise reproducible and independent of the save grid.
 #pragma once
@@ -1300,7 +1304,8 @@ struct Kern {
 };
 
 // MAXT: largest block the variant is launched with (128: one-warp teams, 4 per CTA, 2 CTAs = 8 warps per SM,
-// up to 255 registers so nothing spills; 288: teams of up to 9 warps, 168 registers).
+// up to 255 registers so nothing spills; 256: teams of 2-8 warps, one CTA per SM, 255 registers; 288: row-split
+// teams of nine warps (865 > n > 768), 168 registers).
 // MINB: minimum resident CTAs per SM the register allocation must allow; IM: purely imaginary generator
 // (unitary evolution under a real Hamiltonian): value slots hold Im(A) only, 2 DFMA per multiply-add.
 template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS>
