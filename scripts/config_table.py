@@ -2,7 +2,7 @@
 events, next to the CPU oracle (faithful mode, all host threads) on a small sample of the same points.
 Not the benchmark (bench.py measures cfg2 at full size); this is the table in profiles/README.md.
 
-usage: python scripts/config_table.py [cfgN:points:t_final ...] [--cpu-points K] > gpurun_out/config_table.jsonl
+usage: python scripts/config_table.py [cfgN:points:t_final ...] [--cpu-points K | --no-cpu] > gpurun_out/config_table.jsonl
 """
 import json
 import os
@@ -25,6 +25,7 @@ ORACLE_FN = {"unitary_propagator": co.UNITARY_PROPAGATOR, "me_propagator": co.ME
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     cpu_points = 0
+    no_cpu = "--no-cpu" in sys.argv[1:]
     for a in sys.argv[1:]:
         if a.startswith("--cpu-points="):
             cpu_points = int(a.split("=")[1])
@@ -70,7 +71,7 @@ def main():
                "kernel_ms": ms, "traj_per_s": n / (ms * 1e-3), "attempted_steps": steps,
                "steps_per_traj": steps / n, "executed_tflops": flops / (ms * 1e-3) / 1e12,
                "frac_of_fp64_peak": flops / (ms * 1e-3) / 1e12 / peak, "retcodes": np.unique(st["retcode"]).tolist()}
-        k = cpu_points or {"cfg1": 1, "cfg2": 2 * cores, "cfg3": cores, "cfg4": cores, "cfg5": 0}[name]
+        k = 0 if no_cpu else cpu_points or {"cfg1": 1, "cfg2": 2 * cores, "cfg3": cores, "cfg4": cores, "cfg5": 0}[name]
         if k > 0:
             kidx = np.linspace(0, n - 1, min(k, n)).astype(int)
             O = co.OracleProblem(cqs)
