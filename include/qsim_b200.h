@@ -226,6 +226,9 @@ int qsim_problem_eval(qsim_problem *prob, int kind, double t,
 /*
  * n_traj trajectories; trajectory i uses params[i*n_params .. ] and the save
  * grid ts[i*ts_stride .. +n_ts) (ts_stride == 0: one grid shared by all).
+ * ts_stride must be 0 or >= n_ts.  The state solvers read the initial state of
+ * trajectory i at init[i*init_stride ..] (complex elements); init_stride must be 0
+ * (one state shared by all) or >= the state length (d, or d*d for me_state).
  * ts must be sorted (the reference asserts issorted, time_evolution.jl:30);
  * integration starts at ts[0] from the identity / the given initial state and
  * one result is written per ts[k], ts[0] included (save_start=true).

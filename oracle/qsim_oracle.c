@@ -289,6 +289,34 @@ static void zgemm(int m, int n, int k, const double *A, const double *B, double 
         }
     }
 }
+/* As zgemm, also skipping the zero entries of A (A is k columns of m; its nonzeros are listed once per call).
+ * The surviving terms are added in the same order as in zgemm, so the result differs at most in the sign of
+ * zeros.  Used by the structured me_propagator mode, where H and the collapse operators are sparse. */
+static void zgemm_sa(int m, int n, int k, const double *A, const double *B, double *Cm, int accumulate, int *idx) {
+    /* idx: workspace of k*(m+1) ints: per column q of A, count followed by the row indices of its nonzeros */
+    for (int q = 0; q < k; q++) {
+        int cnt = 0;
+        for (int i = 0; i < m; i++)
+            if (A[2 * ((size_t)q * m + i)] != 0.0 || A[2 * ((size_t)q * m + i) + 1] != 0.0) idx[q * (m + 1) + 1 + cnt++] = i;
+        idx[q * (m + 1)] = cnt;
+    }
+    if (!accumulate) memset(Cm, 0, sizeof(double) * 2 * m * n);
+    for (int j = 0; j < n; j++) {
+        double *cj = Cm + 2 * (size_t)j * m;
+        for (int q = 0; q < k; q++) {
+            const double br = B[2 * ((size_t)j * k + q)], bi = B[2 * ((size_t)j * k + q) + 1];
+            if (br == 0.0 && bi == 0.0) continue;
+            const double *aq = A + 2 * (size_t)q * m;
+            const int *iq = idx + q * (m + 1);
+            for (int e = 1; e <= iq[0]; e++) {
+                const int i = iq[e];
+                double ar = aq[2 * i], ai = aq[2 * i + 1];
+                cj[2 * i] += ar * br - ai * bi;
+                cj[2 * i + 1] += ar * bi + ai * br;
+            }
+        }
+    }
+}
 /* dense GEMM without the zero skip: used in faithful mode (BLAS does not skip) */
 static void zgemm_dense(int m, int n, int k, const double *A, const double *B, double *Cm, int accumulate) {
     if (!accumulate) memset(Cm, 0, sizeof(double) * 2 * m * n);
@@ -339,6 +367,9 @@ typedef struct {
     int d;
     size_t n; /* complex unknowns */
     double *ham, *lm, *lh, *ldl, *tmp1, *tmp2, *eye, *sup, *xt;
+    /* per-RHS-call collapse operators L_i(t), L_i', L_i'L_i (n_lind matrices each; me_prepare) */
+    double *lms, *lhs, *ldls;
+    int *spidx;
 } rhs_ctx;
 
 static void lind_matrix(const rhs_ctx *c, int i, double t, double *lm) {
@@ -351,11 +382,28 @@ static void lind_matrix(const rhs_ctx *c, int i, double t, double *lm) {
     }
 }
 
-/* d x d master-equation RHS on one matrix X (time_evolution.jl:146,152) */
-static void me_apply(rhs_ctx *c, double t, const double *X, double *dX) {
+/* collapse operators at time t, formed once per RHS call (they are the same for every column) */
+static void me_prepare(rhs_ctx *c, double t) {
+    const int d = c->d, dd = d * d, nl = c->p->n_lind;
+    if (!c->lms && nl > 0) {
+        c->lms = (double *)malloc(sizeof(double) * 2 * dd * nl);
+        c->lhs = (double *)malloc(sizeof(double) * 2 * dd * nl);
+        c->ldls = (double *)malloc(sizeof(double) * 2 * dd * nl);
+    }
+    if (!c->spidx) c->spidx = (int *)malloc(sizeof(int) * (size_t)d * (d + 1));
+    for (int i = 0; i < nl; i++) {
+        double *lm = c->lms + 2 * (size_t)dd * i, *lh = c->lhs + 2 * (size_t)dd * i, *ldl = c->ldls + 2 * (size_t)dd * i;
+        lind_matrix(c, i, t, lm);
+        adjoint(d, lm, lh);
+        zgemm(d, d, d, lh, lm, ldl, 0);
+    }
+}
+
+/* d x d master-equation RHS on one matrix X (time_evolution.jl:146,152); me_prepare(c, t) first */
+static void me_apply(rhs_ctx *c, const double *X, double *dX) {
     const int d = c->d, dd = d * d;
     /* -2 pi i (H X - X H) */
-    zgemm(d, d, d, c->ham, X, c->tmp1, 0);
+    zgemm_sa(d, d, d, c->ham, X, c->tmp1, 0, c->spidx);
     zgemm(d, d, d, X, c->ham, c->tmp2, 0);
     for (int q = 0; q < dd; q++) {
         double re = c->tmp1[2 * q] - c->tmp2[2 * q], im = c->tmp1[2 * q + 1] - c->tmp2[2 * q + 1];
@@ -363,16 +411,15 @@ static void me_apply(rhs_ctx *c, double t, const double *X, double *dX) {
         dX[2 * q + 1] = -TWO_PI * re;
     }
     for (int i = 0; i < c->p->n_lind; i++) {
-        lind_matrix(c, i, t, c->lm);
-        adjoint(d, c->lm, c->lh);
+        const double *lm = c->lms + 2 * (size_t)dd * i, *lh = c->lhs + 2 * (size_t)dd * i,
+                     *ldl = c->ldls + 2 * (size_t)dd * i;
         /* L X L' */
-        zgemm(d, d, d, c->lm, X, c->tmp1, 0);
-        zgemm(d, d, d, c->tmp1, c->lh, c->tmp2, 0);
+        zgemm_sa(d, d, d, lm, X, c->tmp1, 0, c->spidx);
+        zgemm(d, d, d, c->tmp1, lh, c->tmp2, 0);
         for (int q = 0; q < 2 * dd; q++) dX[q] += TWO_PI * c->tmp2[q];
         /* -1/2 L'L X - 1/2 X L'L */
-        zgemm(d, d, d, c->lh, c->lm, c->ldl, 0);
-        zgemm(d, d, d, c->ldl, X, c->tmp1, 0);
-        zgemm(d, d, d, X, c->ldl, c->tmp2, 0);
+        zgemm_sa(d, d, d, ldl, X, c->tmp1, 0, c->spidx);
+        zgemm(d, d, d, X, ldl, c->tmp2, 0);
         for (int q = 0; q < 2 * dd; q++) dX[q] -= TWO_PI * 0.5 * (c->tmp1[q] + c->tmp2[q]);
     }
 }
@@ -428,9 +475,11 @@ static void rhs_eval(rhs_ctx *c, const double *u, double t, double *du) {
         else
             zgemm(d, c->which == 0 ? d : 1, d, c->ham, u, du, 0);
     } else if (c->which == 3) {
-        me_apply(c, t, u, du);
+        me_prepare(c, t);
+        me_apply(c, u, du);
     } else if (c->mode == 1) {
-        for (int j = 0; j < dd; j++) me_apply(c, t, u + 2 * (size_t)j * dd, du + 2 * (size_t)j * dd);
+        me_prepare(c, t);
+        for (int j = 0; j < dd; j++) me_apply(c, u + 2 * (size_t)j * dd, du + 2 * (size_t)j * dd);
     } else {
         build_super_h(c, c->sup);
         zgemm_dense(dd, dd, dd, c->sup, u, du, 0);
@@ -699,6 +748,7 @@ static void *sweep_worker(void *arg) {
                   job->stats ? job->stats + i : NULL);
     }
     free(u0); free(c.ham); free(c.lm); free(c.lh); free(c.ldl); free(c.tmp1); free(c.tmp2); free(c.eye); free(c.sup);
+    free(c.lms); free(c.lhs); free(c.ldls); free(c.spidx);
     return NULL;
 }
 

@@ -813,6 +813,12 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     if (p->n_params > 0 && !params) return fail(QSIM_ERR_ARG, "params is NULL but the problem has sweep parameters");
     if ((which == 1 || which == 3) && !init) return fail(QSIM_ERR_ARG, "initial state is NULL");
     if (ts_stride != 0 && ts_stride < n_ts) return fail(QSIM_ERR_ARG, "ts_stride must be 0 or >= n_ts");
+    if (which == 1 || which == 3) {
+        // a per-trajectory initial state must hold the whole state vector (d or d*d complex numbers)
+        const int64_t n_init = which == 1 ? p->d : (int64_t)p->d * p->d;
+        if (init_stride != 0 && init_stride < n_init)
+            return fail(QSIM_ERR_ARG, "init_stride must be 0 (shared initial state) or >= the state length");
+    }
     qsim_solver_opts o;
     if (opts_in)
         o = *opts_in;

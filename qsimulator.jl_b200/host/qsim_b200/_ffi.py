@@ -127,6 +127,17 @@ class Context:
         return v.value
 
 
+def device_available() -> bool:
+    """False only when qsim_create reports QSIM_ERR_NO_DEVICE (no usable CUDA device); any other failure raises."""
+    try:
+        Context(0).close()
+        return True
+    except QsimError as e:
+        if e.code == _abi.ERR_NO_DEVICE and os.path.exists(LIB_PATH):
+            return False
+        raise
+
+
 _default_ctx: Optional[Context] = None
 
 

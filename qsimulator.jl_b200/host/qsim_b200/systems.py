@@ -7,9 +7,9 @@ time-evolution hot path:
   hamiltonian  Resonator :178-179, duffing_hamiltonian :189-194,
                DuffingTransmon :199-206, PerturbativeTransmon :213-216,
                RotatingFrameSystem :242-252, subtract_number! :259-265
-ChargeBasisTransmon / DiagonalChargeBasisTransmon / fit_transmon are out of
-scope: they need a 101x101 eigensolve per RHS call
-or run once as pre-processing.
+  fit_transmon, TransmonSpec(DuffingSpec) :70-73, :288-323 (perturbative model)
+ChargeBasisTransmon drives are out of scope: they need a
+101x101 eigensolve per RHS call.
 """
 from __future__ import annotations
 

@@ -19,3 +19,16 @@ def pytest_sessionstart(session):
         sys.path.insert(0, ROOT)
         import __graft_entry__
         __graft_entry__.build()
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests skip (instead of failing) on a box without a usable CUDA device."""
+    import pytest
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if not gpu_items:
+        return
+    from qsim_b200 import _ffi
+    if not _ffi.device_available():   # only the library's own QSIM_ERR_NO_DEVICE skips; any other failure raises
+        skip = pytest.mark.skip(reason="no usable CUDA device (qsim_create returned QSIM_ERR_NO_DEVICE)")
+        for it in gpu_items:
+            it.add_marker(skip)

@@ -63,10 +63,12 @@ def test_cfg2_sweep_corners_and_interior():
 
 
 def test_cfg3_three_transmons():
-    """d = 27: one trajectory per 9-warp team."""
+    """d = 27 (BASELINE config 3), 20 ns = ~8.3k steps per trajectory, 21 saves: corners and interior of the grid."""
     cqs, _, _, _ = W.config("cfg3")
-    params = W.amp_freq_grid(128, 128)[[0, 8191, 16383]]
-    check_parity(cqs, "unitary_propagator", np.arange(0.0, 4.0), params)
+    params = W.amp_freq_grid(128, 128)[[0, 5000, 8191, 16383]]
+    got, st, err = check_parity(cqs, "unitary_propagator", np.arange(0.0, 21.0), params)
+    assert st["n_accept"].min() > 8000
+    print(f"cfg3 20 ns: max rel err {err:.2e}, steps {st['n_accept'].min()}..{st['n_accept'].max()}")
 
 
 def test_literal_hermitian_dense_and_states():
@@ -212,11 +214,13 @@ def test_decay_and_dephasing_known_answer():
 
 
 def test_cfg4_lindblad_two_transmons():
-    """d^2 = 81 superoperator propagator, swept T1/Tphi (streamed kernel), 3 ns."""
+    """d^2 = 81 superoperator propagator (BASELINE config 4), swept T1/Tphi, 6 ns = ~1.4k steps per trajectory."""
     cqs, params, _, _ = W.config("cfg4")
     pr = params[[0, 4097, 8191]]
-    ts = np.array([0.0, 1.5, 3.0])
+    ts = np.array([0.0, 1.5, 6.0])
     got, st, err = check_parity(cqs, "me_propagator", ts, pr)
+    assert st["n_accept"].min() > 1300
+    print(f"cfg4 6 ns: max rel err {err:.2e}, steps {st['n_accept'].min()}..{st['n_accept'].max()}")
     vi = np.eye(9).ravel(order="F")
     for s in got[:, -1]:
         assert np.abs(vi @ s - vi).max() < 1e-5          # trace preservation
@@ -262,7 +266,9 @@ def test_rowsplit_d12_lindblad_propagator_and_state():
 
 
 def test_cfg5_three_transmon_lindblad():
-    """d^2 = 729 (BASELINE config 5): me_state against the oracle; me_propagator checked through the
+    """d^2 = 729 (BASELINE config 5).  me_propagator against the oracle's structured mode (the commutator /
+    sandwich form of time_evolution.jl:98-111 applied column by column) elementwise to 1e-8 with identical step
+    counts, on two sweep points over a span of seven accepted steps; me_state against the oracle; and the
     properties the domain offers (trace preservation, agreement with me_state on a basis state)."""
     cqs, params, _, _ = W.config("cfg5")
     pr = params[[0, 40000]]
@@ -272,8 +278,9 @@ def test_cfg5_three_transmon_lindblad():
     rhos, _, _ = check_parity(cqs, "me_state", ts, pr, init=rho0)
     P = Problem(cqs)
     assert "rowsplit" in P.kernel_name("me_propagator")
-    sup, st = P.solve("me_propagator", ts, params=pr)
-    assert np.all(st["retcode"] == 0)
+    sup, st, err = check_parity(cqs, "me_propagator", ts, pr)
+    assert st["n_accept"].min() >= 3
+    print(f"cfg5 me_propagator vs structured oracle: max rel err {err:.2e}, steps {st['n_accept'].tolist()}")
     vi = np.eye(27).ravel(order="F")
     for s, rho in zip(sup[:, -1], rhos[:, -1]):
         assert np.abs(vi @ s - vi).max() < 1e-5
