@@ -21,6 +21,14 @@
 
 namespace qsim {
 void build_generator(const qsim_problem &p, int which, Generator &g);
+// qsim_layout.cpp: bank-conflict-aware placement for the row-split kernels
+void rowsplit_rows(const Generator &g, std::vector<std::vector<uint32_t>> &compact, std::vector<int> &perm);
+void rowsplit_groups(const Generator &g, const std::vector<std::vector<uint32_t>> &compact, const std::vector<int> &perm,
+                     int what, std::vector<std::vector<int>> &groups);
+void anneal_colors(const std::vector<std::vector<int>> &groups, const std::vector<int> &cls, int n_colors, long iters,
+                   std::vector<int> &color);
+long layout_groups_cost(const std::vector<std::vector<int>> &groups, const std::vector<int> &color, int n_colors);
+void optimize_value_slots(Generator &g, long iters);
 void host_eval_generator(const Generator &g, double t, const double *row, cplx *dense);
 const SeriesTables &series_tables();
 }  // namespace qsim
@@ -79,22 +87,30 @@ struct qsim_problem::DeviceCopy {
     double *dyn_rec = nullptr;       // 64-byte records of the time-dependent slots
     double *tables = nullptr;        // tabulated envelopes (nullptr when the problem has none)
     int fast_ok = 0, fast_chA = 0, fast_chB = 0;  // records are in (constant, channel A, channel B) order
-    uint32_t *ell_packed = nullptr;  // row-split kernels: sorted, translated rows; row permutation; chunk lengths
-    int *rs_perm = nullptr, *rs_len = nullptr;
-    int packed_stride = -1, packed_warps = -1, packed_vm = -1;
+    // row-split kernels: sorted, translated rows; row permutation; chunk offsets and lengths.  One set per
+    // (stage stride, team warps, value mode): me_propagator and me_state of one problem use different sets and may
+    // run concurrently from different ctxs, so sets are never replaced, only added (freed with the problem).
+    struct Packed {
+        int stride, warps, vm;
+        uint32_t *ell = nullptr;
+        int *perm = nullptr, *off = nullptr, *len = nullptr, *pos = nullptr;
+    };
+    std::vector<Packed> packed;
     uint8_t *slot_imag = nullptr;    // value mode 4
     uint32_t *blk_ell = nullptr;     // blocked kernels: row table and value slot ids (built by make_plan)
     uint16_t *blk_slot = nullptr;
     ~DeviceCopy() { free_all(); }  // the owning device must be current
     void free_all() {
-        cudaFree(ell_packed);
-        cudaFree(rs_perm);
-        cudaFree(rs_len);
+        for (auto &pk : packed) {
+            cudaFree(pk.ell);
+            cudaFree(pk.perm);
+            cudaFree(pk.off);
+            cudaFree(pk.len);
+            cudaFree(pk.pos);
+        }
+        packed.clear();
         cudaFree(slot_imag);
         slot_imag = nullptr;
-        ell_packed = nullptr;
-        rs_perm = nullptr;
-        rs_len = nullptr;
         cudaFree(blk_ell);
         cudaFree(blk_slot);
         blk_ell = nullptr;
@@ -354,11 +370,48 @@ int qsim_problem_finalize(qsim_problem *p) {
     return QSIM_OK;
 }
 
+// Value mode 4 ("mixed"): every off-diagonal entry purely real or purely imaginary for all times and parameters
+// (all channel weights of its slot real, or all imaginary); the diagonal may be complex.  slot_imag[sl] = 1 for the
+// purely imaginary slots.
+static bool generator_is_mixed(const Generator &g, std::vector<uint8_t> &slot_imag) {
+    const int n = g.n;
+    bool mixed = g.n_slots <= 2045;  // 8-byte offsets into both halves of the split table fit 15 bits
+    slot_imag.assign((size_t)g.n_slots, 0);
+    std::vector<uint8_t> off_diag((size_t)g.n_slots, 0);
+    for (int j = 1; j < g.max_nnz; j++)
+        for (int r = 0; r < n; r++) {
+            const uint32_t sl = g.ell[(size_t)j * n + r] >> 16;
+            if (sl != 0xFFFFu) off_diag[sl] = 1;
+        }
+    for (int sl = 0; sl < g.n_slots && mixed; sl++) {
+        bool any_re = false, any_im = false;
+        for (int q = g.slot_ptr[sl]; q < g.slot_ptr[sl + 1]; q++) {
+            any_re = any_re || g.pair_w[(size_t)q].real() != 0.0;
+            any_im = any_im || g.pair_w[(size_t)q].imag() != 0.0;
+        }
+        if (off_diag[(size_t)sl] && any_re && any_im) mixed = false;
+        slot_imag[(size_t)sl] = any_im ? 1 : 0;
+    }
+    return mixed;
+}
+
+static long anneal_iters(int n_items) {
+    if (const char *env = std::getenv("QSIM_ANNEAL_ITERS")) return std::atol(env);   // development: 0 disables
+    return std::min<long>(1500000, 2000L * n_items);
+}
+
 static int ensure_generator(qsim_problem *p, int w) {
     if (!p->finalized) return fail(QSIM_ERR_STATE, "problem is not finalized");
+    std::lock_guard<std::mutex> lock(p->dev_mutex);
     if (p->gen_built[w]) return QSIM_OK;
     try {
         build_generator(*p, w, p->gen[w]);
+        Generator &g = p->gen[w];
+        // Row-split kernels with a complex value table (16 bytes per slot): renumber the slots so that the values a
+        // quarter warp reads together sit in distinct shared-memory bank groups (qsim_layout.cpp).
+        std::vector<uint8_t> slot_imag;
+        if ((g.n > 96 || g.max_nnz > 16) && !g.imag_only && !generator_is_mixed(g, slot_imag) && anneal_iters(g.n_slots) > 0)
+            optimize_value_slots(g, anneal_iters(g.n_slots));
     } catch (const std::exception &e) {
         return fail(QSIM_ERR_UNSUPPORTED, std::string("generator assembly failed: ") + e.what());
     }
@@ -395,6 +448,10 @@ struct Plan {
     int off_dptr = 0, off_dw = 0, off_drec = 0, dyn_fast = 0;
     size_t smem = 0, scratch_per_team = 0;
     int vm = 0;                        // value mode of the chosen variant
+    // row-split teams: compact row table (see LaunchArgs::rs_off), row permutation, chunk offsets / lengths
+    std::vector<uint32_t> rs_table;
+    std::vector<int> rs_perm, rs_off, rs_len, rs_pos;
+    int ell_in_smem = 0, off_ell = 0, ell_bytes = 0, rs_prefetch = 0, off_pf = 0;
     std::vector<uint8_t> slot_imag;    // value mode 4: per slot, 1 = purely imaginary, 0 = purely real
     // blocked variant (value mode 3): block rows, row table [1 + max blocks][n] and value slot ids
     int blk_rows = 0, blk_nnz = 0;
@@ -529,6 +586,82 @@ static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int bloc
     return best;
 }
 
+// Row tables of the row-split kernels.  Rows are sorted by descending length and dealt out in chunks of 32
+// (chunk c = slot * team_warps + warp), so each (warp, slot) group runs exactly as many entries as its longest row
+// and the warps of a team carry equal work; without this every row would be padded to the longest row of the
+// matrix (12 entries against an average of 6 for the d^2 = 729 superoperator).  Entries are translated to byte
+// offsets into the stage buffer (indexed by sorted position) and the value table.  Compact layout: chunk c owns
+// table rows [off[c], off[c] + len[c]) of 32 entries (one per lane); len[c] = 1 (diagonal) + the chunk's longest
+// off-diagonal count rounded up to even; two more zero rows follow each chunk so the kernel's pairwise-pipelined
+// gather may read one pair ahead.  Lanes past the last row and short rows read zero-slot entries.
+// full == false: only the chunk offsets / lengths and the table size (make_plan runs on every call); full == true: also
+// the entries, with the rows' positions inside the stage buffer chosen by anneal_colors() so that the sources a
+// quarter warp gathers together fall into distinct bank groups (rs_pos[q] = position of sorted row q; the stage
+// vector is the only thing stored in that order -- scratch, prefetch buffers and the table itself stay in sorted order).
+static void build_rowsplit_table(const Generator &g, Plan &pl, bool full) {
+    const int n = g.n, n_chunks = 3 * pl.team_warps;
+    const uint32_t vb = pl.vm >= 1 ? 8u : 16u;
+    std::vector<std::vector<uint32_t>> compact;
+    std::vector<int> perm;
+    rowsplit_rows(g, compact, perm);
+    pl.rs_perm = perm;
+    pl.rs_off.assign((size_t)n_chunks, 0);
+    pl.rs_len.assign((size_t)n_chunks, 1);
+    size_t total = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        int longest = 1;
+        if (c * 32 < n) longest = (int)compact[(size_t)perm[(size_t)c * 32]].size();
+        pl.rs_off[(size_t)c] = (int)(total / 32);
+        pl.rs_len[(size_t)c] = 1 + 2 * (longest / 2);  // 1 + (longest - 1) rounded up to even
+        total += (size_t)32 * (pl.rs_len[(size_t)c] + 2);
+    }
+    pl.ell_bytes = (int)(total * sizeof(uint32_t));
+    if (!full) return;
+
+    // positions inside the stage buffer: pos[r] for state row r
+    std::vector<int> pos((size_t)n);
+    {
+        std::vector<int> color((size_t)n), cls((size_t)n, 0);
+        for (int q = 0; q < n; q++) color[(size_t)perm[(size_t)q]] = q % 8;
+        const long iters = anneal_iters(n);
+        if (iters > 0 && pl.y_row_stride % 2 == 1) {
+            std::vector<std::vector<int>> groups;
+            rowsplit_groups(g, compact, perm, 0, groups);
+            const long before = layout_groups_cost(groups, color, 8);
+            anneal_colors(groups, cls, 8, iters, color);
+            if (std::getenv("QSIM_DEBUG"))
+                std::fprintf(stderr, "[qsim] row-split stage layout: %zu quarter-warp accesses, wavefronts %ld -> %ld\n",
+                             groups.size(), before, layout_groups_cost(groups, color, 8));
+        }
+        std::vector<std::vector<int>> free_pos(8);
+        for (int p = n - 1; p >= 0; p--) free_pos[(size_t)(p % 8)].push_back(p);
+        for (int q = 0; q < n; q++) {
+            auto &v = free_pos[(size_t)color[(size_t)perm[(size_t)q]]];
+            pos[(size_t)perm[(size_t)q]] = v.back();
+            v.pop_back();
+        }
+    }
+    pl.rs_pos.resize((size_t)n);
+    for (int q = 0; q < n; q++) pl.rs_pos[(size_t)q] = pos[(size_t)perm[(size_t)q]];
+    const uint32_t zero = (16u * (uint32_t)pos[(size_t)perm[(size_t)n - 1]] * (uint32_t)pl.y_row_stride) | ((vb * (uint32_t)g.n_slots) << 16);
+    pl.rs_table.assign(total, zero);
+    for (int c = 0; c < n_chunks; c++) {
+        uint32_t *tab = pl.rs_table.data() + (size_t)32 * pl.rs_off[(size_t)c];
+        for (int l = 0; l < 32 && c * 32 + l < n; l++) {
+            const auto &row = compact[(size_t)perm[(size_t)c * 32 + l]];
+            for (size_t j = 0; j < row.size(); j++) {
+                const uint32_t src = (uint32_t)pos[(size_t)(row[j] & 0xFFFFu)];
+                const uint32_t sl = (row[j] >> 16) == 0xFFFFu ? (uint32_t)g.n_slots : (row[j] >> 16);
+                uint32_t e = (16u * src * (uint32_t)pl.y_row_stride) | ((vb * sl) << 16);
+                // value mode 4: an imaginary off-diagonal entry reads the second half of the split value table
+                if (pl.vm == 4 && j > 0 && sl < (uint32_t)g.n_slots && pl.slot_imag[sl])
+                    e = (e + ((8u * (uint32_t)pl.nvp) << 16)) | 0x80000000u;
+                tab[j * 32 + (size_t)l] = e;
+            }
+        }
+    }
+}
+
 // which: 0 unitary_propagator, 1 unitary_state, 2 me_propagator, 3 me_state
 static int make_plan(qsim_problem *p, int which, Plan &pl) {
     pl.w = which >= 2 ? 1 : 0;
@@ -625,25 +758,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         if (static_off && rpl * cpl <= 3 && find_variant(rpl, cpl, g.max_nnz, pl.block, 2, 0)) vm = 2;
     }
     if (vm == 0) {
-        // value mode 4: every off-diagonal entry purely real or purely imaginary for all times and parameters
-        // (all channel weights of its slot real, or all imaginary); the diagonal may be complex
-        bool mixed = g.n_slots <= 2045;  // 8-byte offsets into both halves of the split table fit 15 bits
-        pl.slot_imag.assign((size_t)g.n_slots, 0);
-        std::vector<uint8_t> off_diag((size_t)g.n_slots, 0);
-        for (int j = 1; j < g.max_nnz; j++)
-            for (int r = 0; r < n; r++) {
-                const uint32_t sl = g.ell[(size_t)j * n + r] >> 16;
-                if (sl != 0xFFFFu) off_diag[sl] = 1;
-            }
-        for (int sl = 0; sl < g.n_slots && mixed; sl++) {
-            bool any_re = false, any_im = false;
-            for (int q = g.slot_ptr[sl]; q < g.slot_ptr[sl + 1]; q++) {
-                any_re = any_re || g.pair_w[(size_t)q].real() != 0.0;
-                any_im = any_im || g.pair_w[(size_t)q].imag() != 0.0;
-            }
-            if (off_diag[(size_t)sl] && any_re && any_im) mixed = false;
-            pl.slot_imag[(size_t)sl] = any_im ? 1 : 0;
-        }
+        const bool mixed = generator_is_mixed(g, pl.slot_imag);
         if (mixed && find_variant(rpl, cpl, g.max_nnz, pl.block, 4, pl.rowsplit)) vm = 4;
     }
     pl.vm = vm;
@@ -689,13 +804,39 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     pl.common_bytes = pl.off_drec + (pl.dyn_fast ? 64 * std::max(g.n_dyn_slots, 1) : 16);
     pl.team_bytes = ((((pl.vm >= 1 && pl.vm <= 3) ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
                     (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride + 128 * pl.team_warps;
+    const size_t smem_cap = 220 * 1024;
+    if (pl.rowsplit) {
+        build_rowsplit_table(g, pl, std::getenv("QSIM_DEBUG_LAYOUT") != nullptr);   // (debug: run the annealer without a GPU)
+        // team region: + three mbarriers, + the two prefetch buffers (u, k1 of a column each) for streamed teams;
+        // common region: + the row table.  Both are dropped (global-memory table, direct scratch loads) when the
+        // CTA would not fit.
+        pl.off_pf = (pl.team_bytes + 15) & ~15;
+        pl.team_bytes = pl.off_pf + 32;
+        pl.off_ell = (pl.common_bytes + 15) & ~15;
+        const size_t base = (size_t)pl.off_ell + (size_t)pl.team_bytes * pl.teams_per_cta;
+        const size_t pf = pl.streamed ? (size_t)4 * 16 * n : 0;
+        const bool no_smem_table = std::getenv("QSIM_RS_GLOBAL_TABLE") != nullptr;   // development switches
+        const bool no_prefetch = std::getenv("QSIM_RS_NO_PREFETCH") != nullptr;
+        if (!no_smem_table && base + pl.ell_bytes <= smem_cap) {
+            pl.ell_in_smem = 1;
+            pl.common_bytes = pl.off_ell + pl.ell_bytes;
+        }
+        if (pf > 0 && !no_prefetch && (size_t)pl.common_bytes + (size_t)(pl.team_bytes + pf) * pl.teams_per_cta <= smem_cap) {
+            pl.rs_prefetch = 1;
+            pl.team_bytes += (int)pf;
+        }
+    }
     pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
     // large value tables (dense Hamiltonians): fewer teams per CTA until the CTA fits
-    while (pl.smem > 220 * 1024 && pl.teams_per_cta > 1) {
+    while (pl.smem > smem_cap && pl.teams_per_cta > 1) {
         pl.teams_per_cta /= 2;
         pl.block = pl.team_warps * 32 * pl.teams_per_cta;
         pl.smem = (size_t)pl.common_bytes + (size_t)pl.team_bytes * pl.teams_per_cta;
     }
+    if (std::getenv("QSIM_DEBUG"))
+        std::fprintf(stderr, "[qsim] n=%d slots=%d (dyn %d) chan=%d: common %d B, team %d B x %d, smem %zu B%s%s\n", n, g.n_slots,
+                     g.n_dyn_slots, g.n_chan, pl.common_bytes, pl.team_bytes, pl.teams_per_cta, pl.smem,
+                     pl.ell_in_smem ? ", row table in smem" : "", pl.rs_prefetch ? ", bulk prefetch" : "");
     pl.scratch_per_team = pl.streamed ? (size_t)4 * pl.n_batches * cpb * n * sizeof(double2) : 0;
     if (pl.smem > 220 * 1024) return fail(QSIM_ERR_UNSUPPORTED, "problem needs more shared memory than one SM has");
     return QSIM_OK;
@@ -842,66 +983,43 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     qsim_problem::DeviceCopy *dc = nullptr;
     if (int rc = ensure_device_copy(c, p, pl.w, &dc)) return rc;
     const Generator &g = p->gen[pl.w];
-    std::unique_lock<std::mutex> packed_lock(p->dev_mutex);
-    if (pl.rowsplit && (!dc->ell_packed || dc->packed_stride != pl.y_row_stride || dc->packed_warps != pl.team_warps ||
-                        dc->packed_vm != pl.vm)) {
-        // Row tables of the row-split kernels.  Rows are sorted by descending length and dealt out in chunks of 32
-        // (chunk c = slot * team_warps + warp), so each (warp, slot) group runs exactly as many entries as its
-        // longest row and the warps of a team carry equal work; without this every row would be padded to the
-        // longest row of the matrix (20 entries against an average of 6 for the d^2 = 729 superoperator).
-        // Entries are translated to byte offsets into the stage buffer (indexed by sorted position) and the
-        // value table; eight zero-slot padding rows serve the lanes past the last row.
-        const int n = g.n, rows = n + 8;
-        const uint32_t vb = pl.vm >= 1 ? 8u : 16u;
-        std::vector<std::vector<uint32_t>> compact((size_t)n);
-        for (int r = 0; r < n; r++) {
-            compact[(size_t)r].push_back(g.ell[(size_t)r]);  // the diagonal entry (own row; slot 0xFFFF if absent)
-            for (int j = 1; j < g.max_nnz; j++) {
-                const uint32_t e = g.ell[(size_t)j * n + r];
-                if ((e >> 16) != 0xFFFFu) compact[(size_t)r].push_back(e);
+    // device tables that depend on the plan: looked up / uploaded under the problem's lock, and the pointers this
+    // launch uses are copied out while it is held (another ctx may add sets concurrently; sets are never replaced)
+    qsim_problem::DeviceCopy::Packed pk;
+    const uint8_t *d_slot_imag = nullptr;
+    const uint32_t *d_blk_ell = nullptr;
+    const uint16_t *d_blk_slot = nullptr;
+    {
+        std::lock_guard<std::mutex> packed_lock(p->dev_mutex);
+        if (pl.rowsplit) {
+            bool have = false;
+            for (const auto &q : dc->packed)
+                if (q.stride == pl.y_row_stride && q.warps == pl.team_warps && q.vm == pl.vm) {
+                    pk = q;
+                    have = true;
+                }
+            if (!have) {
+                pk.stride = pl.y_row_stride;
+                pk.warps = pl.team_warps;
+                pk.vm = pl.vm;
+                build_rowsplit_table(g, pl, true);
+                CU(upload(&pk.ell, pl.rs_table));
+                CU(upload(&pk.pos, pl.rs_pos));
+                CU(upload(&pk.perm, pl.rs_perm));
+                CU(upload(&pk.off, pl.rs_off));
+                CU(upload(&pk.len, pl.rs_len));
+                dc->packed.push_back(pk);
             }
         }
-        std::vector<int> perm((size_t)n), inv((size_t)n);
-        for (int r = 0; r < n; r++) perm[(size_t)r] = r;
-        std::stable_sort(perm.begin(), perm.end(),
-                         [&](int x, int y) { return compact[(size_t)x].size() > compact[(size_t)y].size(); });
-        for (int q = 0; q < n; q++) inv[(size_t)perm[(size_t)q]] = q;
-        const int depth = (int)compact[(size_t)perm[0]].size();
-        std::vector<int> lens((size_t)3 * pl.team_warps, 0);
-        for (int c = 0; c * 32 < n; c++) lens[(size_t)c] = (int)compact[(size_t)perm[(size_t)c * 32]].size();
-        const uint32_t zero = (16u * (uint32_t)(n - 1) * (uint32_t)pl.y_row_stride) | ((vb * (uint32_t)g.n_slots) << 16);
-        std::vector<uint32_t> packed((size_t)depth * rows, zero);
-        for (int q = 0; q < n; q++) {
-            const auto &row = compact[(size_t)perm[(size_t)q]];
-            for (size_t j = 0; j < row.size(); j++) {
-                const uint32_t src = (uint32_t)inv[(size_t)(row[j] & 0xFFFFu)];
-                const uint32_t sl = (row[j] >> 16) == 0xFFFFu ? (uint32_t)g.n_slots : (row[j] >> 16);
-                uint32_t e = (16u * src * (uint32_t)pl.y_row_stride) | ((vb * sl) << 16);
-                // value mode 4: an imaginary off-diagonal entry reads the second half of the split value table
-                if (pl.vm == 4 && j > 0 && sl < (uint32_t)g.n_slots && pl.slot_imag[sl])
-                    e = (e + ((8u * (uint32_t)pl.nvp) << 16)) | 0x80000000u;
-                packed[j * rows + (size_t)q] = e;
-            }
+        if (pl.vm == 4 && !dc->slot_imag) CU(upload(&dc->slot_imag, pl.slot_imag));
+        if (pl.blk_rows > 0 && !dc->blk_ell) {
+            CU(upload(&dc->blk_ell, pl.blk_ell));
+            CU(upload(&dc->blk_slot, pl.blk_slot));
         }
-        cudaFree(dc->ell_packed);
-        cudaFree(dc->rs_perm);
-        cudaFree(dc->rs_len);
-        dc->ell_packed = nullptr;
-        dc->rs_perm = nullptr;
-        dc->rs_len = nullptr;
-        CU(upload(&dc->ell_packed, packed));
-        CU(upload(&dc->rs_perm, perm));
-        CU(upload(&dc->rs_len, lens));
-        dc->packed_stride = pl.y_row_stride;
-        dc->packed_warps = pl.team_warps;
-        dc->packed_vm = pl.vm;
+        d_slot_imag = dc->slot_imag;
+        d_blk_ell = dc->blk_ell;
+        d_blk_slot = dc->blk_slot;
     }
-    if (pl.vm == 4 && !dc->slot_imag) CU(upload(&dc->slot_imag, pl.slot_imag));
-    if (pl.blk_rows > 0 && !dc->blk_ell) {
-        CU(upload(&dc->blk_ell, pl.blk_ell));
-        CU(upload(&dc->blk_slot, pl.blk_slot));
-    }
-    packed_lock.unlock();
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : c->stream;
 
     int ctas_per_sm = 0;
@@ -993,16 +1111,23 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.fast_chA = dc->fast_chA;
     a.fast_chB = dc->fast_chB;
     if (pl.blk_rows > 0) {
-        a.g.ell = dc->blk_ell;
+        a.g.ell = d_blk_ell;
         a.g.max_nnz = pl.blk_nnz;
-        a.blk_slot = dc->blk_slot;
+        a.blk_slot = d_blk_slot;
         a.n_blk_rows = pl.blk_rows;
     }
-    a.ell_packed = dc->ell_packed;
+    a.ell_packed = pk.ell;
     a.ell_rows = g.n + 8;
-    a.rs_perm = dc->rs_perm;
-    a.rs_len = dc->rs_len;
-    a.slot_imag = dc->slot_imag;
+    a.rs_perm = pk.perm;
+    a.rs_off = pk.off;
+    a.rs_pos = pk.pos;
+    a.rs_len = pk.len;
+    a.ell_in_smem = pl.ell_in_smem;
+    a.off_ell = pl.off_ell;
+    a.ell_bytes = pl.ell_bytes;
+    a.rs_prefetch = pl.rs_prefetch;
+    a.off_pf = pl.off_pf;
+    a.slot_imag = d_slot_imag;
     a.ncols = pl.ncols;
     a.identity_init = pl.identity;
     a.n_params = p->n_params;

@@ -30,11 +30,12 @@ QSIM_DECLARE(variants_blocked)
         R, C, M, T, B, I, 0, "tsit5_r" #R "c" #C "_nnz" #M "_t" #T "_vm" #I,                                \
             launch_solver<R, C, M, T, B, I, false>, occupancy_solver<R, C, M, T, B, I, false>               \
     }
-// row-split variants: rows spread over the team's warps, sparse rows streamed from global memory
+// row-split variants: rows spread over the team's warps, sparse rows from a table in shared (or global) memory;
+// the per-lane `ell` registers hold {table offset, row length} of each of the lane's three chunks
 #define QSIM_VARIANT_RS(T, I)                                                                             \
     {                                                                                                     \
-        3, 1, 1, T, 1, I, 1, "tsit5_rowsplit_r3c1_t" #T "_vm" #I, launch_solver<3, 1, 1, T, 1, I, true>,      \
-            occupancy_solver<3, 1, 1, T, 1, I, true>                                                      \
+        3, 1, 2, T, 1, I, 1, "tsit5_rowsplit_r3c1_t" #T "_vm" #I, launch_solver<3, 1, 2, T, 1, I, true>,      \
+            occupancy_solver<3, 1, 2, T, 1, I, true>                                                      \
     }
 
 #ifdef QSIM_FAST_BUILD

@@ -80,6 +80,16 @@ struct LaunchArgs {
     int ell_rows;
     const int *rs_perm;
     const int *rs_len;
+    // Row-split tables, compact form: chunk c owns table rows [rs_off[c], rs_off[c] + rs_len[c]) of 32 entries each
+    // (entry j of the chunk's lane l at ell_packed[(rs_off[c] + j) * 32 + l]); every chunk is padded with zero-slot
+    // entries to 1 + an even number of off-diagonal entries plus two more rows, so the pairwise-pipelined gather may
+    // read one pair ahead.  ell_in_smem: the table (ell_bytes) is staged in the CTA-wide shared region at off_ell.
+    const int *rs_off;
+    const int *rs_pos;       // position of sorted row q inside the stage buffer (chosen on the host against bank conflicts)
+    int ell_in_smem, off_ell, ell_bytes;
+    // streamed row-split teams: the next column's u and k1 are prefetched from the scratch into shared memory by
+    // cp.async.bulk (two buffers of 2 * n * 16 bytes at off_pf inside the team region, completion on mbarriers)
+    int rs_prefetch, off_pf;
     const uint8_t *slot_imag;    // value mode 4: per slot, 1 when the slot is purely imaginary (0: purely real)
     int team_warps, teams_per_cta, n_batches, groups, streamed;
     int y_row_stride, y_grp_stride;  // stage-buffer layout in 16-byte units (chosen on the host to avoid bank conflicts)
@@ -169,6 +179,43 @@ __device__ __forceinline__ int ldsi(uint32_t addr) {
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+
+__device__ __forceinline__ uint32_t ldsu(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// ---- mbarriers and bulk copies (row-split teams) ----------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+    for (int it = 0;; it++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (it > (1 << 22)) __trap();  // a lost arrival must fail the launch, not hang the device
+    }
+}
+// global -> shared bulk copy (TMA), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+// generic-proxy writes (st.global / st.shared) made visible to later async-proxy (bulk copy) reads
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // Branch-free reciprocal square root / reciprocal: hardware seed (MUFU.RSQ64H / MUFU.RCP64H, ~2^-22) and two
 // Newton steps (full double precision up to an ulp or two).  The library versions carry special-case
@@ -289,6 +336,10 @@ struct Geo {
     double stage_c;                             // kStageC[lane] for lanes 0..4 (fast_tables), set once per thread
     int blk_row;                                // blocked variants: this lane's block row
     uint32_t v_stride;                          // bytes between value tables
+    // row-split teams: row table in shared memory (0: read it from global memory), prefetch buffers (0: none),
+    // mbarriers {stage exchange, prefetch buffer 0, prefetch buffer 1}; phase bits of those three barriers
+    uint32_t sm_ell, sm_pf, sm_mbar;
+    mutable uint32_t ph_stage, ph_pf;
 };
 
 // Stops the compiler from hoisting per-entry address arithmetic out of the step loop (register pressure).
@@ -619,9 +670,12 @@ struct Kern {
 #pragma unroll
                 for (int c = 0; c < CPL; c++) sts2(yb + my_off[i] + 16 * c, y[i * CPL + c]);
             }
-        if (RS)
-            team_sync(a.team_warps, g.bar_id);
-        else
+        if (RS) {
+            // split barrier: announce this warp's part of the stage vector now, wait for the others' just before
+            // the gather (apply); the work in between (the next stage's partial combination) hides the latency
+            __syncwarp();
+            if (g.lane == 0) mbar_arrive(g.sm_mbar);
+        } else
             __syncwarp();
     }
 
@@ -688,7 +742,7 @@ struct Kern {
     // `hook` runs between the issue of a row's operand loads and their first use: independent work placed
     // there (the next stage's partial combination) executes under the shared-memory latency.
     template <typename Hook = NoHook>
-    static __device__ __forceinline__ void apply(const LaunchArgs &a, uint32_t Vs, uint32_t yb,
+    static __device__ __forceinline__ void apply(const LaunchArgs &a, const Geo &g, uint32_t Vs, uint32_t yb,
                                                  const uint32_t (&ell)[RPL][MAXNNZ], const double (&vstat)[NVS],
                                                  const int (&row_of)[RPL], const Vec &yreg, Vec &k, Hook hook = Hook()) {
         if (BLK) {
@@ -722,20 +776,50 @@ struct Kern {
             for (int i = 0; i < RPL; i++) k[i] = acc[i];
             return;
         }
+        if (RS) {
+            // independent work first, then wait for every warp's part of the stage vector (put_stage arrived)
+            hook();
+            mbar_wait(g.sm_mbar, g.ph_stage);
+            g.ph_stage ^= 1u;
+        }
 #pragma unroll
         for (int i = 0; i < RPL; i++) {
             double2 acc[CPL];
 #pragma unroll
             for (int c = 0; c < CPL; c++) acc[c] = make_double2(0.0, 0.0);
             if (RS) {
-                // rows come from global memory (translated on the host); rows past n read row n-1's
-                // entries with the zero slot substituted by the host-side table's padding row
-                const uint32_t *er = a.ell_packed + (ell[i][0] & 0xFFFFu);
-                const int nnz = (int)(ell[i][0] >> 16), stride = a.ell_rows;  // this (warp, slot) group's row length
-                if (i == RPL - 1) hook();
-                if (nnz > 0) mac(a, Vs, yb, __ldg(er), true, &yreg[i * CPL], acc);
+                // Row table (shared memory, or global memory when it does not fit): entry j of this lane's row in
+                // chunk (slot i, warp) sits 128 bytes after entry j - 1.  The chunk's rows all have `nnz` entries
+                // (padded on the host to 1 + an even count, plus one spare pair), so the off-diagonal entries are
+                // taken two at a time with the next pair's table words requested ahead of the multiply-adds.
+                const int nnz = (int)ell[i][MAXNNZ > 1 ? 1 : 0];
+                if (g.sm_ell) {
+                    const uint32_t tb = g.sm_ell + ell[i][0];
+                    uint32_t ea = ldsu(tb + 128u), eb = ldsu(tb + 256u);
+                    mac(a, Vs, yb, ldsu(tb), true, &yreg[i * CPL], acc);
+                    for (int j = 1; j < nnz; j += 2) {
+                        const uint32_t na = ldsu(tb + 128u * (uint32_t)(j + 2)), nb = ldsu(tb + 128u * (uint32_t)(j + 3));
+                        const double2 va = ldv(Vs, ea), vb = ldv(Vs, eb);
+                        double2 ya[CPL], yb2[CPL];
+#pragma unroll
+                        for (int c = 0; c < CPL; c++) {
+                            ya[c] = lds2(yb + (ea & 0xFFFFu) + 16 * c);
+                            yb2[c] = lds2(yb + (eb & 0xFFFFu) + 16 * c);
+                        }
+#pragma unroll
+                        for (int c = 0; c < CPL; c++) {
+                            cfma(acc[c], va, ea, ya[c]);
+                            cfma(acc[c], vb, eb, yb2[c]);
+                        }
+                        ea = na;
+                        eb = nb;
+                    }
+                } else {
+                    const uint32_t *er = a.ell_packed + (ell[i][0] >> 2);
+                    mac(a, Vs, yb, __ldg(er), true, &yreg[i * CPL], acc);
 #pragma unroll 4
-                for (int j = 1; j < nnz; j++) mac(a, Vs, yb, __ldg(er + (size_t)j * stride), false, &yreg[i * CPL], acc);
+                    for (int j = 1; j < nnz; j++) mac(a, Vs, yb, __ldg(er + 32 * j), false, &yreg[i * CPL], acc);
+                }
             } else {
                 // no per-entry branch (short rows are padded with the zero slot).  Operands are requested in
                 // chunks of up to four off-diagonal entries, all loads of a chunk ahead of its multiply-adds, so a
@@ -897,8 +981,10 @@ struct Kern {
     // ---- one trajectory -----------------------------------------------------------------
     static __device__ __forceinline__ void run(const LaunchArgs &a, const Geo &g, const double *smem_gen,
                                                const uint32_t (&ell)[RPL][MAXNNZ], const uint32_t (&my_off)[RPL],
-                                               const int (&row_of)[RPL], const bool (&row_ok)[RPL], double2 *sc_base,
-                                               long long traj) {
+                                               const int (&row_of)[RPL], const bool (&row_ok)[RPL],
+                                               const int (&sidx)[RPL], double2 *sc_base, long long traj) {
+        // sidx: this lane's row indices inside the scratch buffers (row-split teams keep the scratch in their
+        // sorted row order so that a warp's accesses are contiguous; everyone else uses the state row)
         const int n = a.g.n;
         const double *ts = a.ts + (size_t)traj * a.ts_stride;
         const double *prow = a.params + (size_t)traj * a.n_params;
@@ -908,6 +994,32 @@ struct Kern {
         const uint32_t yb0 = g.sm_y0, yb1 = g.sm_y1;
         const size_t sbuf = (size_t)a.n_batches * g.cpb * n;
         double2 *const sc_u0 = sc_base, *const sc_k0 = sc_base + sbuf;
+        // Streamed row-split teams: column b's u and k1 are fetched by bulk copies into one of two shared-memory
+        // buffers while column b - 1 is being integrated (issued by one thread, completion on the buffer's mbarrier).
+        const uint32_t nb16 = 16u * (uint32_t)n;
+        auto pf_issue = [&](int b, const double2 *su, const double2 *sk) {
+            const uint32_t buf = g.sm_pf + (uint32_t)(b & 1) * 2u * nb16, mb = g.sm_mbar + 8u * (uint32_t)(1 + (b & 1));
+            mbar_expect_tx(mb, 2u * nb16);
+            bulk_g2s(buf, su + (size_t)b * n, nb16, mb);
+            bulk_g2s(buf + nb16, sk + (size_t)b * n, nb16, mb);
+        };
+        // u and k1 of batch b (RS && prefetch: from the shared-memory buffer; otherwise straight from the scratch)
+        auto fetch_uk = [&](int b, int col0, const double2 *su, const double2 *sk, Vec &uu, Vec &kk) {
+            if (RS && g.sm_pf) {
+                if (g.team_thread == 0 && b + 1 < a.n_batches) pf_issue(b + 1, su, sk);
+                const uint32_t buf = g.sm_pf + (uint32_t)(b & 1) * 2u * nb16;
+                mbar_wait(g.sm_mbar + 8u * (uint32_t)(1 + (b & 1)), (g.ph_pf >> (b & 1)) & 1u);
+                g.ph_pf ^= 1u << (b & 1);
+#pragma unroll
+                for (int i = 0; i < RPL; i++) {
+                    uu[i] = row_ok[i] ? lds2(buf + 16u * (uint32_t)sidx[i]) : make_double2(0.0, 0.0);
+                    kk[i] = row_ok[i] ? lds2(buf + nb16 + 16u * (uint32_t)sidx[i]) : make_double2(0.0, 0.0);
+                }
+            } else {
+                load_batch(su, n, col0, sidx, row_ok, uu);
+                load_batch(sk, n, col0, sidx, row_ok, kk);
+            }
+        };
 
         qsim_traj_stats st;
         st.retcode = QSIM_RET_SUCCESS;
@@ -959,10 +1071,10 @@ struct Kern {
                 initial_state(a, traj, col0, row_of, row_ok, u);
                 for (int ks = 0; ks < nsave; ks++) write_out(a, traj, ks, col0, row_of, row_ok, u);
                 put_stage(a, g, u, yb0, my_off, row_ok);
-                apply(a, V0, yb0, ell, vstat, row_of, u, k1);
+                apply(a, g, V0, yb0, ell, vstat, row_of, u, k1);
                 if (a.streamed) {
-                    store_batch(sc_u0, n, col0, row_of, row_ok, u);
-                    store_batch(sc_k0, n, col0, row_of, row_ok, k1);
+                    store_batch(sc_u0, n, col0, sidx, row_ok, u);
+                    store_batch(sc_k0, n, col0, sidx, row_ok, k1);
                 }
 #pragma unroll
                 for (int e = 0; e < E; e++) {
@@ -972,22 +1084,24 @@ struct Kern {
                     acc2[1] += fx * fx + fy * fy;
                 }
             }
+            if (RS && g.sm_pf) fence_async_proxy();  // scratch stores above -> bulk-copy reads below
             team_sum<2>(acc2, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
             const double d0 = sqrt(acc2[0] / ntot), d1 = sqrt(acc2[1] / ntot);
             double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
             dt0 = fmin(dt0, dtmax);
             compute_tables<1>(a, g, smem_gen, t0 + dt0, 0.0, false, 1);  // table 1 <- t0 + dt0 (table 0 keeps t0)
             double acc1[1] = {0.0};
+            if (RS && g.sm_pf && a.streamed) {
+                if (a.team_warps == 1) __syncwarp();
+                if (g.team_thread == 0) pf_issue(0, sc_u0, sc_k0);
+            }
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                 const int col0 = b * g.cpb + g.colofs;
-                if (a.streamed) {
-                    load_batch(sc_u0, n, col0, row_of, row_ok, u);
-                    load_batch(sc_k0, n, col0, row_of, row_ok, k1);
-                }
+                if (a.streamed) fetch_uk(b, col0, sc_u0, sc_k0, u, k1);
 #pragma unroll
                 for (int e = 0; e < E; e++) tmp[e] = make_double2(u[e].x + dt0 * k1[e].x, u[e].y + dt0 * k1[e].y);
                 put_stage(a, g, tmp, yb1, my_off, row_ok);
-                apply(a, V1, yb1, ell, vstat, row_of, tmp, k2);
+                apply(a, g, V1, yb1, ell, vstat, row_of, tmp, k2);
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     const double sk = a.abstol + sqrt(u[e].x * u[e].x + u[e].y * u[e].y) * a.reltol;
@@ -1085,12 +1199,14 @@ struct Kern {
 
                 double err[1] = {0.0};
                 QSIM_TICK(3)
+                if (RS && g.sm_pf && a.streamed) {
+                    if (a.team_warps == 1) __syncwarp();  // (larger teams passed the error-norm barrier)
+                    if (g.team_thread == 0) pf_issue(0, sc_u0 + (size_t)(2 * cur) * sbuf, sc_k0 + (size_t)(2 * cur) * sbuf);
+                }
                 for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                     const int col0 = b * g.cpb + g.colofs;
-                    if (a.streamed) {
-                        load_batch(sc_u0 + (size_t)(2 * cur) * sbuf, n, col0, row_of, row_ok, u);
-                        load_batch(sc_k0 + (size_t)(2 * cur) * sbuf, n, col0, row_of, row_ok, k1);
-                    }
+                    if (a.streamed)
+                        fetch_uk(b, col0, sc_u0 + (size_t)(2 * cur) * sbuf, sc_k0 + (size_t)(2 * cur) * sbuf, u, k1);
                     Vec part;  // partial combination of the next stage, formed while the current stage's operands load
 #pragma unroll
                     for (int e = 0; e < E; e++) {
@@ -1099,7 +1215,7 @@ struct Kern {
                     }
                     put_stage(a, g, tmp, yb0, my_off, row_ok);
                     QSIM_TICK(4)
-                    apply(a, V0, yb0, ell, vstat, row_of, tmp, k2, [&] {
+                    apply(a, g, V0, yb0, ell, vstat, row_of, tmp, k2, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++) part[e] = make_double2(A31 * k1[e].x, A31 * k1[e].y);
                     });
@@ -1110,7 +1226,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
-                    apply(a, V1, yb1, ell, vstat, row_of, tmp, k3, [&] {
+                    apply(a, g, V1, yb1, ell, vstat, row_of, tmp, k3, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++)
                             part[e] = make_double2(fma(A42, k2[e].x, A41 * k1[e].x), fma(A42, k2[e].y, A41 * k1[e].y));
@@ -1121,7 +1237,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb0, my_off, row_ok);
-                    apply(a, V2, yb0, ell, vstat, row_of, tmp, k4, [&] {
+                    apply(a, g, V2, yb0, ell, vstat, row_of, tmp, k4, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++)
                             part[e] = make_double2(fma(A53, k3[e].x, fma(A52, k2[e].x, A51 * k1[e].x)),
@@ -1133,7 +1249,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
-                    apply(a, V3, yb1, ell, vstat, row_of, tmp, k5, [&] {
+                    apply(a, g, V3, yb1, ell, vstat, row_of, tmp, k5, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++)
                             part[e] = make_double2(
@@ -1146,7 +1262,7 @@ struct Kern {
                         tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                     }
                     put_stage(a, g, tmp, yb0, my_off, row_ok);
-                    apply(a, V4, yb0, ell, vstat, row_of, tmp, k6, [&] {
+                    apply(a, g, V4, yb0, ell, vstat, row_of, tmp, k6, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++)
                             part[e] = make_double2(
@@ -1161,7 +1277,7 @@ struct Kern {
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
                     // while stage 7's operands load: the k1..k6 part of the error combination
                     double ex[E], ey[E];
-                    apply(a, V4, yb1, ell, vstat, row_of, tmp, k7, [&] {
+                    apply(a, g, V4, yb1, ell, vstat, row_of, tmp, k7, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++) {
                             ex[e] = fma(BT6, k6[e].x, fma(BT5, k5[e].x, fma(BT4, k4[e].x, fma(BT3, k3[e].x, fma(BT2, k2[e].x, BT1 * k1[e].x)))));
@@ -1214,8 +1330,8 @@ struct Kern {
                     if (a.streamed) {
                         // tentative: the next buffers are adopted only if the step is accepted; dense-output
                         // slots are rewritten by the retried / a later step if it is not
-                        store_batch(sc_u0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, row_of, row_ok, tmp);
-                        store_batch(sc_k0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, row_of, row_ok, k7);
+                        store_batch(sc_u0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, sidx, row_ok, tmp);
+                        store_batch(sc_k0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, sidx, row_ok, k7);
                         if (nsave_hi > nsave)
                             save_points(a, traj, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok, u, k1,
                                         k2, k3, k4, k5, k6, k7, tmp);
@@ -1223,6 +1339,7 @@ struct Kern {
                 }
                 n_attempt++;
                 QSIM_TICK(7)
+                if (RS && g.sm_pf && a.streamed) fence_async_proxy();  // this step's scratch stores -> next step's bulk reads
                 err[0] = team_sum_alt(err[0], g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id, red_par);
                 QSIM_TICK(8)
                 // EEst^2 = mean |r_i|^2.  PI controller (stepsize_controller! / step_accept_controller! /
@@ -1363,6 +1480,11 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
               16u * g_idx * a.y_grp_stride;
     g.sm_y1 = g.sm_y0 + ybytes;
     g.sm_ctl = g.sm_red + 8u * (a.team_warps * 4 + 8) + (RS ? 1 : a.team_warps) * 2 * ybytes + 128u * g.warp_in_team;
+    g.sm_ell = (RS && a.ell_in_smem) ? sbase + a.off_ell : 0u;
+    g.sm_mbar = tbase + a.off_pf;                                   // three mbarriers (32 bytes reserved)
+    g.sm_pf = (RS && a.rs_prefetch) ? g.sm_mbar + 32u : 0u;        // two buffers of 2 * n * 16 bytes
+    g.ph_stage = 0u;
+    g.ph_pf = 0u;
 
     // ---- CTA-wide constants: series tables and the dynamic slots' pair lists ----
     {
@@ -1377,6 +1499,17 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
             dptr[a.g.n_dyn_slots + 1 + i] = a.g.pair_chan[i];
             sts2(g.sm_dw + 16 * i, a.g.pair_w[i]);
         }
+        if (RS) {
+            if (a.ell_in_smem)
+                for (int i = threadIdx.x; i < a.ell_bytes / 4; i += blockDim.x)
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + a.off_ell + 4u * i), "r"(a.ell_packed[i]) : "memory");
+            if (g.team_thread == 0) {
+                mbar_init(g.sm_mbar, (uint32_t)a.team_warps);  // stage exchange: one arrival per warp
+                mbar_init(g.sm_mbar + 8u, 1u);                 // prefetch buffers: the issuing thread + transaction bytes
+                mbar_init(g.sm_mbar + 16u, 1u);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+        }
         // the zero slot of every table (padding entries of short rows read it)
         for (int s = g.team_thread; s < 5; s += g.team_threads)
             if (K::MX) {
@@ -1390,25 +1523,30 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     __syncthreads();
 
     // ---- per-lane sparse rows, kept in registers for the whole kernel ----
-    int row_of[RPL];
+    int row_of[RPL], sidx[RPL];
     bool row_ok[RPL];
     uint32_t my_off[RPL];
     uint32_t ell[RPL][MAXNNZ];
 #pragma unroll
     for (int i = 0; i < RPL; i++) {
         if (RS) {
-            // sorted row q of chunk (slot i, this warp); the stage buffer and the packed table are indexed by q,
-            // initial state / results / scratch by the state row rs_perm[q]
+            // sorted row q of chunk (slot i, this warp); the stage buffer, the scratch and the packed table are
+            // indexed by q, initial state and results by the state row rs_perm[q].  Lanes past the last row read
+            // the table's zero-slot padding (the host fills the whole chunk).
             const int chunk = i * a.team_warps + g.warp_in_team;
             const int q = chunk * 32 + g.lane;
             row_ok[i] = q < n;
             row_of[i] = row_ok[i] ? __ldg(a.rs_perm + q) : 0;
-            my_off[i] = 16u * ((q < n ? q : n - 1) * a.y_row_stride);
-            ell[i][0] = (uint32_t)(row_ok[i] ? q : n + (q - n) % 8) | ((uint32_t)__ldg(a.rs_len + chunk) << 16);
+            sidx[i] = row_ok[i] ? q : 0;
+            my_off[i] = 16u * (uint32_t)(__ldg(a.rs_pos + (q < n ? q : n - 1)) * a.y_row_stride);
+            ell[i][0] = 4u * (32u * (uint32_t)__ldg(a.rs_off + chunk) + (uint32_t)g.lane);  // byte offset of entry 0
+            ell[i][MAXNNZ - 1] = (uint32_t)__ldg(a.rs_len + chunk);                          // entries per row (0: no rows)
             continue;
         }
+        sidx[i] = 0;
         row_of[i] = K::BLK ? g.blk_row * RPL + i : row0 + 32 * i;
         row_ok[i] = lane_active && row_of[i] < n;
+        sidx[i] = row_of[i];
         const int row_eff = row_of[i] < n ? row_of[i] : n - 1;
         my_off[i] = 16u * (row_eff * a.y_row_stride);
 #pragma unroll
@@ -1439,7 +1577,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         asm volatile("ld.shared.u64 %0, [%1];" : "=l"(traj) : "r"(wslot));
         team_sync(a.team_warps, g.bar_id);
         if (traj >= (unsigned long long)a.n_traj) break;
-        K::run(a, g, smem, ell, my_off, row_of, row_ok, sc_base, (long long)traj);
+        K::run(a, g, smem, ell, my_off, row_of, row_ok, sidx, sc_base, (long long)traj);
     }
 }
 
