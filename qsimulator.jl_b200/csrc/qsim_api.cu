@@ -97,6 +97,8 @@ struct qsim_problem::DeviceCopy {
     };
     std::vector<Packed> packed;
     uint8_t *slot_imag = nullptr;    // value mode 4
+    uint32_t *split_ell = nullptr;   // split rows: row table with the helper rows appended, per-lane info
+    uint8_t *split_info = nullptr;
     uint32_t *blk_ell = nullptr;     // blocked kernels: row table and value slot ids (built by make_plan)
     uint16_t *blk_slot = nullptr;
     ~DeviceCopy() { free_all(); }  // the owning device must be current
@@ -111,6 +113,10 @@ struct qsim_problem::DeviceCopy {
         packed.clear();
         cudaFree(slot_imag);
         slot_imag = nullptr;
+        cudaFree(split_ell);
+        cudaFree(split_info);
+        split_ell = nullptr;
+        split_info = nullptr;
         cudaFree(blk_ell);
         cudaFree(blk_slot);
         blk_ell = nullptr;
@@ -452,6 +458,11 @@ struct Plan {
     std::vector<uint32_t> rs_table;
     std::vector<int> rs_perm, rs_off, rs_len, rs_pos;
     int ell_in_smem = 0, off_ell = 0, ell_bytes = 0, rs_prefetch = 0, off_pf = 0;
+    // split rows (LaunchArgs::split_info): virtual row table [split_nnz][split_nv], per-lane info
+    int split_nv = 0, split_nnz = 0;
+    std::vector<uint32_t> split_ell;
+    std::vector<uint8_t> split_info;
+    int cu = 0, rpl = 1;               // column-per-lane mapping (LaunchArgs::cu_map); rows per lane of the variant
     std::vector<uint8_t> slot_imag;    // value mode 4: per slot, 1 = purely imaginary, 0 = purely real
     // blocked variant (value mode 3): block rows, row table [1 + max blocks][n] and value slot ids
     int blk_rows = 0, blk_nnz = 0;
@@ -513,12 +524,13 @@ static bool build_blocked(const Generator &g, int R, int capacity, Plan &pl) {
 // blk_rows > 0: blocked variants (lane = block row + blk_rows * group, rows rpl*block_row + i) with their own
 // row table `ell` of `max_nnz` entries per row.
 static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S, int Cg, int blk_rows = 0,
-                        const uint32_t *ell = nullptr, int max_nnz = 0) {
+                        const uint32_t *ell = nullptr, int max_nnz = 0, int table_rows = 0) {
     const int n = g.n;
     if (!ell) {
         ell = g.ell.data();
         max_nnz = g.max_nnz;
     }
+    if (table_rows <= 0) table_rows = n;  // (split rows: the table also holds the helper lanes' rows n..table_rows-1)
     long cost = 0;
     for (int i = 0; i < rpl; i++) {
         for (int j = 0; j <= max_nnz; j++) {  // j == max_nnz: the lane's own store
@@ -539,17 +551,18 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
                         gi = le / n;
                         r = le % n;
                     }
-                    if (r >= n) {
+                    const bool helper = active && r >= n && r < table_rows;
+                    if (r >= n && !helper) {
                         active = false;
                         r = n - 1;
                     }
                     int src = r;
                     if (j == max_nnz) {
-                        if (!active) continue;  // inactive lanes do not store
+                        if (!active || helper) continue;  // inactive lanes and helpers do not store
                     } else if (j == 0) {
                         continue;  // diagonal operand comes from registers
                     } else {
-                        src = (int)(ell[(size_t)j * n + r] & 0xFFFFu);
+                        src = (int)(ell[(size_t)j * table_rows + r] & 0xFFFFu);
                     }
                     const int unit = src * S + gi * Cg;
                     const int b = unit & 7;
@@ -566,11 +579,67 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
     return cost;
 }
 
+// Split rows: with one row per lane and fewer than 32 rows, cut the longest rows in two and give the second half to
+// an idle lane.  Chooses the smallest row length M such that every row longer than M can get a helper (at most
+// 32 - n of them, each row at most 2 M long), and rebuilds the row table with n + helpers rows and 1 + M entries
+// per row (diagonal first; helpers carry a zero diagonal).  Returns false when nothing is gained.
+static bool build_split_rows(const Generator &g, Plan &pl) {
+    const int n = g.n, spare = 32 - n;
+    if (spare <= 0 || g.max_nnz < 3) return false;
+    std::vector<std::vector<uint32_t>> off((size_t)n);
+    int longest = 0;
+    for (int r = 0; r < n; r++) {
+        for (int j = 1; j < g.max_nnz; j++) {
+            const uint32_t e = g.ell[(size_t)j * n + r];
+            if ((e >> 16) != 0xFFFFu) off[(size_t)r].push_back(e);
+        }
+        longest = std::max(longest, (int)off[(size_t)r].size());
+    }
+    int M = longest;
+    for (int m = (longest + 1) / 2; m < longest; m++) {
+        int need = 0;
+        for (int r = 0; r < n; r++) need += (int)off[(size_t)r].size() > m ? 1 : 0;
+        if (need <= spare) {
+            M = m;
+            break;
+        }
+    }
+    if (M >= longest) return false;
+    std::vector<int> helper_of((size_t)n, -1);
+    int nv = n;
+    for (int r = 0; r < n; r++)
+        if ((int)off[(size_t)r].size() > M) helper_of[(size_t)r] = nv++;
+    pl.split_nv = nv;
+    pl.split_nnz = 1 + M;
+    pl.split_ell.assign((size_t)pl.split_nnz * nv, 0);
+    pl.split_info.assign(32, 0);
+    for (int l = 0; l < 32; l++) pl.split_info[(size_t)l] = (uint8_t)l;
+    for (int v = 0; v < nv; v++) {
+        // padding: own (owner's) row, zero slot
+        for (int j = 0; j < pl.split_nnz; j++) pl.split_ell[(size_t)j * nv + v] = (uint32_t)std::min(v, n - 1) | (0xFFFFu << 16);
+    }
+    for (int r = 0; r < n; r++) {
+        pl.split_ell[(size_t)r] = g.ell[(size_t)r];  // diagonal
+        const auto &o = off[(size_t)r];
+        const int h = helper_of[(size_t)r];
+        const int first = h >= 0 ? ((int)o.size() + 1) / 2 : (int)o.size();
+        for (int j = 0; j < first; j++) pl.split_ell[(size_t)(1 + j) * nv + r] = o[(size_t)j];
+        if (h >= 0) {
+            for (int j = first; j < (int)o.size(); j++) pl.split_ell[(size_t)(1 + j - first) * nv + h] = o[(size_t)j];
+            for (int j = 0; j < pl.split_nnz; j++)   // helper's padding reads the owner's row (broadcast-friendly)
+                if ((pl.split_ell[(size_t)j * nv + h] >> 16) == 0xFFFFu) pl.split_ell[(size_t)j * nv + h] = (uint32_t)r | (0xFFFFu << 16);
+            pl.split_info[(size_t)r] = (uint8_t)(h | 64);
+            pl.split_info[(size_t)h] = (uint8_t)(r | 32);
+        }
+    }
+    return true;
+}
+
 static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int vm, int rs) {
     const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c3_t128, variants_r1c3_t256,
                                               variants_r1c4_t256, variants_r2c1_t128,
                                               variants_r2c2_t256, variants_r3c1_t128, variants_r3c1_t256,
-                                              variants_rowsplit, variants_blocked};
+                                              variants_rowsplit, variants_colperlane, variants_blocked};
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
         int cnt = 0;
@@ -599,12 +668,62 @@ static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int bloc
 // quarter warp gathers together fall into distinct bank groups (rs_pos[q] = position of sorted row q; the stage
 // vector is the only thing stored in that order -- scratch, prefetch buffers and the table itself stay in sorted order).
 static void build_rowsplit_table(const Generator &g, Plan &pl, bool full) {
-    const int n = g.n, n_chunks = 3 * pl.team_warps;
+    const int n = g.n, n_chunks = pl.rpl * pl.team_warps;
     const uint32_t vb = pl.vm >= 1 ? 8u : 16u;
     std::vector<std::vector<uint32_t>> compact;
     std::vector<int> perm;
     rowsplit_rows(g, compact, perm);
-    pl.rs_perm = perm;
+    if (pl.cu) {
+        // Column-per-lane mapping: chunk (slot, warp) is ONE row, the same in all 32 lanes (the lane picks the
+        // column).  Rows go to warps longest first, each to the warp with the fewest entries so far that still has a
+        // free slot, so the warps of a team carry (nearly) equal work; within a warp the slots are filled in that
+        // order.  The stage buffer keeps the state's own row order: row r at 16 * r * y_row_stride (+ 16 * column).
+        const int W = pl.team_warps;
+        std::vector<int> load((size_t)W, 0), used((size_t)W, 0), row_of_chunk((size_t)n_chunks, -1);
+        for (int q = 0; q < n; q++) {
+            int best = -1;
+            for (int w = 0; w < W; w++)
+                if (used[(size_t)w] < pl.rpl && (best < 0 || load[(size_t)w] < load[(size_t)best])) best = w;
+            row_of_chunk[(size_t)(used[(size_t)best] * W + best)] = perm[(size_t)q];
+            used[(size_t)best]++;
+            load[(size_t)best] += (int)compact[(size_t)perm[(size_t)q]].size();
+        }
+        pl.rs_off.assign((size_t)n_chunks, 0);
+        pl.rs_len.assign((size_t)n_chunks, 1);
+        size_t total = 0;
+        for (int c = 0; c < n_chunks; c++) {
+            const int longest = row_of_chunk[(size_t)c] >= 0 ? (int)compact[(size_t)row_of_chunk[(size_t)c]].size() : 1;
+            pl.rs_off[(size_t)c] = (int)(total / 32);
+            pl.rs_len[(size_t)c] = 1 + 2 * (longest / 2);
+            total += (size_t)32 * (pl.rs_len[(size_t)c] + 2);
+        }
+        pl.ell_bytes = (int)(total * sizeof(uint32_t));
+        if (!full) return;
+        pl.rs_perm.assign((size_t)n_chunks * 32, -1);
+        pl.rs_pos.assign((size_t)n_chunks * 32, 0);
+        const uint32_t zero = (vb * (uint32_t)g.n_slots) << 16;   // row 0, zero slot
+        pl.rs_table.assign(total, zero);
+        for (int c = 0; c < n_chunks; c++) {
+            const int r = row_of_chunk[(size_t)c];
+            if (r < 0) continue;
+            uint32_t *tab = pl.rs_table.data() + (size_t)32 * pl.rs_off[(size_t)c];
+            const auto &row = compact[(size_t)r];
+            for (int l = 0; l < 32; l++) {
+                pl.rs_perm[(size_t)c * 32 + l] = r;
+                pl.rs_pos[(size_t)c * 32 + l] = r;
+                for (size_t j = 0; j < row.size(); j++) {
+                    const uint32_t sl = (row[j] >> 16) == 0xFFFFu ? (uint32_t)g.n_slots : (row[j] >> 16);
+                    uint32_t e = (16u * (row[j] & 0xFFFFu) * (uint32_t)pl.y_row_stride) | ((vb * sl) << 16);
+                    if (pl.vm == 4 && j > 0 && sl < (uint32_t)g.n_slots && pl.slot_imag[sl])
+                        e = (e + ((8u * (uint32_t)pl.nvp) << 16)) | 0x80000000u;
+                    tab[j * 32 + (size_t)l] = e;
+                }
+            }
+        }
+        return;
+    }
+    pl.rs_perm.assign((size_t)n_chunks * 32, -1);
+    for (int q = 0; q < n; q++) pl.rs_perm[(size_t)q] = perm[(size_t)q];
     pl.rs_off.assign((size_t)n_chunks, 0);
     pl.rs_len.assign((size_t)n_chunks, 1);
     size_t total = 0;
@@ -641,7 +760,7 @@ static void build_rowsplit_table(const Generator &g, Plan &pl, bool full) {
             v.pop_back();
         }
     }
-    pl.rs_pos.resize((size_t)n);
+    pl.rs_pos.assign((size_t)n_chunks * 32, pos[(size_t)perm[(size_t)n - 1]]);
     for (int q = 0; q < n; q++) pl.rs_pos[(size_t)q] = pos[(size_t)perm[(size_t)q]];
     const uint32_t zero = (16u * (uint32_t)pos[(size_t)perm[(size_t)n - 1]] * (uint32_t)pl.y_row_stride) | ((vb * (uint32_t)g.n_slots) << 16);
     pl.rs_table.assign(total, zero);
@@ -675,6 +794,17 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         rpl = 1;
         pl.groups = std::min(32 / n, pl.ncols);
         cpl = (pl.ncols + pl.groups - 1) / pl.groups > 1 ? 3 : 1;
+    } else if (n <= 32 && pl.identity && std::getenv("QSIM_COLPERLANE")) {
+        // Opt-in experiment (QSIM_COLPERLANE=1) for propagators with 17..32 rows: column-per-lane mapping of the
+        // row-split machinery -- lane = column, four whole rows per warp, ceil(n/4) <= 8 warps, warp-uniform sparse
+        // rows (LaunchArgs::cu_map).  Parity-green but measured 2x slower than the row-per-lane kernel on cfg3
+        // (d = 27): half the shared-memory wavefronts, yet with one 7-warp team per SM the dynamic row loops and the
+        // seven team-wide stage exchanges per step leave the step latency-bound (instruction-fetch stalls 38 %).
+        rpl = 4;
+        cpl = 1;
+        pl.rowsplit = 1;
+        pl.cu = 1;
+        pl.groups = 32;
     } else if (n <= 32) {
         // three columns per lane up to 24 rows, four above: at most eight warps per trajectory
         rpl = 1;
@@ -724,7 +854,19 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
             }
         }
     }
-    if (pl.rowsplit) {
+    // Split rows (one row per lane, spare lanes): halves the longest rows; see build_split_rows.  Opt-in
+    // (QSIM_SPLIT_ROWS=1): parity-green, but on cfg3 (d = 27: rows of 1 + 4 instead of 1 + 8 entries) the saved operand
+    // loads are paid back by the per-stage shuffles of the helpers' partial sums and by bank conflicts of the compacted
+    // rows (profiles/r2_cfg3_experiments.txt: 953 ms against 937 ms for 1184 x 50 ns).
+    bool split = false;
+    if (!pl.rowsplit && !blocked && rpl == 1 && pl.groups == 1 && n < 32 && std::getenv("QSIM_SPLIT_ROWS"))
+        split = build_split_rows(g, pl);
+    const int eff_nnz = split ? pl.split_nnz : g.max_nnz;
+    pl.rpl = rpl;
+    if (pl.cu) {
+        pl.team_warps = (n + 3) / 4;
+        pl.streamed = 0;   // all n <= 32 columns in one batch: the state never leaves registers
+    } else if (pl.rowsplit) {
         pl.team_warps = (n + 95) / 96;
         pl.streamed = pl.n_batches > 1 ? 1 : 0;
     } else if (pl.n_batches <= 8) {
@@ -755,25 +897,34 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
                 if (sl != 0xFFFFu && (int)sl < g.n_dyn_slots) static_off = false;
             }
         // (with four entries per lane the extra value registers would spill: stay in mode 1)
-        if (static_off && rpl * cpl <= 3 && find_variant(rpl, cpl, g.max_nnz, pl.block, 2, 0)) vm = 2;
+        if (static_off && rpl * cpl <= 3 && find_variant(rpl, cpl, eff_nnz, pl.block, 2, 0)) vm = 2;
     }
     if (vm == 0) {
         const bool mixed = generator_is_mixed(g, pl.slot_imag);
-        if (mixed && find_variant(rpl, cpl, g.max_nnz, pl.block, 4, pl.rowsplit)) vm = 4;
+        if (mixed && find_variant(rpl, cpl, eff_nnz, pl.block, 4, pl.rowsplit)) vm = 4;
     }
     pl.vm = vm;
-    pl.kv = find_variant(rpl, cpl, blocked ? pl.blk_nnz : g.max_nnz, pl.block, vm, pl.rowsplit);
+    pl.kv = find_variant(rpl, cpl, blocked ? pl.blk_nnz : eff_nnz, pl.block, vm, pl.rowsplit);
+    if (!pl.kv && split) {   // (no variant with the shorter capacity and this value mode: fall back to whole rows)
+        split = false;
+        pl.split_nv = 0;
+        pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block, vm, pl.rowsplit);
+    }
     if (!pl.kv)
         return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
                                               std::to_string(g.max_nnz) + ")");
     // stage-buffer layout: smallest-cost (row stride, group stride) near the dense one
-    {
+    if (pl.cu) {
+        pl.y_row_stride = 32;   // a row of the stage buffer = 32 columns of 16 bytes: every gather reads one aligned 512-byte row
+        pl.y_grp_stride = 1;
+    } else {
         long best = -1;
         for (int Cg = cpl; Cg <= cpl + 16; Cg++)
             for (int S = (pl.groups - 1) * Cg + cpl; S <= (pl.groups - 1) * Cg + cpl + 16; S++) {
                 if (pl.groups == 1 && Cg > cpl) break;  // no groups: only the row stride matters
                 if (16 * n * S > 65535) continue;
                 const long c = (blocked ? layout_cost(g, rpl, cpl, pl.groups, S, Cg, pl.blk_rows, pl.blk_ell.data(), pl.blk_nnz)
+                                : split ? layout_cost(g, rpl, cpl, pl.groups, S, Cg, 0, pl.split_ell.data(), pl.split_nnz, pl.split_nv)
                                         : layout_cost(g, rpl, cpl, pl.groups, S, Cg)) * 64 + S;  // ties: smaller buffer
                 if (best < 0 || c < best) {
                     best = c;
@@ -782,6 +933,9 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
                 }
             }
         if (best < 0) return fail(QSIM_ERR_UNSUPPORTED, "state too large for the packed 16-bit row offsets");
+        if (std::getenv("QSIM_DEBUG") && split)
+            std::fprintf(stderr, "[qsim] split rows: %d helper lanes, rows of 1 + %d entries instead of 1 + %d\n", pl.split_nv - n,
+                         pl.split_nnz - 1, g.max_nnz - 1);
         if (std::getenv("QSIM_DEBUG"))
             std::fprintf(stderr, "[qsim] n=%d groups=%d cpl=%d: stage layout S=%d Cg=%d wavefronts %ld (dense layout %ld)\n", n,
                          pl.groups, cpl, pl.y_row_stride, pl.y_grp_stride, best / 64,
@@ -1016,6 +1170,10 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
             CU(upload(&dc->blk_ell, pl.blk_ell));
             CU(upload(&dc->blk_slot, pl.blk_slot));
         }
+        if (pl.split_nv > 0 && !dc->split_ell) {
+            CU(upload(&dc->split_ell, pl.split_ell));
+            CU(upload(&dc->split_info, pl.split_info));
+        }
         d_slot_imag = dc->slot_imag;
         d_blk_ell = dc->blk_ell;
         d_blk_slot = dc->blk_slot;
@@ -1089,6 +1247,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.g.n_evals = (int)g.evals.size();
     a.g.n_dyn_pairs = pl.n_dyn_pairs;
     a.g.ell = dc->ell;
+    a.g.n_vrows = g.n;
     a.g.row_len = dc->row_len;
     a.g.slot_ptr = dc->slot_ptr;
     a.g.pair_chan = dc->pair_chan;
@@ -1116,6 +1275,12 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         a.blk_slot = d_blk_slot;
         a.n_blk_rows = pl.blk_rows;
     }
+    if (pl.split_nv > 0) {
+        a.g.ell = dc->split_ell;
+        a.g.max_nnz = pl.split_nnz;
+        a.g.n_vrows = pl.split_nv;
+        a.split_info = dc->split_info;
+    }
     a.ell_packed = pk.ell;
     a.ell_rows = g.n + 8;
     a.rs_perm = pk.perm;
@@ -1126,6 +1291,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.off_ell = pl.off_ell;
     a.ell_bytes = pl.ell_bytes;
     a.rs_prefetch = pl.rs_prefetch;
+    a.cu_map = pl.cu;
     a.off_pf = pl.off_pf;
     a.slot_imag = d_slot_imag;
     a.ncols = pl.ncols;

@@ -23,6 +23,7 @@ QSIM_DECLARE(variants_r2c1_t128)
 QSIM_DECLARE(variants_r2c2_t256)  // 33-64 level propagators always stream their columns through an 8-warp team
 QSIM_DECLARE(variants_r3c1_t128) QSIM_DECLARE(variants_r3c1_t256)
 QSIM_DECLARE(variants_rowsplit)
+QSIM_DECLARE(variants_colperlane)
 QSIM_DECLARE(variants_blocked)
 
 #define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \
@@ -36,6 +37,12 @@ QSIM_DECLARE(variants_blocked)
     {                                                                                                     \
         3, 1, 2, T, 1, I, 1, "tsit5_rowsplit_r3c1_t" #T "_vm" #I, launch_solver<3, 1, 2, T, 1, I, true>,      \
             occupancy_solver<3, 1, 2, T, 1, I, true>                                                      \
+    }
+// column-per-lane variants (propagators with 17..32 rows): four whole rows per warp, lane = column
+#define QSIM_VARIANT_CU(T, I)                                                                             \
+    {                                                                                                     \
+        4, 1, 2, T, 1, I, 1, "tsit5_colperlane_r4c1_t" #T "_vm" #I, launch_solver<4, 1, 2, T, 1, I, true>,    \
+            occupancy_solver<4, 1, 2, T, 1, I, true>                                                      \
     }
 
 #ifdef QSIM_FAST_BUILD

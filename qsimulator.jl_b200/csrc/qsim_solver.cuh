@@ -42,6 +42,7 @@ namespace qsim {
 
 struct DevGenerator {
     int n, max_nnz, n_slots, n_dyn_slots, n_chan, n_evals;
+    int n_vrows;              // rows of `ell` (>= n: rows n.. are the helper lanes' halves of split rows; see split_info)
     int n_dyn_pairs;          // pairs of the dynamic slots (a prefix of the pair arrays)
     const uint32_t *ell;      // [max_nnz][n]: src | slot << 16, 0xFFFFFFFF = padding
     const uint8_t *row_len;   // [n]
@@ -92,6 +93,16 @@ struct LaunchArgs {
     int rs_prefetch, off_pf;
     const uint8_t *slot_imag;    // value mode 4: per slot, 1 when the slot is purely imaginary (0: purely real)
     int team_warps, teams_per_cta, n_batches, groups, streamed;
+    // Column-per-lane mapping of the row-split kernels (propagators with 17..32 rows): lane = column, every warp
+    // holds a few whole rows (the same rows in all its lanes), so the sparse-row entries and values are
+    // warp-uniform (no padding to the longest row of a warp's lanes, broadcast loads) and the operand gather of a
+    // row reads 16 bytes per lane from consecutive addresses (no bank conflicts).
+    int cu_map;
+    // Split rows (one row per lane, fewer than 32 rows): the longest rows are cut in two and the second half is
+    // given to an otherwise idle lane (a "helper": virtual row >= n in g.ell), so a warp executes half the entries of
+    // its longest row; the helper's partial sums reach the row's owner by one shuffle per stage.
+    // split_info[lane]: bits 0-4 partner lane, bit 5 lane is a helper, bit 6 lane owns a split row.  nullptr: off.
+    const uint8_t *split_info;
     int y_row_stride, y_grp_stride;  // stage-buffer layout in 16-byte units (chosen on the host to avoid bank conflicts)
     int nvp, ncp;         // padded slot / channel counts (nvp > n_slots: slot n_slots is the zero slot)
     int common_bytes;     // CTA-wide shared region (series tables + Chebyshev block + dynamic pair lists)
@@ -340,6 +351,8 @@ struct Geo {
     // mbarriers {stage exchange, prefetch buffer 0, prefetch buffer 1}; phase bits of those three barriers
     uint32_t sm_ell, sm_pf, sm_mbar;
     mutable uint32_t ph_stage, ph_pf;
+    int split_partner;                          // split rows: lane to take partial sums from (own lane: none)
+    bool split_helper, split_owner;
 };
 
 // Stops the compiler from hoisting per-entry address arithmetic out of the step loop (register pressure).
@@ -860,6 +873,16 @@ struct Kern {
                             for (int c = 0; c < CPL; c++) cfma(acc[c], vv[q], ell[i][j0 + q], yy[q][c]);
                         }
                     }
+                }
+            }
+            if (!RS && !BLK && a.split_info) {
+                // split rows: the owner adds its helper's half, the helper keeps no state of its own
+#pragma unroll
+                for (int c = 0; c < CPL; c++) {
+                    const double px = __shfl_sync(0xffffffffu, acc[c].x, g.split_partner),
+                                 py = __shfl_sync(0xffffffffu, acc[c].y, g.split_partner);
+                    acc[c].x = g.split_helper ? 0.0 : acc[c].x + (g.split_owner ? px : 0.0);
+                    acc[c].y = g.split_helper ? 0.0 : acc[c].y + (g.split_owner ? py : 0.0);
                 }
             }
 #pragma unroll
@@ -1450,6 +1473,8 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         const int le = lane_active ? g.lane : a.groups * a.n_blk_rows - 1;
         g_idx = le / a.n_blk_rows;
         g.blk_row = le - g_idx * a.n_blk_rows;
+    } else if (RS && a.cu_map) {
+        g_idx = g.lane;            // column (within the batch of 32); rows come from the table (rs_perm)
     } else if (a.groups > 1) {
         lane_active = g.lane < a.groups * n;
         const int le = lane_active ? g.lane : a.groups * n - 1;
@@ -1457,6 +1482,14 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         row0 = le - g_idx * n;
     }
     g.colofs = g_idx * CPL;
+    g.split_partner = g.lane;
+    g.split_helper = g.split_owner = false;
+    if (!RS && a.split_info) {
+        const unsigned si = a.split_info[g.lane];
+        g.split_partner = (int)(si & 31u);
+        g.split_helper = (si & 32u) != 0;
+        g.split_owner = (si & 64u) != 0;
+    }
     g.stage_c = kStageC[g.lane < 5 ? g.lane : 4];
 
     // ---- shared memory map (byte addresses) ----
@@ -1533,12 +1566,15 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
             // sorted row q of chunk (slot i, this warp); the stage buffer, the scratch and the packed table are
             // indexed by q, initial state and results by the state row rs_perm[q].  Lanes past the last row read
             // the table's zero-slot padding (the host fills the whole chunk).
+            // (rs_perm / rs_pos hold 32 entries per chunk; -1 marks a lane without a row.  With the column-per-lane
+            // mapping all lanes of a chunk name the same row and the lane selects the column instead.)
             const int chunk = i * a.team_warps + g.warp_in_team;
             const int q = chunk * 32 + g.lane;
-            row_ok[i] = q < n;
-            row_of[i] = row_ok[i] ? __ldg(a.rs_perm + q) : 0;
+            const int rr = __ldg(a.rs_perm + q);
+            row_ok[i] = rr >= 0;
+            row_of[i] = row_ok[i] ? rr : 0;
             sidx[i] = row_ok[i] ? q : 0;
-            my_off[i] = 16u * (uint32_t)(__ldg(a.rs_pos + (q < n ? q : n - 1)) * a.y_row_stride);
+            my_off[i] = 16u * (uint32_t)(__ldg(a.rs_pos + q) * a.y_row_stride);
             ell[i][0] = 4u * (32u * (uint32_t)__ldg(a.rs_off + chunk) + (uint32_t)g.lane);  // byte offset of entry 0
             ell[i][MAXNNZ - 1] = (uint32_t)__ldg(a.rs_len + chunk);                          // entries per row (0: no rows)
             continue;
@@ -1549,13 +1585,16 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         sidx[i] = row_of[i];
         const int row_eff = row_of[i] < n ? row_of[i] : n - 1;
         my_off[i] = 16u * (row_eff * a.y_row_stride);
+        // the row table may hold more rows than the state (helper lanes of split rows): those lanes gather too
+        const bool ell_ok = lane_active && row_of[i] < a.g.n_vrows;
+        const int ell_row = ell_ok ? row_of[i] : n - 1;
 #pragma unroll
         for (int j = 0; j < MAXNNZ; j++) {
             // rows shorter than the variant's capacity: own row, zero slot
             uint32_t e = (uint32_t)row_eff | (0xFFFFu << 16);
-            if (!RS && j < a.g.max_nnz) e = a.g.ell[(size_t)j * n + row_eff];
+            if (!RS && j < a.g.max_nnz) e = a.g.ell[(size_t)j * a.g.n_vrows + ell_row];
             // slot 0xFFFF marks a zero entry (padding, or a row without a stored diagonal)
-            const uint32_t sl = (!row_ok[i] || (e >> 16) == 0xFFFFu) ? (uint32_t)a.g.n_slots : (e >> 16);
+            const uint32_t sl = (!ell_ok || (e >> 16) == 0xFFFFu) ? (uint32_t)a.g.n_slots : (e >> 16);
             ell[i][j] = (16u * (e & 0xFFFFu) * a.y_row_stride) | ((K::VB * sl) << 16);
             // mixed mode: an imaginary off-diagonal entry reads the second half of the split table
             if (K::MX && j > 0 && sl < (uint32_t)a.g.n_slots && __ldg(a.slot_imag + sl))
