@@ -298,6 +298,19 @@ int qsim_problem_kernel_name(qsim_problem *prob, int which, char *buf, int bufle
 /* Number of kernel launches issued through this ctx since creation.          */
 int64_t qsim_launch_count(qsim_ctx *ctx);
 
+/* Device time (CUDA events on the launch stream, milliseconds) from the start of the first to the end of
+ * the last kernel of the most recent solver call on this ctx: the integration alone, without the
+ * host<->device copies around it.  Waits for that call's kernels if they are still running.            */
+int qsim_last_kernel_ms(qsim_ctx *ctx, double *ms);
+
+/* Facts about the generator and the launch plan of one entry point (which: 0..3 as above), for reports and
+ * tests.  info[0] state rows n, [1] columns integrated together, [2] stored generator entries (nnz),
+ * [3] longest row, [4] value slots, [5] time-dependent value slots, [6] channels, [7] warps per trajectory,
+ * [8] trajectories (teams) per CTA, [9] threads per CTA, [10] dynamic shared memory per CTA in bytes,
+ * [11] 1 when the columns stream through scratch memory, [12] scratch bytes per trajectory in flight,
+ * [13] value mode of the kernel, [14] 1 for the row-split kernels, [15] reserved (0).                   */
+int qsim_problem_plan_info(qsim_problem *prob, int which, int64_t info[16]);
+
 /* FP64 FMA micro-benchmark: sustained DFMA TFLOP/s of the ctx's device,
  * measured with CUDA events over `ms_target` milliseconds of work.           */
 int qsim_peak_fp64(qsim_ctx *ctx, double ms_target, double *tflops);

@@ -66,14 +66,18 @@ struct DevBuf {
     }
 };
 
+#define QSIM_N_COUNTERS 4
 struct qsim_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaDeviceProp prop;
     SeriesTables *d_tab = nullptr;
     double *d_cheb = nullptr;  // Chebyshev transform / nodes / check points for the drive windows
-    unsigned long long *d_counter = nullptr;
-    DevBuf params, ts, init, out, stats, scratch, sel;
+    cudaStream_t stream2 = nullptr;            // second launch stream of pipelined host-buffer calls
+    unsigned long long *d_counter = nullptr;   // work-queue counters, one per launch in flight (QSIM_N_COUNTERS)
+    DevBuf params, ts, init, out, out2, stats, scratch, scratch2, sel;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the kernel launch(es) of the last solver call
+    bool timed = false;
     int64_t launches = 0;
 };
 
@@ -91,7 +95,7 @@ struct qsim_problem::DeviceCopy {
     // (stage stride, team warps, value mode): me_propagator and me_state of one problem use different sets and may
     // run concurrently from different ctxs, so sets are never replaced, only added (freed with the problem).
     struct Packed {
-        int stride, warps, vm;
+        int stride, warps, vm, cu = 0;
         uint32_t *ell = nullptr;
         int *perm = nullptr, *off = nullptr, *len = nullptr, *pos = nullptr;
     };
@@ -168,7 +172,10 @@ int qsim_create(int device, qsim_ctx **out) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&c->d_tab, sizeof(SeriesTables)));
     CU(cudaMemcpy(c->d_tab, &series_tables(), sizeof(SeriesTables), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
+    CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->d_counter, QSIM_N_COUNTERS * sizeof(unsigned long long)));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
     {
         // c_k = sum_j T[k][j] f(x_j), x_j = cos(pi (j + 1/2) / N): p(x) = sum_k c_k T_k(x)
         const int N = QSIM_NN;
@@ -192,7 +199,12 @@ int qsim_destroy(qsim_ctx *c) {
     if (!c) return QSIM_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->params.release(); c->ts.release(); c->init.release(); c->out.release(); c->stats.release(); c->scratch.release(); c->sel.release();
+    cudaStreamSynchronize(c->stream2);
+    c->params.release(); c->ts.release(); c->init.release(); c->out.release(); c->out2.release(); c->stats.release();
+    c->scratch.release(); c->scratch2.release(); c->sel.release();
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream2);
     cudaFree(c->d_tab);
     cudaFree(c->d_cheb);
     cudaFree(c->d_counter);
@@ -225,9 +237,21 @@ int qsim_synchronize(qsim_ctx *c) {
 
 int64_t qsim_launch_count(qsim_ctx *c) { return c ? c->launches : 0; }
 
+int qsim_last_kernel_ms(qsim_ctx *c, double *ms) {
+    if (!c || !ms) return fail(QSIM_ERR_ARG, "NULL argument");
+    if (!c->timed) return fail(QSIM_ERR_STATE, "no solver call has completed on this ctx yet");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev1));
+    float f = 0.0f;
+    CU(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+    *ms = (double)f;
+    return QSIM_OK;
+}
+
 int qsim_alloc_pinned(size_t bytes, void **ptr) {
     if (!ptr) return fail(QSIM_ERR_ARG, "ptr is NULL");
-    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    // portable + mapped: every device of a multi-ctx call may write results straight into it
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
     return QSIM_OK;
 }
 int qsim_free_pinned(void *ptr) {
@@ -855,12 +879,14 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         }
     }
     // Split rows (one row per lane, spare lanes): halves the longest rows; see build_split_rows.  Opt-in
-    // (QSIM_SPLIT_ROWS=1): parity-green, but on cfg3 (d = 27: rows of 1 + 4 instead of 1 + 8 entries) the saved operand
+    // (build with -DQSIM_SPLIT_ROWS, run with QSIM_SPLIT_ROWS=1): parity-green, but on cfg3 (d = 27: rows of 1 + 4 instead of 1 + 8 entries) the saved operand
     // loads are paid back by the per-stage shuffles of the helpers' partial sums and by bank conflicts of the compacted
     // rows (profiles/r2_cfg3_experiments.txt: 953 ms against 937 ms for 1184 x 50 ns).
     bool split = false;
+#ifdef QSIM_SPLIT_ROWS   // experimental build (make EXTRA=-DQSIM_SPLIT_ROWS) + QSIM_SPLIT_ROWS=1 in the environment
     if (!pl.rowsplit && !blocked && rpl == 1 && pl.groups == 1 && n < 32 && std::getenv("QSIM_SPLIT_ROWS"))
         split = build_split_rows(g, pl);
+#endif
     const int eff_nnz = split ? pl.split_nnz : g.max_nnz;
     pl.rpl = rpl;
     if (pl.cu) {
@@ -1004,6 +1030,18 @@ extern "C" int qsim_problem_kernel_name(qsim_problem *p, int which, char *buf, i
     return QSIM_OK;
 }
 
+extern "C" int qsim_problem_plan_info(qsim_problem *p, int which, int64_t info[16]) {
+    if (!p || !info || which < 0 || which > 3) return fail(QSIM_ERR_ARG, "bad argument");
+    Plan pl;
+    if (int rc = make_plan(p, which, pl)) return rc;
+    const Generator &g = p->gen[pl.w];
+    const int64_t v[16] = {g.n, pl.ncols, g.nnz, g.max_nnz, g.n_slots, g.n_dyn_slots, g.n_chan, pl.team_warps,
+                           pl.teams_per_cta, pl.block, (int64_t)pl.smem, pl.streamed, (int64_t)pl.scratch_per_team, pl.vm,
+                           pl.rowsplit, 0};
+    std::memcpy(info, v, sizeof(v));
+    return QSIM_OK;
+}
+
 extern "C" int qsim_problem_flops_per_rhs(qsim_problem *p, int which, double *flops) {
     if (!p || !flops || which < 0 || which > 3) return fail(QSIM_ERR_ARG, "bad argument");
     Plan pl;
@@ -1095,11 +1133,26 @@ struct Selection {
     int n_sel = 0, abs2 = 0;
     const int32_t *rows = nullptr, *cols = nullptr;
 };
+// A block-cyclic shard of a sweep: the call integrates points first, first + step, ... (n_traj of them) of arrays
+// that hold `total` points; results go to the same positions of the caller's arrays.
+struct Shard {
+    int64_t first = 0, step = 1, total = 0;
+};
+static bool host_pointer_is_pinned(const void *ptr, void **dev_alias) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    *dev_alias = at.devicePointer;
+    return true;
+}
 
 static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj, const double *params,
                         const double *ts, int n_ts, int64_t ts_stride, const double *init, int64_t init_stride,
                         const qsim_solver_opts *opts_in, double *out, qsim_traj_stats *stats,
-                        const Selection *sel = nullptr) {
+                        const Selection *sel = nullptr, const Shard *shard = nullptr) {
     if (!c) return fail(QSIM_ERR_NO_DEVICE, "ctx is NULL: create one with qsim_create (needs a CUDA device; no CPU fallback)");
     if (!p) return fail(QSIM_ERR_ARG, "prob is NULL");
     if (n_traj < 0) return fail(QSIM_ERR_ARG, "n_traj < 0");
@@ -1122,7 +1175,10 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     if (!(o.reltol > 0) || !(o.abstol >= 0) || !(o.gamma > 0) || !(o.qmin > 0) || !(o.qmax > 0))
         return fail(QSIM_ERR_ARG, "solver options out of range");
     const bool dev_ptrs = (o.flags & QSIM_FLAG_DEVICE_PTRS) != 0;
-    if (!dev_ptrs) {
+    Shard sh;
+    if (shard) sh = *shard;
+    else sh.total = n_traj;
+    if (!dev_ptrs && !shard) {   // (a sharded call's arrays were checked once by its caller)
         // @assert issorted(ts)   (time_evolution.jl:30,64,97,141)
         const int64_t ngrids = ts_stride ? n_traj : 1;
         for (int64_t i = 0; i < ngrids; i++)
@@ -1148,7 +1204,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         if (pl.rowsplit) {
             bool have = false;
             for (const auto &q : dc->packed)
-                if (q.stride == pl.y_row_stride && q.warps == pl.team_warps && q.vm == pl.vm) {
+                if (q.stride == pl.y_row_stride && q.warps == pl.team_warps && q.vm == pl.vm && q.cu == pl.cu) {
                     pk = q;
                     have = true;
                 }
@@ -1156,6 +1212,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
                 pk.stride = pl.y_row_stride;
                 pk.warps = pl.team_warps;
                 pk.vm = pl.vm;
+                pk.cu = pl.cu;
                 build_rowsplit_table(g, pl, true);
                 CU(upload(&pk.ell, pl.rs_table));
                 CU(upload(&pk.pos, pl.rs_pos));
@@ -1187,11 +1244,10 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     pl.grid = (int)std::min<int64_t>((int64_t)ctas_per_sm * c->prop.multiProcessorCount, need);
 
     const size_t n_state = (size_t)g.n * pl.ncols;
-    const size_t b_params = sizeof(double) * (size_t)std::max(p->n_params, 1) * n_traj;
-    const size_t b_ts = sizeof(double) * (size_t)(ts_stride ? ts_stride * n_traj : n_ts);
-    const size_t b_init = init ? sizeof(double2) * (size_t)(init_stride ? init_stride * n_traj : g.n) : 0;
-    size_t b_out = sizeof(double2) * n_state * n_ts * n_traj;
-    const size_t b_stats = sizeof(qsim_traj_stats) * n_traj;
+    const size_t b_params = sizeof(double) * (size_t)std::max(p->n_params, 1) * sh.total;
+    const size_t b_ts = sizeof(double) * (size_t)(ts_stride ? ts_stride * sh.total : n_ts);
+    const size_t b_init = init ? sizeof(double2) * (size_t)(init_stride ? init_stride * sh.total : g.n) : 0;
+    size_t traj_bytes = sizeof(double2) * n_state * n_ts;     // result bytes per trajectory
 
     LaunchArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -1210,8 +1266,22 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         a.sel_index = (const int *)c->sel.p;
         a.n_sel = sel->n_sel;
         a.sel_abs2 = sel->abs2;
-        b_out = (sel->abs2 ? sizeof(double) : sizeof(double2)) * (size_t)sel->n_sel * n_ts * n_traj;
+        traj_bytes = (sel->abs2 ? sizeof(double) : sizeof(double2)) * (size_t)sel->n_sel * n_ts;
     }
+    // How results leave the device (host buffers):
+    //   zero-copy  the caller's `out` is page-locked (qsim_alloc_pinned / cudaHostRegister): the kernel writes it in
+    //              place over PCIe while it integrates -- no device result buffer, no copy after the kernel;
+    //   pipelined  pageable `out`, large results: the trajectories are cut into chunks launched alternately on two
+    //              streams into two device buffers; chunk k's results are copied out while chunk k + 1 integrates;
+    //   plain      small results: one launch, one copy.
+    void *out_alias = nullptr, *stats_alias = nullptr;
+    const bool zero_copy = !dev_ptrs && !std::getenv("QSIM_NO_ZEROCOPY") && host_pointer_is_pinned(out, &out_alias);
+    const bool stats_direct = zero_copy && stats && host_pointer_is_pinned(stats, &stats_alias);
+    const int64_t capacity = (int64_t)ctas_per_sm * c->prop.multiProcessorCount * pl.teams_per_cta;  // teams in flight
+    int n_chunks = 1;
+    if (!dev_ptrs && !zero_copy && !o.stream && (double)traj_bytes * (double)n_traj > 64e6 && !std::getenv("QSIM_NO_PIPELINE"))
+        n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(8, n_traj / std::max<int64_t>(capacity, 1)));
+    const int64_t per_chunk = (n_traj + n_chunks - 1) / n_chunks;
     if (dev_ptrs) {
         a.params = params;
         a.ts = ts;
@@ -1221,8 +1291,11 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     } else {
         CU(c->params.reserve(b_params));
         CU(c->ts.reserve(b_ts));
-        CU(c->out.reserve(b_out));
-        CU(c->stats.reserve(b_stats));
+        if (!zero_copy) {
+            CU(c->out.reserve(traj_bytes * (size_t)per_chunk));
+            if (n_chunks > 1) CU(c->out2.reserve(traj_bytes * (size_t)per_chunk));
+        }
+        if (!stats_direct) CU(c->stats.reserve(sizeof(qsim_traj_stats) * (size_t)n_traj));
         if (params && p->n_params > 0) CU(cudaMemcpyAsync(c->params.p, params, b_params, cudaMemcpyHostToDevice, stream));
         CU(cudaMemcpyAsync(c->ts.p, ts, b_ts, cudaMemcpyHostToDevice, stream));
         if (init) {
@@ -1232,13 +1305,19 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         a.params = (const double *)c->params.p;
         a.ts = (const double *)c->ts.p;
         a.init = (const double2 *)c->init.p;
-        a.out = (double2 *)c->out.p;
-        a.stats = (qsim_traj_stats *)c->stats.p;
+        a.out = zero_copy ? (double2 *)out_alias : (double2 *)c->out.p;
+        a.stats = stats_direct ? (qsim_traj_stats *)stats_alias : (qsim_traj_stats *)c->stats.p;
     }
+    a.in_first = sh.first;
+    a.in_step = sh.step;
+    a.out_first = (dev_ptrs || zero_copy) ? sh.first : 0;
+    a.out_step = (dev_ptrs || zero_copy) ? sh.step : 1;
     if (pl.streamed) {
         CU(c->scratch.reserve(pl.scratch_per_team * (size_t)pl.grid * pl.teams_per_cta));
         a.scratch = (double2 *)c->scratch.p;
+        if (n_chunks > 1) CU(c->scratch2.reserve(pl.scratch_per_team * (size_t)pl.grid * pl.teams_per_cta));
     }
+
     a.g.n = g.n;
     a.g.max_nnz = g.max_nnz;
     a.g.n_slots = g.n_slots;
@@ -1334,13 +1413,65 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         for (int e = 0; e < QSIM_POW_NE; e++) a.pow_exp2[w][e] = std::exp2(pw * (double)(e + QSIM_POW_EMIN));
     }
 
-    CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), stream));
-    CU(pl.kv->launch(a, pl.grid, pl.block, pl.smem, stream));
-    c->launches++;
-    if (!dev_ptrs) {
-        CU(cudaMemcpyAsync(out, c->out.p, b_out, cudaMemcpyDeviceToHost, stream));
-        if (stats) CU(cudaMemcpyAsync(stats, c->stats.p, b_stats, cudaMemcpyDeviceToHost, stream));
-        CU(cudaStreamSynchronize(stream));
+    if (n_chunks == 1) {
+        CU(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), stream));
+        CU(cudaEventRecord(c->ev0, stream));
+        CU(pl.kv->launch(a, pl.grid, pl.block, pl.smem, stream));
+        CU(cudaEventRecord(c->ev1, stream));
+        c->timed = true;
+        c->launches++;
+        if (!dev_ptrs) {
+            // results: in place already (zero-copy), or one strided copy into the caller's positions
+            if (!zero_copy)
+                CU(cudaMemcpy2DAsync((char *)out + traj_bytes * (size_t)sh.first, traj_bytes * (size_t)sh.step, c->out.p, traj_bytes,
+                                     traj_bytes, (size_t)n_traj, cudaMemcpyDeviceToHost, stream));
+            if (stats && !stats_direct)
+                CU(cudaMemcpy2DAsync(stats + sh.first, sizeof(qsim_traj_stats) * (size_t)sh.step, c->stats.p, sizeof(qsim_traj_stats),
+                                     sizeof(qsim_traj_stats), (size_t)n_traj, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+        }
+        return QSIM_OK;
+    }
+    // pipelined: chunk k on stream k % 2 into result buffer k % 2 (its own scratch and work counter); the host copies
+    // chunk k - 1 out (a blocking pageable copy) while chunk k integrates.  Inputs were queued on `stream`: make the
+    // second stream wait for them.
+    CU(cudaEventRecord(c->ev1, stream));
+    CU(cudaStreamWaitEvent(c->stream2, c->ev1, 0));
+    cudaStream_t streams[2] = {stream, c->stream2};
+    auto copy_out = [&](int k) -> int {
+        const int64_t lo = (int64_t)k * per_chunk, cnt = std::min<int64_t>(per_chunk, n_traj - lo);
+        const void *src = (k % 2) ? c->out2.p : c->out.p;
+        CU(cudaMemcpy2DAsync((char *)out + traj_bytes * (size_t)(sh.first + lo * sh.step), traj_bytes * (size_t)sh.step, src,
+                             traj_bytes, traj_bytes, (size_t)cnt, cudaMemcpyDeviceToHost, streams[k % 2]));
+        CU(cudaStreamSynchronize(streams[k % 2]));
+        return QSIM_OK;
+    };
+    for (int k = 0; k < n_chunks; k++) {
+        const int64_t lo = (int64_t)k * per_chunk, cnt = std::min<int64_t>(per_chunk, n_traj - lo);
+        if (cnt <= 0) break;
+        LaunchArgs ak = a;
+        ak.n_traj = cnt;
+        ak.in_first = sh.first + lo * sh.step;
+        ak.out = (double2 *)((k % 2) ? c->out2.p : c->out.p);
+        ak.stats = (qsim_traj_stats *)c->stats.p + lo;
+        ak.work_counter = c->d_counter + (k % QSIM_N_COUNTERS);
+        if (pl.streamed && (k % 2)) ak.scratch = (double2 *)c->scratch2.p;
+        const int grid_k = (int)std::min<int64_t>(pl.grid, (cnt + pl.teams_per_cta - 1) / pl.teams_per_cta);
+        CU(cudaMemsetAsync(ak.work_counter, 0, sizeof(unsigned long long), streams[k % 2]));
+        if (k == 0) CU(cudaEventRecord(c->ev0, streams[0]));
+        CU(pl.kv->launch(ak, grid_k, pl.block, pl.smem, streams[k % 2]));
+        c->launches++;
+        if (k >= 1)
+            if (int rc = copy_out(k - 1)) return rc;
+    }
+    {
+        const int last = (int)((n_traj + per_chunk - 1) / per_chunk) - 1;
+        CU(cudaEventRecord(c->ev1, streams[last % 2]));
+        c->timed = true;
+        if (int rc = copy_out(last)) return rc;
+        if (stats)
+            CU(cudaMemcpy2D(stats + sh.first, sizeof(qsim_traj_stats) * (size_t)sh.step, c->stats.p, sizeof(qsim_traj_stats),
+                            sizeof(qsim_traj_stats), (size_t)n_traj, cudaMemcpyDeviceToHost));
     }
     return QSIM_OK;
 }
@@ -1396,8 +1527,8 @@ int qsim_solve_selected(qsim_ctx *ctx, qsim_problem *prob, int which, int64_t n_
 }
 
 // One sweep over several devices from one call (SURVEY.md section 8b "Threading": the fan-out happens inside
-// the library so a Julia caller needs no threads).  Trajectories are split into contiguous blocks, block i
-// runs through ctxs[i] on its own host thread and copies its results straight into the caller's buffers.
+// the library so a Julia caller needs no threads).  Trajectories are dealt block-cyclically, shard i runs through
+// ctxs[i] on its own host thread and delivers its results straight into the caller's buffers.
 int qsim_solve_multi(qsim_ctx **ctxs, int n_ctx, qsim_problem *prob, int which, int64_t n_traj, const double *params,
                      const double *ts, int n_ts, int64_t ts_stride, const double *init, int64_t init_stride,
                      const qsim_solver_opts *opts, double *out, qsim_traj_stats *stats) {
@@ -1416,23 +1547,30 @@ int qsim_solve_multi(qsim_ctx **ctxs, int n_ctx, qsim_problem *prob, int which, 
     if (n_ctx == 1 || n_traj <= 1)
         return solve_common(ctxs[0], prob, which, n_traj, params, ts, n_ts, ts_stride, has_init ? init : nullptr, init_stride,
                             opts, out, stats);
+    if (n_ts < 1 || !ts) return fail(QSIM_ERR_ARG, "need at least one save time");
+    if (ts_stride != 0 && ts_stride < n_ts) return fail(QSIM_ERR_ARG, "ts_stride must be 0 or >= n_ts");
+    for (int64_t i = 0; i < (ts_stride ? n_traj : 1); i++)   // @assert issorted(ts), once for all shards
+        for (int k = 1; k < n_ts; k++)
+            if (!(ts[i * ts_stride + k - 1] <= ts[i * ts_stride + k])) return fail(QSIM_ERR_ARG, "ts must be sorted");
     // build the generator and check the plan once, on this thread (the workers then only read the problem)
     Plan pl;
     if (int rc = make_plan(prob, which, pl)) return rc;
-    const size_t n_state = (size_t)prob->gen[pl.w].n * pl.ncols;
-    const int64_t per = (n_traj + n_ctx - 1) / n_ctx;
+    // Block-cyclic shards: ctx i integrates points i, i + n_ctx, ... and puts their results at
+    // those positions of the caller's arrays -- in place when `out` is page-locked, otherwise through the pipelined
+    // copy of solve_common, which hides the device-to-host transfer behind the next chunk's integration.
     std::vector<int> rcs((size_t)n_ctx, QSIM_OK);
     std::vector<std::string> msgs((size_t)n_ctx);
     std::vector<std::thread> workers;
     for (int i = 0; i < n_ctx; i++) {
-        const int64_t lo = std::min<int64_t>(n_traj, per * i), hi = std::min<int64_t>(n_traj, per * (i + 1));
-        if (hi <= lo) continue;
+        const int64_t cnt = (n_traj - i + n_ctx - 1) / n_ctx;
+        if (cnt <= 0) continue;
         workers.emplace_back([=, &rcs, &msgs]() {
-            const double *par_i = params ? params + (size_t)lo * std::max(prob->n_params, 1) : nullptr;
-            const double *ts_i = ts_stride ? ts + (size_t)lo * ts_stride : ts;
-            const double *init_i = has_init ? (init_stride ? init + 2 * (size_t)lo * init_stride : init) : nullptr;
-            rcs[(size_t)i] = solve_common(ctxs[i], prob, which, hi - lo, par_i, ts_i, n_ts, ts_stride, init_i, init_stride, opts,
-                                          out + 2 * (size_t)lo * n_ts * n_state, stats ? stats + lo : nullptr);
+            Shard sh;
+            sh.first = i;
+            sh.step = n_ctx;
+            sh.total = n_traj;
+            rcs[(size_t)i] = solve_common(ctxs[i], prob, which, cnt, params, ts, n_ts, ts_stride, has_init ? init : nullptr,
+                                          init_stride, opts, out, stats, nullptr, &sh);
             if (rcs[(size_t)i] != QSIM_OK) msgs[(size_t)i] = g_err;  // g_err is per thread
         });
     }

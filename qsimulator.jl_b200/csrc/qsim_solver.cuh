@@ -60,6 +60,10 @@ struct LaunchArgs {
     int identity_init;    // 1: u0 = I (propagators); 0: u0 = init (column 0)
     int n_params, n_ts;
     long long ts_stride, init_stride, n_traj;
+    // Trajectory j of this launch reads inputs (params, ts, init) of sweep point in_first + j * in_step and writes
+    // results and stats at position out_first + j * out_step: a block-cyclic shard of a sweep addresses the
+    // caller's arrays in place; a chunk of a pipelined call writes a chunk-local result buffer.
+    long long in_first, in_step, out_first, out_step;
     const double *params, *ts;
     const double2 *init;
     double2 *out;
@@ -875,6 +879,7 @@ struct Kern {
                     }
                 }
             }
+#ifdef QSIM_SPLIT_ROWS   // (experimental build only: a run-time test here would split the gather's basic block)
             if (!RS && !BLK && a.split_info) {
                 // split rows: the owner adds its helper's half, the helper keeps no state of its own
 #pragma unroll
@@ -885,6 +890,7 @@ struct Kern {
                     acc[c].y = g.split_helper ? 0.0 : acc[c].y + (g.split_owner ? py : 0.0);
                 }
             }
+#endif
 #pragma unroll
             for (int c = 0; c < CPL; c++) k[i * CPL + c] = acc[c];
         }
@@ -1009,8 +1015,9 @@ struct Kern {
         // sidx: this lane's row indices inside the scratch buffers (row-split teams keep the scratch in their
         // sorted row order so that a warp's accesses are contiguous; everyone else uses the state row)
         const int n = a.g.n;
-        const double *ts = a.ts + (size_t)traj * a.ts_stride;
-        const double *prow = a.params + (size_t)traj * a.n_params;
+        const long long tin = a.in_first + traj * a.in_step, tout = a.out_first + traj * a.out_step;
+        const double *ts = a.ts + (size_t)tin * a.ts_stride;
+        const double *prow = a.params + (size_t)tin * a.n_params;
         const double t0 = ts[0], tend = ts[a.n_ts - 1];
         const double ntot = (double)n * (double)a.ncols;
         const uint32_t V0 = g.sm_V, V1 = V0 + g.v_stride, V2 = V1 + g.v_stride, V3 = V2 + g.v_stride, V4 = V3 + g.v_stride;
@@ -1091,8 +1098,8 @@ struct Kern {
             double acc2[2] = {0.0, 0.0};
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                 const int col0 = b * g.cpb + g.colofs;
-                initial_state(a, traj, col0, row_of, row_ok, u);
-                for (int ks = 0; ks < nsave; ks++) write_out(a, traj, ks, col0, row_of, row_ok, u);
+                initial_state(a, tin, col0, row_of, row_ok, u);
+                for (int ks = 0; ks < nsave; ks++) write_out(a, tout, ks, col0, row_of, row_ok, u);
                 put_stage(a, g, u, yb0, my_off, row_ok);
                 apply(a, g, V0, yb0, ell, vstat, row_of, u, k1);
                 if (a.streamed) {
@@ -1356,7 +1363,7 @@ struct Kern {
                         store_batch(sc_u0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, sidx, row_ok, tmp);
                         store_batch(sc_k0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, sidx, row_ok, k7);
                         if (nsave_hi > nsave)
-                            save_points(a, traj, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok, u, k1,
+                            save_points(a, tout, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok, u, k1,
                                         k2, k3, k4, k5, k6, k7, tmp);
                     }
                 }
@@ -1390,7 +1397,7 @@ struct Kern {
                     CTL_ST(C_QOLDPOW, e2 >= qinit2 ? rb : qinit_pow);  // qold = max(EEst, qoldinit)
                     if (!a.streamed) {
                         if (nsave_hi > nsave && (RS || g.warp_in_team < a.n_batches))
-                            save_points(a, traj, ts, nsave, nsave_hi, t, dt, tnew,
+                            save_points(a, tout, ts, nsave, nsave_hi, t, dt, tnew,
                                         (RS ? 0 : g.warp_in_team) * g.cpb + g.colofs,
                                         row_of, row_ok, u, k1, k2, k3, k4, k5, k6, k7, tmp);
 #pragma unroll
@@ -1426,8 +1433,8 @@ struct Kern {
             // zero-length span: only the start saves
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                 const int col0 = b * g.cpb + g.colofs;
-                initial_state(a, traj, col0, row_of, row_ok, u);
-                for (int ks = 0; ks < nsave; ks++) write_out(a, traj, ks, col0, row_of, row_ok, u);
+                initial_state(a, tin, col0, row_of, row_ok, u);
+                for (int ks = 0; ks < nsave; ks++) write_out(a, tout, ks, col0, row_of, row_ok, u);
             }
         }
         // unreached save points of a failed trajectory: NaN
@@ -1436,10 +1443,10 @@ struct Kern {
 #pragma unroll
             for (int e = 0; e < E; e++) tmp[e] = make_double2(qnan, qnan);
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps)
-                for (int ks = nsave; ks < a.n_ts; ks++) write_out(a, traj, ks, b * g.cpb + g.colofs, row_of, row_ok, tmp);
+                for (int ks = nsave; ks < a.n_ts; ks++) write_out(a, tout, ks, b * g.cpb + g.colofs, row_of, row_ok, tmp);
         }
         st.t_final = t;
-        if (g.team_thread == 0 && a.stats) a.stats[traj] = st;
+        if (g.team_thread == 0 && a.stats) a.stats[tout] = st;
     }
 };
 

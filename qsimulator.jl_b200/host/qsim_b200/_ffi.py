@@ -24,7 +24,7 @@ EXPORTS = [
     "qsim_problem_finalize",
     "qsim_problem_eval", "qsim_unitary_propagator", "qsim_unitary_state", "qsim_me_propagator", "qsim_me_state",
     "qsim_solve_selected", "qsim_solve_multi", "qsim_problem_flops_per_rhs", "qsim_problem_kernel_name", "qsim_launch_count",
-    "qsim_peak_fp64",
+    "qsim_peak_fp64", "qsim_last_kernel_ms", "qsim_problem_plan_info",
 ]
 
 
@@ -81,6 +81,8 @@ def lib():
     L.qsim_launch_count.argtypes = [vp]
     L.qsim_launch_count.restype = C.c_int64
     L.qsim_peak_fp64.argtypes = [vp, C.c_double, dp]
+    L.qsim_last_kernel_ms.argtypes = [vp, dp]
+    L.qsim_problem_plan_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -120,6 +122,12 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().qsim_launch_count(self._h))
+
+    def last_kernel_ms(self) -> float:
+        """Device time of the kernels of the most recent solver call on this context (CUDA events)."""
+        v = C.c_double()
+        check(lib().qsim_last_kernel_ms(self._h, C.byref(v)))
+        return v.value
 
     def peak_fp64(self, ms_target: float = 200.0) -> float:
         v = C.c_double()
@@ -236,6 +244,15 @@ class Problem:
         v = C.c_double()
         check(lib().qsim_problem_flops_per_rhs(self._h, WHICH.get(which, which), C.byref(v)))
         return v.value
+
+    PLAN_KEYS = ("n", "ncols", "nnz", "max_row", "n_slots", "n_dyn_slots", "n_chan", "team_warps", "teams_per_cta",
+                 "block", "smem_bytes", "streamed", "scratch_bytes_per_team", "value_mode", "rowsplit", "_reserved")
+
+    def plan_info(self, which) -> dict:
+        """Generator and launch-plan facts of one entry point (qsim_problem_plan_info)."""
+        v = (C.c_int64 * 16)()
+        check(lib().qsim_problem_plan_info(self._h, WHICH.get(which, which), v))
+        return {k: int(x) for k, x in zip(self.PLAN_KEYS, v) if not k.startswith("_")}
 
     def kernel_name(self, which) -> str:
         buf = C.create_string_buffer(128)

@@ -1,0 +1,79 @@
+"""How results leave the device (qsim_api.cu, solve_common): page-locked caller buffers are written in place by
+the kernel ("zero-copy"), large pageable results go through the pipelined chunk copy, small ones through one copy;
+qsim_solve_multi deals the sweep block-cyclically.  All paths must deliver bitwise identical results."""
+import numpy as np
+import pytest
+
+from qsim_b200 import Context, PinnedArray, Problem, _abi
+from qsim_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg2(n_points, t_final):
+    cqs, params, _, _ = W.config("cfg2")
+    idx = np.linspace(0, len(params) - 1, n_points).astype(int)
+    return cqs, np.ascontiguousarray(params[idx]), np.arange(0.0, t_final + 1.0)
+
+
+def test_zero_copy_equals_staged_copy():
+    cqs, params, ts = _cfg2(300, 4.0)
+    ctx, prob = Context(0), Problem(cqs)
+    ref, st_ref = prob.solve("unitary_propagator", ts, params=params, ctx=ctx)          # pageable: one staged copy
+    pin = PinnedArray((len(params), len(ts), 81), np.complex128)
+    pin.array[...] = np.nan
+    got, st = prob.solve("unitary_propagator", ts, params=params, ctx=ctx, out=pin.array)   # written in place
+    assert np.array_equal(got, ref) and np.array_equal(st, st_ref)
+    assert ctx.last_kernel_ms() > 0.0
+    # selected output through the same path
+    sel = [(0, 0), (4, 4), (3, 1)]
+    ref_s, _ = prob.solve("unitary_propagator", ts, params=params, ctx=ctx, select=sel)
+    pin_s = PinnedArray((len(params), len(ts), 3), np.complex128)
+    got_s, _ = prob.solve("unitary_propagator", ts, params=params, ctx=ctx, select=sel, out=pin_s.array)
+    assert np.array_equal(got_s, ref_s)
+    assert np.array_equal(ref_s[:, :, 1], ref[:, :, 4, 4])
+
+
+def test_pipelined_pageable_copy_equals_single_launch():
+    """4096 points x 61 saves = 324 MB of results in pageable memory: cut into chunks launched on two streams, each
+    copied out while the next integrates; bitwise equal to the one-launch result in page-locked memory, and to a run
+    with the pipeline switched off."""
+    import os
+    cqs, params, ts = _cfg2(4096, 60.0)
+    ctx, prob = Context(0), Problem(cqs)
+    l0 = ctx.launch_count()
+    got, st = prob.solve("unitary_propagator", ts, params=params, ctx=ctx)
+    assert ctx.launch_count() - l0 > 1, "expected a pipelined (multi-launch) call"
+    pin = PinnedArray((len(params), len(ts), 81), np.complex128)
+    l0 = ctx.launch_count()
+    ref, st_ref = prob.solve("unitary_propagator", ts, params=params, ctx=ctx, out=pin.array)
+    assert ctx.launch_count() - l0 == 1
+    assert np.array_equal(got, ref) and np.array_equal(st, st_ref)
+    os.environ["QSIM_NO_PIPELINE"] = "1"
+    try:
+        one, _ = prob.solve("unitary_propagator", ts, params=params, ctx=ctx)
+    finally:
+        del os.environ["QSIM_NO_PIPELINE"]
+    assert np.array_equal(one, ref)
+
+
+def test_block_cyclic_fanout_two_contexts_one_device():
+    """qsim_solve_multi with two contexts (on one device when the box has one): shard i = points i, i + 2, ...;
+    results land at the points' own positions, pageable and page-locked alike."""
+    cqs, params, ts = _cfg2(301, 3.0)
+    prob = Problem(cqs)
+    ref, st_ref = prob.solve("unitary_propagator", ts, params=params, ctx=Context(0))
+    ctxs = [Context(0), Context(0)]
+    got, st = prob.solve("unitary_propagator", ts, params=params, ctx=ctxs)
+    assert np.array_equal(got, ref) and np.array_equal(st, st_ref)
+    pin = PinnedArray((len(params), len(ts), 81), np.complex128)
+    got2, _ = prob.solve("unitary_propagator", ts, params=params, ctx=ctxs, out=pin.array)
+    assert np.array_equal(got2, ref)
+    # states with per-trajectory initial vectors and save grids
+    rng = np.random.default_rng(5)
+    psi = rng.normal(size=(len(params), 9)) + 1j * rng.normal(size=(len(params), 9))
+    tss = np.sort(rng.uniform(0, 3, size=(len(params), 4)), axis=1)
+    tss[:, 0] = 0.0
+    r1, s1 = prob.solve("unitary_state", tss, params=params, init=psi, ctx=Context(0))
+    r2, s2 = prob.solve("unitary_state", tss, params=params, init=psi, ctx=ctxs)
+    assert np.array_equal(r1, r2) and np.array_equal(s1, s2)
