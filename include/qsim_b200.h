@@ -295,6 +295,25 @@ int qsim_problem_flops_per_rhs(qsim_problem *prob, int which, double *flops);
 /* Name of the kernel variant the dispatcher picks for this problem.          */
 int qsim_problem_kernel_name(qsim_problem *prob, int which, char *buf, int buflen);
 
+/* Dimension and number of sweep parameters the problem was created with.       */
+int qsim_problem_dims(qsim_problem *prob, int *d, int *n_params);
+
+/* Floquet propagation of a whole sweep in one call: replaces, batched and device-resident, the reference's
+ * floquet_propagator / floquet_rise_fall_propagator (src/time_evolution.jl:188-220, 312-338) wrapped around
+ * unitary_propagator (which = 0) or me_propagator (which = 2).  The system of trajectory i is taken to be periodic
+ * with period t_period[i * period_stride] (period_stride 0: one period for all) between ts[0] + rise_time and
+ * ts[n_ts-1] - fall_time; with rise_time = fall_time = 0 this is floquet_propagator.  rtol <= 0 selects the
+ * reference's default eps(t_period) for merging the times modulo the period (unique_tol, :355-360).
+ * Every segment (rise, the unique remainders plus one period, fall) of every trajectory is one trajectory of a
+ * single batched solver launch; U(n tau + dt) = U(dt) U(tau)^n and the segment products are formed on the device
+ * and only out[traj][k][n*n] (n = d or d*d, column-major) is delivered.  Host buffers only.  stats (may be NULL)
+ * sums the step counts of a trajectory's segments.                                                        */
+int qsim_floquet_propagator(qsim_ctx *ctx, qsim_problem *prob, int which, int64_t n_traj,
+                            const double *params, const double *ts, int n_ts, int64_t ts_stride,
+                            const double *t_period, int64_t period_stride, double rise_time,
+                            double fall_time, double rtol, const qsim_solver_opts *opts,
+                            double *out, qsim_traj_stats *stats);
+
 /* Number of kernel launches issued through this ctx since creation.          */
 int64_t qsim_launch_count(qsim_ctx *ctx);
 

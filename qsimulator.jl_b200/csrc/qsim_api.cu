@@ -76,6 +76,10 @@ struct qsim_ctx {
     cudaStream_t stream2 = nullptr;            // second launch stream of pipelined host-buffer calls
     unsigned long long *d_counter = nullptr;   // work-queue counters, one per launch in flight (QSIM_N_COUNTERS)
     DevBuf params, ts, init, out, out2, stats, scratch, scratch2, sel;
+    DevBuf fl_seg, fl_work, fl_idx;            // qsim_floquet_propagator: segment propagators, power workspace, index tables
+    void *stage[2] = {nullptr, nullptr};       // page-locked staging buffers of the pipelined result copies
+    size_t stage_cap[2] = {0, 0};
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the kernel launch(es) of the last solver call
     bool timed = false;
     int64_t launches = 0;
@@ -176,6 +180,8 @@ int qsim_create(int device, qsim_ctx **out) {
     CU(cudaMalloc(&c->d_counter, QSIM_N_COUNTERS * sizeof(unsigned long long)));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    CU(cudaEventCreateWithFlags(&c->ev_copy[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_copy[1], cudaEventDisableTiming));
     {
         // c_k = sum_j T[k][j] f(x_j), x_j = cos(pi (j + 1/2) / N): p(x) = sum_k c_k T_k(x)
         const int N = QSIM_NN;
@@ -202,8 +208,13 @@ int qsim_destroy(qsim_ctx *c) {
     cudaStreamSynchronize(c->stream2);
     c->params.release(); c->ts.release(); c->init.release(); c->out.release(); c->out2.release(); c->stats.release();
     c->scratch.release(); c->scratch2.release(); c->sel.release();
+    c->fl_seg.release(); c->fl_work.release(); c->fl_idx.release();
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(c->ev_copy[i]);
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+    }
     cudaStreamDestroy(c->stream2);
     cudaFree(c->d_tab);
     cudaFree(c->d_cheb);
@@ -1129,6 +1140,7 @@ static int ensure_device_copy(qsim_ctx *c, qsim_problem *p, int w, qsim_problem:
     return QSIM_OK;
 }
 
+#define QSIM_FLAG_INTERNAL_DEVICE_OUT (1u << 30)   // library-internal: `out` is device memory, everything else host
 struct Selection {
     int n_sel = 0, abs2 = 0;
     const int32_t *rows = nullptr, *cols = nullptr;
@@ -1275,7 +1287,9 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     //              streams into two device buffers; chunk k's results are copied out while chunk k + 1 integrates;
     //   plain      small results: one launch, one copy.
     void *out_alias = nullptr, *stats_alias = nullptr;
-    const bool zero_copy = !dev_ptrs && !std::getenv("QSIM_NO_ZEROCOPY") && host_pointer_is_pinned(out, &out_alias);
+    const bool device_out = (o.flags & QSIM_FLAG_INTERNAL_DEVICE_OUT) != 0;   // host inputs, results stay on the device
+    if (device_out) out_alias = out;
+    const bool zero_copy = device_out || (!dev_ptrs && !std::getenv("QSIM_NO_ZEROCOPY") && host_pointer_is_pinned(out, &out_alias));
     const bool stats_direct = zero_copy && stats && host_pointer_is_pinned(stats, &stats_alias);
     const int64_t capacity = (int64_t)ctas_per_sm * c->prop.multiProcessorCount * pl.teams_per_cta;  // teams in flight
     int n_chunks = 1;
@@ -1432,20 +1446,35 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         }
         return QSIM_OK;
     }
-    // pipelined: chunk k on stream k % 2 into result buffer k % 2 (its own scratch and work counter); the host copies
-    // chunk k - 1 out (a blocking pageable copy) while chunk k integrates.  Inputs were queued on `stream`: make the
-    // second stream wait for them.
+    // pipelined: chunk k on stream k % 2 into result buffer k % 2 (its own scratch and work counter), followed on the
+    // same stream by a copy into page-locked staging buffer k % 2; while chunk k integrates and chunk k - 1's copy
+    // drains, this thread moves chunk k - 1 from its staging buffer to the caller's (pageable, possibly strided)
+    // positions.  Inputs were queued on `stream`: make the second stream wait for them.
+    for (int i = 0; i < 2; i++) {
+        const size_t need_b = traj_bytes * (size_t)per_chunk;
+        if (c->stage_cap[i] < need_b) {
+            if (c->stage[i]) CU(cudaFreeHost(c->stage[i]));
+            c->stage[i] = nullptr;
+            c->stage_cap[i] = 0;
+            CU(cudaHostAlloc(&c->stage[i], need_b, cudaHostAllocDefault));
+            c->stage_cap[i] = need_b;
+        }
+    }
     CU(cudaEventRecord(c->ev1, stream));
     CU(cudaStreamWaitEvent(c->stream2, c->ev1, 0));
     cudaStream_t streams[2] = {stream, c->stream2};
-    auto copy_out = [&](int k) -> int {
+    auto move_out = [&](int k) -> int {   // staging buffer k % 2 -> the caller's arrays (host memcpy)
         const int64_t lo = (int64_t)k * per_chunk, cnt = std::min<int64_t>(per_chunk, n_traj - lo);
-        const void *src = (k % 2) ? c->out2.p : c->out.p;
-        CU(cudaMemcpy2DAsync((char *)out + traj_bytes * (size_t)(sh.first + lo * sh.step), traj_bytes * (size_t)sh.step, src,
-                             traj_bytes, traj_bytes, (size_t)cnt, cudaMemcpyDeviceToHost, streams[k % 2]));
-        CU(cudaStreamSynchronize(streams[k % 2]));
+        CU(cudaEventSynchronize(c->ev_copy[k % 2]));
+        const char *src = (const char *)c->stage[k % 2];
+        char *dst = (char *)out + traj_bytes * (size_t)(sh.first + lo * sh.step);
+        if (sh.step == 1)
+            std::memcpy(dst, src, traj_bytes * (size_t)cnt);
+        else
+            for (int64_t j = 0; j < cnt; j++) std::memcpy(dst + traj_bytes * (size_t)(j * sh.step), src + traj_bytes * (size_t)j, traj_bytes);
         return QSIM_OK;
     };
+    int last = -1;
     for (int k = 0; k < n_chunks; k++) {
         const int64_t lo = (int64_t)k * per_chunk, cnt = std::min<int64_t>(per_chunk, n_traj - lo);
         if (cnt <= 0) break;
@@ -1461,18 +1490,18 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         if (k == 0) CU(cudaEventRecord(c->ev0, streams[0]));
         CU(pl.kv->launch(ak, grid_k, pl.block, pl.smem, streams[k % 2]));
         c->launches++;
+        CU(cudaEventRecord(c->ev1, streams[k % 2]));   // (kept from the last chunk: end of the kernels)
+        CU(cudaMemcpyAsync(c->stage[k % 2], ak.out, traj_bytes * (size_t)cnt, cudaMemcpyDeviceToHost, streams[k % 2]));
+        CU(cudaEventRecord(c->ev_copy[k % 2], streams[k % 2]));
+        last = k;
         if (k >= 1)
-            if (int rc = copy_out(k - 1)) return rc;
+            if (int rc = move_out(k - 1)) return rc;
     }
-    {
-        const int last = (int)((n_traj + per_chunk - 1) / per_chunk) - 1;
-        CU(cudaEventRecord(c->ev1, streams[last % 2]));
-        c->timed = true;
-        if (int rc = copy_out(last)) return rc;
-        if (stats)
-            CU(cudaMemcpy2D(stats + sh.first, sizeof(qsim_traj_stats) * (size_t)sh.step, c->stats.p, sizeof(qsim_traj_stats),
-                            sizeof(qsim_traj_stats), (size_t)n_traj, cudaMemcpyDeviceToHost));
-    }
+    c->timed = true;
+    if (int rc = move_out(last)) return rc;
+    if (stats)
+        CU(cudaMemcpy2D(stats + sh.first, sizeof(qsim_traj_stats) * (size_t)sh.step, c->stats.p, sizeof(qsim_traj_stats),
+                        sizeof(qsim_traj_stats), (size_t)n_traj, cudaMemcpyDeviceToHost));
     return QSIM_OK;
 }
 
@@ -1625,5 +1654,34 @@ extern "C" int qsim_peak_fp64(qsim_ctx *c, double ms_target, double *tflops) {
     cudaEventDestroy(e1);
     cudaFree(sink);
     *tflops = best;
+    return QSIM_OK;
+}
+
+// ---------------------------------------------------------------- hooks for qsim_floquet.cu
+int qsim_internal_fail(int code, const std::string &msg) { return fail(code, msg); }
+void qsim_internal_count_launch(qsim_ctx *c) { c->launches++; }
+int qsim_internal_floquet_buffers(qsim_ctx *c, size_t seg_bytes, size_t work_bytes, size_t idx_bytes, void **seg, void **work,
+                                  void **idx, cudaStream_t *stream, int *device) {
+    CU(cudaSetDevice(c->device));
+    CU(c->fl_seg.reserve(seg_bytes));
+    CU(c->fl_work.reserve(work_bytes));
+    CU(c->fl_idx.reserve(idx_bytes));
+    *seg = c->fl_seg.p;
+    *work = c->fl_work.p;
+    *idx = c->fl_idx.p;
+    *stream = c->stream;
+    *device = c->device;
+    return QSIM_OK;
+}
+int qsim_internal_solve_to_device(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj, const double *params, const double *ts,
+                                  int n_ts, int64_t ts_stride, const qsim_solver_opts *opts, void *d_out, qsim_traj_stats *stats) {
+    qsim_solver_opts o = *opts;
+    o.flags |= QSIM_FLAG_INTERNAL_DEVICE_OUT;
+    return solve_common(c, p, which, n_traj, params, ts, n_ts, ts_stride, nullptr, 0, &o, (double *)d_out, stats);
+}
+extern "C" int qsim_problem_dims(qsim_problem *p, int *d, int *n_params) {
+    if (!p) return fail(QSIM_ERR_ARG, "prob is NULL");
+    if (d) *d = p->d;
+    if (n_params) *n_params = p->n_params;
     return QSIM_OK;
 }

@@ -22,5 +22,5 @@ from .time_evolution import unitary_propagator, unitary_state, me_propagator, me
 from .sweep import shard_indices, shard_params, scatter_back, gather_results
 from .postprocess import (populations, subspace_indices, subspace_block, average_gate_fidelity, superoperator,
                           kraus_mix)
-from .floquet import (floquet_propagator, floquet_rise_fall_propagator, choose_times_floquet,
+from .floquet import (floquet_propagator, floquet_rise_fall_propagator, floquet_sweep, choose_times_floquet,
                       decompose_times_floquet, unique_tol)

@@ -24,7 +24,7 @@ EXPORTS = [
     "qsim_problem_finalize",
     "qsim_problem_eval", "qsim_unitary_propagator", "qsim_unitary_state", "qsim_me_propagator", "qsim_me_state",
     "qsim_solve_selected", "qsim_solve_multi", "qsim_problem_flops_per_rhs", "qsim_problem_kernel_name", "qsim_launch_count",
-    "qsim_peak_fp64", "qsim_last_kernel_ms", "qsim_problem_plan_info",
+    "qsim_peak_fp64", "qsim_last_kernel_ms", "qsim_problem_plan_info", "qsim_problem_dims", "qsim_floquet_propagator",
 ]
 
 
@@ -82,6 +82,9 @@ def lib():
     L.qsim_launch_count.restype = C.c_int64
     L.qsim_peak_fp64.argtypes = [vp, C.c_double, dp]
     L.qsim_last_kernel_ms.argtypes = [vp, dp]
+    L.qsim_problem_dims.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.qsim_floquet_propagator.argtypes = [vp, vp, C.c_int, C.c_int64, vp, vp, C.c_int, C.c_int64, vp, C.c_int64, C.c_double,
+                                          C.c_double, C.c_double, C.POINTER(_abi.SolverOpts), vp, vp]
     L.qsim_problem_plan_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
     _lib = L
     return L
@@ -262,6 +265,45 @@ class Problem:
     def state_shape(self, which: int):
         d = self.d
         return {0: (d, d), 1: (d,), 2: (d * d, d * d), 3: (d, d)}[which]
+
+    def floquet(self, which, ts, t_period, params=None, rise_time: float = 0.0, fall_time: float = 0.0, rtol: float = 0.0,
+                opts=None, ctx: Optional["Context"] = None, out=None):
+        """Floquet propagation of the whole sweep in one call (qsim_floquet_propagator): the system of trajectory i
+        is periodic with t_period[i] (a scalar: one period for all) between ts[0] + rise_time and ts[-1] - fall_time.
+        Returns (out[n_traj, n_ts, n, n] indexed [row, col], stats)."""
+        which = WHICH.get(which, which)
+        if which not in (0, 2):
+            raise ValueError("Floquet propagation applies to unitary_propagator and me_propagator")
+        ctx = ctx or default_context()
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        if params is None:
+            params = np.zeros((1, max(self.n_params, 1)))
+        params = np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
+        n_traj = params.shape[0]
+        if self.n_params and params.shape[1] != self.n_params:
+            raise ValueError(f"params needs {self.n_params} columns")
+        if ts.ndim == 2:
+            if ts.shape[0] != n_traj:
+                raise ValueError("per-trajectory ts needs one row per trajectory")
+            n_ts, ts_stride = ts.shape[1], ts.shape[1]
+        else:
+            n_ts, ts_stride = ts.shape[0], 0
+        per = np.ascontiguousarray(np.atleast_1d(t_period), dtype=np.float64)
+        if per.shape not in ((1,), (n_traj,)):
+            raise ValueError("t_period must be a scalar or one period per trajectory")
+        shape = self.state_shape(which)
+        n = int(np.prod(shape))
+        if out is None:
+            out = np.empty((n_traj, n_ts, n), dtype=np.complex128)
+        elif out.shape != (n_traj, n_ts, n) or out.dtype != np.complex128 or not out.flags.c_contiguous:
+            raise ValueError("out buffer has the wrong shape / dtype / layout")
+        stats = np.zeros(n_traj, dtype=_abi.STATS_DTYPE)
+        o = opts if opts is not None else _abi.default_opts()
+        check(lib().qsim_floquet_propagator(ctx._h, self._h, which, n_traj, params.ctypes.data, ts.ctypes.data, n_ts, ts_stride,
+                                            per.ctypes.data, 0 if per.shape[0] == 1 and n_traj != 1 else (1 if per.shape[0] > 1 else 0),
+                                            float(rise_time), float(fall_time), float(rtol), C.byref(o), out.ctypes.data,
+                                            stats.ctypes.data))
+        return out.reshape(n_traj, n_ts, shape[1], shape[0]).transpose(0, 1, 3, 2), stats
 
     # -- raw call on caller-provided buffers (host numpy arrays, or device pointers as ints) --
     def solve_raw(self, ctx: Context, which: int, n_traj: int, params_ptr, ts_ptr, n_ts: int, ts_stride: int,

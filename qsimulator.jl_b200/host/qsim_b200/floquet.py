@@ -1,112 +1,149 @@
-"""Floquet wrappers: the main in-package callers of the hot path.
+"""Floquet propagation: U(n*tau + dt) = U(dt) U(tau)^n for tau-periodic systems.
 
-Host-side mirror of /root/reference/src/time_evolution.jl:166-360:
-  floquet_propagator            :188-220   U(n*tau + dt) = U(dt) U(tau)^n for a tau-periodic system
-  choose_times_floquet          :238-252
-  decompose_times_floquet       :275-293
-  floquet_rise_fall_propagator  :312-338   non-periodic rise / fall segments around a periodic middle
-  unique_tol                    :355-360
-A `propagator_func` is any callable (cqs, ts) -> sequence of propagators with the identity at ts[0]
-(`unitary_propagator`, `me_propagator`); the wrappers only reorganise which times it is asked for and
-combine the results with matrix powers and products, exactly like the reference.
+Same names and meaning as /root/reference/src/time_evolution.jl:166-360
+  floquet_propagator(propagator_func, t_period[, rtol])                     :188-228
+  floquet_rise_fall_propagator(propagator_func, t_period, rise, fall[, rtol]) :312-346
+  choose_times_floquet / decompose_times_floquet / unique_tol               :238-252, 275-300, 355-360
+but organised for sweeps.  The reference wraps a propagator function and, per system, runs up to three solves
+and a running matrix product on the host.  Here
+
+  floquet_sweep(cqs, ts, t_period, params=..., rise_time=..., fall_time=...)
+
+does a whole parameter sweep in ONE library call (qsim_floquet_propagator, csrc/qsim_floquet.cu): every segment of
+every sweep point is a trajectory of a single batched solver launch with per-trajectory save grids -- each point
+may have its own period, e.g. when the drive frequency is a sweep axis -- and the powers and products are formed
+on the device; only the requested propagators come back.  The reference-style wrappers returned by
+`floquet_propagator(unitary_propagator, tau)` route to that call when they wrap this package's
+`unitary_propagator` / `me_propagator`, and otherwise (any callable (cqs, ts) -> propagators, like the reference
+allows) combine the callable's results with batched numpy products.
 """
 from __future__ import annotations
 
 import math
-from typing import Callable, List, Sequence, Tuple
+from typing import Callable, Optional, Sequence, Tuple
 
 import numpy as np
 
 
+# ---- time bookkeeping (host, O(n_ts)) ------------------------------------------------------------------------
 def unique_tol(ts: Sequence[float], dt: float) -> Tuple[np.ndarray, np.ndarray]:
-    """Values rounded to multiples of `dt`, de-duplicated in first-seen order, and for every input the
-    index of its representative (time_evolution.jl:355-360)."""
-    vals = np.round(np.asarray(ts, dtype=float) / dt) * dt
-    unique_vals: List[float] = []
-    inds = np.empty(len(vals), dtype=int)
-    for i, v in enumerate(vals):
-        for j, uv in enumerate(unique_vals):
-            if uv == v:
-                inds[i] = j
-                break
-        else:
-            unique_vals.append(v)
-            inds[i] = len(unique_vals) - 1
-    return np.array(unique_vals), inds
+    """Values snapped to the grid of spacing `dt`, de-duplicated in first-seen order, and for every input the index
+    of its representative: a[inds] approximates ts to within dt/2 (time_evolution.jl:355-360)."""
+    snapped = np.round(np.asarray(ts, dtype=float) / dt) * dt
+    sorted_vals, first_seen, inverse = np.unique(snapped, return_index=True, return_inverse=True)
+    order = np.argsort(first_seen, kind="stable")            # np.unique sorts by value: restore first-seen order
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    return sorted_vals[order], rank[inverse]
 
 
-def decompose_times_floquet(ts: Sequence[float], t_period: float, rtol: float = None):
-    """ts = quotients * t_period + unique_remainders[unique_inds], unique_remainders[0] == ts[0]
-    (time_evolution.jl:275-293)."""
-    if rtol is None:
-        rtol = float(np.spacing(t_period))      # eps(t_period)
+def _eps(x: float) -> float:
+    return float(np.spacing(abs(x)))
+
+
+def decompose_times_floquet(ts: Sequence[float], t_period: float, rtol: Optional[float] = None):
+    """ts = quotients * t_period + unique_remainders[unique_inds] with as few remainders as possible, sorted, and
+    unique_remainders[0] == ts[0] (time_evolution.jl:275-300; rtol defaults to eps(t_period))."""
+    rtol = _eps(t_period) if rtol is None else rtol
     ts = np.asarray(ts, dtype=float)
-    quotients = np.floor_divide(ts - ts[0], t_period)
-    remainders = np.mod(ts - ts[0], t_period) + ts[0]
-    unique_remainders, unique_inds = unique_tol(remainders, rtol * t_period)
-    sort_inds = np.argsort(unique_remainders, kind="stable")
-    unique_remainders = unique_remainders[sort_inds]
-    unique_inds = np.argsort(sort_inds, kind="stable")[unique_inds]
-    return quotients, unique_remainders, unique_inds
+    shifted = ts - ts[0]
+    remainders = np.mod(shifted, t_period)
+    quotients = np.round((shifted - remainders) / t_period)   # fld, consistent with mod by construction
+    vals, inds = unique_tol(remainders + ts[0], rtol * t_period)
+    order = np.argsort(vals, kind="stable")
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    return quotients, vals[order], rank[inds]
 
 
 def choose_times_floquet(center: float, width: float, t_period: float, dt: float) -> np.ndarray:
-    """Times that maximise remainder overlap for Floquet integration; `center` is one of them
-    (time_evolution.jl:238-252)."""
+    """An odd number of equally spaced times around `center` (which is one of them) whose spacing divides the
+    period, so that few distinct remainders occur (time_evolution.jl:238-252)."""
     assert width >= 0 and dt >= 0
     if width == 0 or dt == 0:
         return np.array([center], dtype=float)
-    dt = t_period / math.ceil(t_period / dt)
-    num_times = int(math.floor(width / dt))
-    num_times += 1 if num_times % 2 == 0 else 0
-    width = dt * num_times
-    times = np.linspace(center - width / 2, center + width / 2, num_times)
-    times[int(math.ceil(num_times / 2)) - 1] = center
+    step = t_period / math.ceil(t_period / dt)
+    count = int(math.floor(width / step))
+    count += (count + 1) % 2                                  # odd, for symmetry about the centre
+    half = step * count / 2
+    times = np.linspace(center - half, center + half, count)
+    times[(count - 1) // 2] = center
     return times
 
 
-def floquet_propagator(propagator_func: Callable, t_period: float, rtol: float = None) -> Callable:
-    """A propagator function for systems periodic with `t_period` (time_evolution.jl:188-220)."""
-    if rtol is None:
-        rtol = float(np.spacing(t_period))
+# ---- the sweep-wide call -------------------------------------------------------------------------------------
+def floquet_sweep(cqs, ts, t_period, params=None, which: str = "unitary_propagator", rise_time: float = 0.0,
+                  fall_time: float = 0.0, rtol: Optional[float] = None, opts=None, ctx=None, return_stats: bool = False):
+    """Propagators at every ts[k] for systems that are periodic with `t_period` (a scalar, or one period per sweep
+    point) between ts[0] + rise_time and ts[-1] - fall_time.  Returns [n_ts, n, n], or [n_traj, n_ts, n, n] with
+    `params`, n = d (unitary_propagator) or d^2 (me_propagator)."""
+    from .time_evolution import _problem_for
+    ts = np.asarray(ts, dtype=np.float64)
+    assert np.all(np.diff(ts, axis=-1) >= 0), "issorted(ts)"
+    n_params = None if params is None else np.atleast_2d(params).shape[1]
+    prob = _problem_for(cqs, n_params)
+    out, stats = prob.floquet(which, ts, t_period, params=params, rise_time=rise_time, fall_time=fall_time,
+                              rtol=0.0 if rtol is None else rtol, opts=opts, ctx=ctx)
+    res = out[0] if params is None else out
+    return (res, stats) if return_stats else res
 
-    def p(cqs, ts):
+
+# ---- reference-style wrappers --------------------------------------------------------------------------------
+def _library_entry(propagator_func) -> Optional[str]:
+    from . import time_evolution as te
+    if propagator_func is te.unitary_propagator:
+        return "unitary_propagator"
+    if propagator_func is te.me_propagator:
+        return "me_propagator"
+    return None
+
+
+def _compose_periodic(propagator_func: Callable, cqs, ts: np.ndarray, t_period: float, rtol: float) -> np.ndarray:
+    """Generic path for an arbitrary propagator function: one call for the unique remainders plus one period, then
+    all powers and products at once (stacked matrices)."""
+    quotients, remainders, inds = decompose_times_floquet(ts, t_period, rtol)
+    stack = np.asarray(propagator_func(cqs, np.concatenate([remainders, [t_period + ts[0]]])))
+    u_period = stack[-1]
+    levels = np.unique(quotients).astype(int)
+    powers = np.stack([np.linalg.matrix_power(u_period, int(v)) for v in levels])
+    return stack[inds] @ powers[np.searchsorted(levels, quotients.astype(int))]
+
+
+def floquet_propagator(propagator_func: Callable, t_period: float, rtol: Optional[float] = None) -> Callable:
+    """A propagator function for systems periodic with `t_period` (time_evolution.jl:188-228)."""
+    entry = _library_entry(propagator_func)
+    tol = _eps(t_period) if rtol is None else rtol
+
+    def p(cqs, ts, **kw):
         ts = np.asarray(ts, dtype=float)
         assert np.all(np.diff(ts) >= 0), "issorted(ts)"
-        quotients, unique_remainders, unique_inds = decompose_times_floquet(ts, t_period, rtol)
-        us_remainders = propagator_func(cqs, np.concatenate([unique_remainders, [t_period + ts[0]]]))
-        u_period = np.asarray(us_remainders[-1])
-        us = []
-        quotient = quotients[0]
-        u_floquet = np.linalg.matrix_power(u_period, int(quotient))
-        for i in range(len(ts)):
-            if quotients[i] > quotient:
-                u_floquet = u_floquet @ np.linalg.matrix_power(u_period, int(quotients[i] - quotient))
-                quotient = quotients[i]
-            us.append(np.asarray(us_remainders[unique_inds[i]]) @ u_floquet)
-        return us
+        if entry is not None:
+            return floquet_sweep(cqs, ts, t_period, which=entry, rtol=tol, **kw)
+        return _compose_periodic(propagator_func, cqs, ts, t_period, tol)
 
     return p
 
 
 def floquet_rise_fall_propagator(propagator_func: Callable, t_period: float, rise_time: float, fall_time: float,
-                                 rtol: float = None) -> Callable:
-    """Floquet evolution with non-periodic rise and fall segments (time_evolution.jl:312-338)."""
+                                 rtol: Optional[float] = None) -> Callable:
+    """Floquet evolution between a non-periodic rise at the start of `ts` and a fall at its end
+    (time_evolution.jl:312-346)."""
     assert t_period >= 0 and rise_time >= 0 and fall_time >= 0
-    floquet_prop = floquet_propagator(propagator_func, t_period, rtol)
+    entry = _library_entry(propagator_func)
+    tol = _eps(t_period) if rtol is None else rtol
 
-    def p(cqs, ts):
+    def p(cqs, ts, **kw):
         ts = np.asarray(ts, dtype=float)
         t0, t1 = ts[0] + rise_time, ts[-1] - fall_time
         assert t0 <= t1
-        us_risetime = propagator_func(cqs, np.concatenate([ts[ts < t0], [t0]]))
-        u0 = np.asarray(us_risetime[-1])
-        us = [np.asarray(u) for u in us_risetime[:-1]]
-        us_floquet = floquet_prop(cqs, np.concatenate([[t0], ts[(t0 <= ts) & (ts <= t1)], [t1]]))
-        u1 = us_floquet[-1] @ u0
-        us.extend(u @ u0 for u in us_floquet[1:-1])
-        us_falltime = propagator_func(cqs, np.concatenate([[t1], ts[t1 < ts]]))
-        us.extend(np.asarray(u) @ u1 for u in us_falltime[1:])
-        return us
+        if entry is not None:
+            return floquet_sweep(cqs, ts, t_period, which=entry, rise_time=rise_time, fall_time=fall_time, rtol=tol, **kw)
+        before, after = ts < t0, ts > t1
+        rise = np.asarray(propagator_func(cqs, np.concatenate([ts[before], [t0]])))
+        middle = _compose_periodic(propagator_func, cqs, np.concatenate([[t0], ts[~before & ~after], [t1]]), t_period, tol)
+        fall = np.asarray(propagator_func(cqs, np.concatenate([[t1], ts[after]])))
+        u_t0 = rise[-1]
+        u_t1 = middle[-1] @ u_t0
+        return np.concatenate([rise[:-1], middle[1:-1] @ u_t0, fall[1:] @ u_t1])
 
     return p

@@ -105,3 +105,78 @@ def test_floquet_with_pulseshape_gpu():
         assert np.linalg.norm(uf - ud) <= 1e-5 * max(np.linalg.norm(uf), np.linalg.norm(ud))
     want, _ = co.OracleProblem(cqs).solve(co.UNITARY_PROPAGATOR, times)
     assert np.max(np.abs(us_direct - want[0]) / np.maximum(np.abs(want[0]), 1e-3)) <= 1e-8
+
+
+@pytest.mark.gpu
+def test_floquet_device_path_equals_host_composition():
+    """The one-call device path (segments in one batched launch, powers and products on the device) against the
+    generic composition of the same library solves on the host: same segments, so agreement to rounding."""
+    from qsim_b200 import unitary_propagator
+    cqs, t_final, t_period, rise_time = _pulseshape_system()
+    times = np.linspace(0.0, t_final, 123)
+    dev = floquet_rise_fall_propagator(unitary_propagator, t_period, rise_time, rise_time)(cqs, times)
+    host = floquet_rise_fall_propagator(lambda c, t: unitary_propagator(c, t), t_period, rise_time, rise_time)(cqs, times)
+    assert dev.shape == host.shape == (123, 9, 9)
+    assert np.max(np.abs(dev - host)) < 1e-11
+    # plain floquet_propagator on a strictly periodic system (integration_tests.jl:66-75)
+    cq = _rabi()
+    ts = np.linspace(0, 40, 41)
+    dev = floquet_propagator(unitary_propagator, 1 / 5.0)(cq, ts)
+    host = floquet_propagator(lambda c, t: unitary_propagator(c, t), 1 / 5.0)(cq, ts)
+    assert np.max(np.abs(dev - host)) < 1e-11
+    direct = unitary_propagator(cq, ts)
+    assert np.max(np.abs(dev - direct)) < 2e-4
+
+
+@pytest.mark.gpu
+def test_floquet_sweep_cfg2_per_trajectory_periods():
+    """cfg2 through one period + powers: the drive frequency is a sweep axis, so every point has its own period
+    1/f.  200 ns of lab-frame evolution become one 7.5-9.1 ns period per point; agreement with the direct solve at
+    the reference's own Floquet tolerance (test_time_evolution.jl:118: 1e-5 per matrix), speed-up printed."""
+    import time
+    from qsim_b200 import Context, floquet_sweep, unitary_propagator
+    from qsim_b200 import workloads as W
+    cqs, params, _, _ = W.config("cfg2")
+    pr = np.ascontiguousarray(params[np.linspace(0, len(params) - 1, 296).astype(int)])
+    ts = np.arange(0.0, 201.0, 4.0)
+    ctx = Context(0)
+    floquet_sweep(cqs, ts[:3], 1.0 / pr[:4, 1], params=pr[:4], ctx=ctx)      # builds the device tables
+    t0 = time.perf_counter()
+    fl, st = floquet_sweep(cqs, ts, 1.0 / pr[:, 1], params=pr, ctx=ctx, return_stats=True)
+    t_fl = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    direct, sd = unitary_propagator(cqs, ts, params=pr, ctx=ctx, return_stats=True)
+    t_direct = time.perf_counter() - t0
+    assert fl.shape == direct.shape == (296, len(ts), 9, 9)
+    assert np.all(st["retcode"] == 0)
+    for a, b in zip(fl.reshape(-1, 9, 9), direct.reshape(-1, 9, 9)):
+        assert np.linalg.norm(a - b) <= 1e-5 * max(np.linalg.norm(a), np.linalg.norm(b))
+    assert st["n_accept"].sum() < 0.1 * sd["n_accept"].sum()
+    print(f"cfg2 Floquet sweep: {t_direct / t_fl:.1f}x faster than the direct solve "
+          f"({int(sd['n_accept'].sum())} -> {int(st['n_accept'].sum())} steps), max |diff| {np.abs(fl - direct).max():.2e}")
+
+
+@pytest.mark.gpu
+def test_floquet_me_propagator():
+    """The wrappers compose whatever the propagator function returns: superoperators of a driven, decaying transmon."""
+    from qsim_b200 import add_lindblad, decay, floquet_sweep, me_propagator
+    q0 = DuffingTransmon("q0", 3, DuffingSpec(5.0, -0.2))
+    cqs = CompositeQSystem([q0])
+    add_hamiltonian(cqs, q0)
+    add_hamiltonian(cqs, dipole_drive(q0, Cos(amp=0.02, freq=5.0)), q0)
+    add_lindblad(cqs, decay(q0, 1e-3), [q0])
+    ts = np.linspace(0.0, 12.0, 25)
+    # 60 periods: the per-period solver error adds up coherently in U(tau)^n, so compare at tight solver tolerances
+    # (the composition itself is exact) and, at the reference's tolerances, at the level those imply
+    from qsim_b200 import _abi
+    tight = _abi.default_opts()
+    tight.reltol, tight.abstol = 1e-11, 1e-13
+    fl = floquet_sweep(cqs, ts, 1 / 5.0, which="me_propagator", opts=tight)
+    direct = me_propagator(cqs, ts, opts=tight)
+    assert fl.shape == (25, 9, 9)
+    for a, b in zip(fl, direct):
+        assert np.linalg.norm(a - b) <= 1e-8 * max(np.linalg.norm(a), np.linalg.norm(b))
+    fl = floquet_sweep(cqs, ts, 1 / 5.0, which="me_propagator")
+    direct = me_propagator(cqs, ts)
+    for a, b in zip(fl, direct):
+        assert np.linalg.norm(a - b) <= 5e-4 * max(np.linalg.norm(a), np.linalg.norm(b))
