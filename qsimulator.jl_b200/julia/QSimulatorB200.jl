@@ -13,11 +13,21 @@
 # (src/composite_systems.jl:40) still dispatches on them and `ham(t)` still returns the matrix the
 # reference closure would, so the stock CPU solver keeps working on the same CompositeQSystem.
 #
+# Beyond the reference's surface (all through the same C ABI):
+#   tabulated(f, t0, t1)                      any real closure as a drive envelope (qsim_problem_add_table)
+#   select = [(row, col), ...], abs2 = true   only those entries (or their squared moduli) of every result
+#                                             leave the device (qsim_solve_selected)
+#   devices = [0, 1, ...]                     one call fans the sweep out over several GPUs, block-cyclically
+#                                             (qsim_solve_multi; no Julia threads involved)
+#   floquet_propagator(unitary_propagator, tau) / floquet_rise_fall_propagator(...)
+#                                             src/time_evolution.jl:188-346 as ONE batched call (qsim_floquet_propagator)
+#
 # NOTE: Julia is not installed in the build/test image of this repository; this file is the binding a
 # maintainer adds on the reference side (see INTEGRATION.md) and has been checked by reading only.
 module QSimulatorB200
 
 using QSimulator
+using Libdl
 using LinearAlgebra: I
 import QSimulator: CompositeQSystem, QSystem, DuffingTransmon, PerturbativeTransmon, RotatingFrameSystem,
                    dimension, spec, hamiltonian, raising, lowering, X, Y, embed
@@ -25,8 +35,15 @@ import QSimulator: CompositeQSystem, QSystem, DuffingTransmon, PerturbativeTrans
 export Param, Signal, CosSignal, SinSignal, ConstSignal, gaussian, erf_squared
 export dipole_drive_b200, rwa_dipole_b200, parametric_drive_b200, xy_exchange_drive_b200, ScaledLindblad
 export unitary_propagator, unitary_state, me_propagator, me_state
+export tabulated, floquet_propagator, floquet_rise_fall_propagator
 
 const libqsim = get(ENV, "QSIM_B200_LIB", joinpath(@__DIR__, "..", "lib", "libqsim_b200.so"))
+# ccall needs a constant (symbol, library) pair; entry points chosen at run time go through dlsym instead
+const LIBHANDLE = Ref{Ptr{Cvoid}}(C_NULL)
+function fptr(name::Symbol)
+    LIBHANDLE[] == C_NULL && (LIBHANDLE[] = Libdl.dlopen(libqsim))
+    return Libdl.dlsym(LIBHANDLE[], name)
+end
 
 # ---- mirrors of the C structs (include/qsim_b200.h) ---------------------------------------
 struct Slot
@@ -70,14 +87,25 @@ end
 
 # ---- drive descriptors ---------------------------------------------------------------------
 const CARRIER_NONE, CARRIER_COS, CARRIER_SIN = Int32(0), Int32(1), Int32(2)
-const ENV_NONE, ENV_GAUSSIAN, ENV_ERF_SQUARED = Int32(0), Int32(1), Int32(2)
+const ENV_NONE, ENV_GAUSSIAN, ENV_ERF_SQUARED, ENV_TABLE = Int32(0), Int32(1), Int32(2), Int32(3)
+
+"A real function of time as a piecewise Chebyshev series: n_seg equal segments over [t_start, t_end], n_coef
+coefficients each (qsim_problem_add_table); `f` is kept so that the signal still calls the closure on the host."
+struct Table
+    t_start::Float64
+    t_end::Float64
+    coef::Matrix{Float64}      # n_coef x n_seg (column = one segment: row-major [n_seg][n_coef] for the C side)
+    f::Function
+end
 
 "Real scalar drive s(t); callable like the closures the reference passes to its drive factories."
 struct Signal <: Function
     carrier::Int32; envelope::Int32; blend::Int32
     offset::Scalar; amp::Scalar; freq::Scalar; phase::Scalar
     t1::Scalar; t2::Scalar; sigma::Scalar; rest::Scalar
+    table::Union{Nothing,Table}
 end
+Signal(c, e, b, offset, amp, freq, phase, t1, t2, sigma, rest) = Signal(c, e, b, offset, amp, freq, phase, t1, t2, sigma, rest, nothing)
 CosSignal(amp, freq; phase=0.0, offset=0.0) = Signal(CARRIER_COS, ENV_NONE, 0, offset, amp, freq, phase, 0.0, 0.0, 1.0, 0.0)
 SinSignal(amp, freq; phase=0.0, offset=0.0) = Signal(CARRIER_SIN, ENV_NONE, 0, offset, amp, freq, phase, 0.0, 0.0, 1.0, 0.0)
 ConstSignal(v) = Signal(CARRIER_NONE, ENV_NONE, 0, 0.0, v, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0)
@@ -87,6 +115,54 @@ erf_squared(s::Signal, t1, t2, sigma) =
     Signal(s.carrier, ENV_ERF_SQUARED, 0, s.offset, s.amp, s.freq, s.phase, t1, t2, sigma, s.rest)
 erf_squared(s::Signal, t1, t2, sigma, rest) =
     Signal(s.carrier, ENV_ERF_SQUARED, 1, s.offset, s.amp, s.freq, s.phase, t1, t2, sigma, rest)
+
+"Clenshaw evaluation of a Table at time t (the same lookup the device does; constant continuation outside)."
+function (tb::Table)(t::Real)
+    n_coef, n_seg = size(tb.coef)
+    u = (t - tb.t_start) * (n_seg / (tb.t_end - tb.t_start))
+    k = clamp(floor(Int, u), 0, n_seg - 1)
+    x = clamp(2.0 * (u - k) - 1.0, -1.0, 1.0)
+    b1 = 0.0; b2 = 0.0
+    for j in n_coef:-1:2
+        b1, b2 = 2.0 * x * b1 + (tb.coef[j, k + 1] - b2), b1
+    end
+    return x * b1 + (tb.coef[1, k + 1] - b2)
+end
+
+"""
+    tabulated(f, t_start, t_end; amp=1.0, offset=0.0, n_coef=12, tol=1e-14)
+
+`t -> offset + amp*f(t)` for an arbitrary real closure `f` on [t_start, t_end] -- the generic path for the opaque
+drive closures of src/composite_systems.jl:40-50.  `f` is sampled into a piecewise Chebyshev series whose segment
+count doubles until it reproduces `f` at 2*n_coef off-node points per segment to `tol * max|f|`.
+"""
+function tabulated(f::Function, t_start::Real, t_end::Real; amp=1.0, offset=0.0, n_coef::Int=12, tol::Real=1e-14)
+    N = n_coef
+    nodes = [cos(pi * (j + 0.5) / N) for j in 0:N-1]
+    dct = [(k == 0 ? 1.0 : 2.0) / N * cos(pi * k * (j + 0.5) / N) for k in 0:N-1, j in 0:N-1]
+    chk = [cos(pi * (j + 0.25) / (2N)) for j in 0:2N-1]
+    n_seg = 1
+    while true
+        h = (t_end - t_start) / n_seg
+        coef = Matrix{Float64}(undef, N, n_seg)
+        for s in 1:n_seg
+            left = t_start + h * (s - 1)
+            coef[:, s] = dct * [Float64(f(left + 0.5 * h * (1.0 + x))) for x in nodes]
+        end
+        tb = Table(Float64(t_start), Float64(t_end), coef, f)
+        err = 0.0; scale = 1e-300
+        for s in 1:n_seg, x in chk
+            t = t_start + h * (s - 1) + 0.5 * h * (1.0 + x)
+            want = Float64(f(t))
+            err = max(err, abs(tb(t) - want)); scale = max(scale, abs(want))
+        end
+        if err <= tol * scale || n_seg >= (1 << 16)
+            err <= 1e-9 * scale || error("could not tabulate the function to 1e-9 with $n_seg segments")
+            return Signal(CARRIER_NONE, ENV_TABLE, 0, offset, amp, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, tb)
+        end
+        n_seg *= 2
+    end
+end
 
 val(x::Real, row) = Float64(x)
 val(p::Param, row) = row === nothing ? error("Param($(p.index)) needs a parameter row") : Float64(row[p.index])
@@ -101,19 +177,22 @@ function (s::Signal)(t::Real, row=nothing)
     elseif s.envelope == ENV_ERF_SQUARED
         sg = val(s.sigma, row)
         env = 0.5 * (erf_((t - val(s.t1, row)) / sg) - erf_((t - val(s.t2, row)) / sg))
+    elseif s.envelope == ENV_TABLE
+        env = Float64(s.table.f(t))     # the closure itself on the host, like the reference
     end
     s.blend == 0 && return val(s.offset, row) + val(s.amp, row) * env * car
     return env * (val(s.offset, row) + val(s.amp, row) * car) + (1 - env) * val(s.rest, row)
 end
 erf_(x) = ccall(:erf, Float64, (Float64,), x)   # libm, avoids a SpecialFunctions dependency
 
-csignal(s::Signal) = CSignal(s.carrier, s.envelope, s.blend, 0, Slot(s.offset), Slot(s.amp), Slot(s.freq),
-                             Slot(s.phase), Slot(s.t1), Slot(s.t2), Slot(s.sigma), Slot(s.rest))
+# table_ids: objectid(Table) -> id returned by qsim_problem_add_table for the problem being built
+csignal(s::Signal, table_ids=nothing) =
+    CSignal(s.carrier, s.envelope, s.blend, s.table === nothing ? Int32(0) : Int32(table_ids[objectid(s.table)]),
+            Slot(s.offset), Slot(s.amp), Slot(s.freq), Slot(s.phase), Slot(s.t1), Slot(s.t2), Slot(s.sigma), Slot(s.rest))
 as_signal(s::Signal) = s
 as_signal(x::Scalar) = ConstSignal(x)
-# Arbitrary closures reach the library as tabulated envelopes (qsim_problem_add_table + ENV_TABLE = 3; the Python
-# mirror's `tabulated(f, t0, t1)` shows the sampling).  This shim does not wire that path yet.
-as_signal(::Function) = error("opaque closures cannot cross the C ABI: pass a Signal (CosSignal/SinSignal/...)")
+# Arbitrary closures reach the library as tabulated envelopes: wrap them with tabulated(f, t_start, t_end).
+as_signal(::Function) = error("opaque closures cannot cross the C ABI as they are: pass tabulated(f, t_start, t_end) or a Signal (CosSignal/SinSignal/...)")
 
 # One lowered qsim_term before embedding
 struct Lowered
@@ -224,10 +303,28 @@ function Problem(cqs::CompositeQSystem, n_params::Integer)
     finalizer(p -> ccall((:qsim_problem_destroy, libqsim), Cint, (Ptr{Cvoid},), p.handle), prob)
     h0 = Matrix{ComplexF64}(hamiltonian(cqs))                       # src/composite_systems.jl:151-157
     check(ccall((:qsim_problem_set_h0, libqsim), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), prob.handle, h0))
+    # tabulated envelopes: one qsim_problem_add_table per distinct Table, ids handed to the signals below
+    table_ids = Dict{UInt,Int32}()
+    function register(sig::Signal)
+        tb = sig.table
+        (tb === nothing || haskey(table_ids, objectid(tb))) && return
+        n_coef, n_seg = size(tb.coef)
+        id = Ref{Int32}(0)
+        check(ccall((:qsim_problem_add_table, libqsim), Cint,
+                    (Ptr{Cvoid}, Cdouble, Cdouble, Cint, Cint, Ptr{Float64}, Ref{Int32}),
+                    prob.handle, tb.t_start, tb.t_end, n_seg, n_coef, tb.coef, id))
+        table_ids[objectid(tb)] = id[]
+    end
+    for (ham, _) in cqs.parametric_Hs
+        ham isa ParametricHamiltonian && foreach(lo -> register(lo.signal), ham.lowered)
+    end
+    for (lf, _) in cqs.parametric_Ls
+        lf isa ScaledLindblad && register(lf.scale)
+    end
     for (ham, idxs) in cqs.parametric_Hs                             # src/composite_systems.jl:40-50
         ham isa ParametricHamiltonian || error("parametric Hamiltonian is an opaque closure; use the *_b200 drive factories")
         for lo in ham.lowered
-            term = Ref(CTerm(lo.kind, Int32(lo.num_terms), csignal(lo.signal), Slot(lo.rate), Slot(lo.anharm),
+            term = Ref(CTerm(lo.kind, Int32(lo.num_terms), csignal(lo.signal, table_ids), Slot(lo.rate), Slot(lo.anharm),
                              Slot(lo.rot), Slot(lo.EC), Slot(lo.EJ1), Slot(lo.EJ2)))
             if lo.kind == TERM_SCALAR || lo.kind == TERM_ROTATING
                 a = embedded(cqs, lo.atom_a, idxs)
@@ -251,7 +348,7 @@ function Problem(cqs::CompositeQSystem, n_params::Integer)
     for (lf, idxs) in cqs.parametric_Ls                              # src/composite_systems.jl:59-62
         lf isa ScaledLindblad || error("parametric Lindblad operator is an opaque closure; use ScaledLindblad")
         l = embedded(cqs, lf.op, idxs)
-        sc = Ref(csignal(lf.scale))
+        sc = Ref(csignal(lf.scale, table_ids))
         check(ccall((:qsim_problem_add_lindblad, libqsim), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ref{CSignal}),
                     prob.handle, l, sc))
     end
@@ -259,42 +356,69 @@ function Problem(cqs::CompositeQSystem, n_params::Integer)
     return prob
 end
 
-# ---- context ---------------------------------------------------------------------------------
-const CTX = Ref{Ptr{Cvoid}}(C_NULL)
-function context()
-    if CTX[] == C_NULL
+# ---- contexts (one per device, created on first use) --------------------------------------------
+const CTXS = Dict{Int,Ptr{Cvoid}}()
+function context(device::Integer=parse(Int, get(ENV, "QSIM_B200_DEVICE", "0")))
+    get!(CTXS, Int(device)) do
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ccall((:qsim_create, libqsim), Cint, (Cint, Ref{Ptr{Cvoid}}), parse(Int, get(ENV, "QSIM_B200_DEVICE", "0")), h))
-        CTX[] = h[]
+        check(ccall((:qsim_create, libqsim), Cint, (Cint, Ref{Ptr{Cvoid}}), device, h))
+        h[]
     end
-    return CTX[]
 end
 
+const WHICH = Dict(:qsim_unitary_propagator => 0, :qsim_unitary_state => 1, :qsim_me_propagator => 2, :qsim_me_state => 3)
+
 # ---- solver calls ------------------------------------------------------------------------------
+# One batched call.  `select` (vector of (row, col) tuples, or of rows for unitary_state; 1-based): only those entries
+# of every result are produced (qsim_solve_selected); with abs2 their squared moduli.  `devices`: fan the sweep out
+# over several GPUs from this one call (qsim_solve_multi, block-cyclic shards, no Julia threads).
 function solve(sym::Symbol, cqs::CompositeQSystem, ts::AbstractVector{<:Real}, params::AbstractMatrix{<:Real},
-               init::Union{Nothing,Array{ComplexF64}}, shape::Tuple)
+               init::Union{Nothing,Array{ComplexF64}}, shape::Tuple; select=nothing, abs2::Bool=false,
+               devices::Union{Nothing,AbstractVector{<:Integer}}=nothing)
     @assert issorted(ts)                                             # src/time_evolution.jl:30,64,97,141
     n_traj, n_params = size(params)
     prob = Problem(cqs, n_params)
     tsv = collect(Float64, ts)
     ptab = Matrix{Float64}(transpose(Float64.(params)))              # row-major rows for the C side
-    n = prod(shape)
-    out = Array{ComplexF64}(undef, shape..., length(tsv), n_traj)    # out[traj][k][col][row], column-major
     stats = Vector{TrajStats}(undef, n_traj)
     opts = Ref(default_opts())
-    GC.@preserve prob tsv ptab out stats init begin
-        rc = if init === nothing
-            ccall((sym, libqsim), Cint,
-                  (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ref{SolverOpts},
-                   Ptr{ComplexF64}, Ptr{TrajStats}),
-                  context(), prob.handle, n_traj, ptab, tsv, length(tsv), 0, opts, out, stats)
-        else
-            ccall((sym, libqsim), Cint,
-                  (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ptr{ComplexF64}, Int64,
-                   Ref{SolverOpts}, Ptr{ComplexF64}, Ptr{TrajStats}),
-                  context(), prob.handle, n_traj, ptab, tsv, length(tsv), 0, init, 0, opts, out, stats)
+    which = WHICH[sym]
+    initp = init === nothing ? Ptr{ComplexF64}(C_NULL) : pointer(init)
+    if select !== nothing
+        devices === nothing || error("select= is not available together with devices=")
+        rows = Int32[(s isa Tuple ? s[1] : s) - 1 for s in select]
+        cols = Int32[(s isa Tuple ? s[2] : 1) - 1 for s in select]
+        out = abs2 ? Array{Float64}(undef, length(rows), length(tsv), n_traj) :
+                     Array{ComplexF64}(undef, length(rows), length(tsv), n_traj)
+        GC.@preserve prob tsv ptab out stats init rows cols begin
+            check(ccall((:qsim_solve_selected, libqsim), Cint,
+                        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ptr{ComplexF64}, Int64,
+                         Ref{SolverOpts}, Cint, Ptr{Int32}, Ptr{Int32}, Cint, Ptr{Cvoid}, Ptr{TrajStats}),
+                        context(), prob.handle, which, n_traj, ptab, tsv, length(tsv), 0, initp, 0, opts, length(rows), rows,
+                        cols, abs2 ? 1 : 0, out, stats))
         end
-        check(rc)
+    else
+        out = Array{ComplexF64}(undef, shape..., length(tsv), n_traj)    # out[traj][k][col][row], column-major
+        GC.@preserve prob tsv ptab out stats init begin
+            rc = if devices !== nothing
+                ctxs = Ptr{Cvoid}[context(dv) for dv in devices]
+                ccall((:qsim_solve_multi, libqsim), Cint,
+                      (Ptr{Ptr{Cvoid}}, Cint, Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ptr{ComplexF64},
+                       Int64, Ref{SolverOpts}, Ptr{ComplexF64}, Ptr{TrajStats}),
+                      ctxs, length(ctxs), prob.handle, which, n_traj, ptab, tsv, length(tsv), 0, initp, 0, opts, out, stats)
+            elseif init === nothing
+                ccall(fptr(sym), Cint,
+                      (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ref{SolverOpts},
+                       Ptr{ComplexF64}, Ptr{TrajStats}),
+                      context(), prob.handle, n_traj, ptab, tsv, length(tsv), 0, opts, out, stats)
+            else
+                ccall(fptr(sym), Cint,
+                      (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ptr{ComplexF64}, Int64,
+                       Ref{SolverOpts}, Ptr{ComplexF64}, Ptr{TrajStats}),
+                      context(), prob.handle, n_traj, ptab, tsv, length(tsv), 0, init, 0, opts, out, stats)
+            end
+            check(rc)
+        end
     end
     for (i, s) in enumerate(stats)
         s.retcode == 0 || @warn "trajectory $i: solver retcode $(s.retcode) at t = $(s.t_final)"   # OrdinaryDiffEq warns too
@@ -302,8 +426,8 @@ function solve(sym::Symbol, cqs::CompositeQSystem, ts::AbstractVector{<:Real}, p
     return out, stats
 end
 
-split_results(out::Array{ComplexF64,4}, traj) = [out[:, :, k, traj] for k in 1:size(out, 3)]
-split_results(out::Array{ComplexF64,3}, traj) = [out[:, k, traj] for k in 1:size(out, 2)]
+split_results(out::Array{<:Number,4}, traj) = [out[:, :, k, traj] for k in 1:size(out, 3)]
+split_results(out::Array{<:Number,3}, traj) = [out[:, k, traj] for k in 1:size(out, 2)]
 no_params(cqs) = zeros(Float64, 1, 0)
 
 # single-system methods: identical signatures and return types to the reference
@@ -334,25 +458,71 @@ function me_state(cqs::CompositeQSystem, ts::AbstractVector{<:Real}, ρ0::Matrix
 end
 me_state(cqs::CompositeQSystem, t::Real, ρ0::Matrix{<:Number}) = me_state(cqs, [0.0, t], ρ0)[end]
 
-# batched methods: one trajectory per row of `params`; result[traj][k]
-function unitary_propagator(cqs::CompositeQSystem, ts::AbstractVector{<:Real}, params::AbstractMatrix{<:Real})
+# batched methods: one trajectory per row of `params`; result[traj][k].  Keywords: select / abs2 (entries of every
+# result, returned as result[traj][k] vectors), devices (GPUs to spread the sweep over).
+function unitary_propagator(cqs::CompositeQSystem, ts::AbstractVector{<:Real}, params::AbstractMatrix{<:Real}; kw...)
     d = dimension(cqs)
-    out, _ = solve(:qsim_unitary_propagator, cqs, ts, params, nothing, (d, d))
+    out, _ = solve(:qsim_unitary_propagator, cqs, ts, params, nothing, (d, d); kw...)
     return [split_results(out, i) for i in 1:size(params, 1)]
 end
-function me_propagator(cqs::CompositeQSystem, ts::AbstractVector{<:Real}, params::AbstractMatrix{<:Real})
+function me_propagator(cqs::CompositeQSystem, ts::AbstractVector{<:Real}, params::AbstractMatrix{<:Real}; kw...)
     d2 = dimension(cqs)^2
-    out, _ = solve(:qsim_me_propagator, cqs, ts, params, nothing, (d2, d2))
+    out, _ = solve(:qsim_me_propagator, cqs, ts, params, nothing, (d2, d2); kw...)
     return [split_results(out, i) for i in 1:size(params, 1)]
 end
-function unitary_state(cqs::CompositeQSystem, ts::AbstractVector{<:Real}, ψ0::Vector{<:Number}, params::AbstractMatrix{<:Real})
-    out, _ = solve(:qsim_unitary_state, cqs, ts, params, Vector{ComplexF64}(ψ0), (dimension(cqs),))
+function unitary_state(cqs::CompositeQSystem, ts::AbstractVector{<:Real}, ψ0::Vector{<:Number}, params::AbstractMatrix{<:Real}; kw...)
+    out, _ = solve(:qsim_unitary_state, cqs, ts, params, Vector{ComplexF64}(ψ0), (dimension(cqs),); kw...)
     return [split_results(out, i) for i in 1:size(params, 1)]
 end
-function me_state(cqs::CompositeQSystem, ts::AbstractVector{<:Real}, ρ0::Matrix{<:Number}, params::AbstractMatrix{<:Real})
+function me_state(cqs::CompositeQSystem, ts::AbstractVector{<:Real}, ρ0::Matrix{<:Number}, params::AbstractMatrix{<:Real}; kw...)
     d = dimension(cqs)
-    out, _ = solve(:qsim_me_state, cqs, ts, params, Matrix{ComplexF64}(ρ0), (d, d))
+    out, _ = solve(:qsim_me_state, cqs, ts, params, Matrix{ComplexF64}(ρ0), (d, d); kw...)
     return [split_results(out, i) for i in 1:size(params, 1)]
+end
+
+# ---- Floquet wrappers (src/time_evolution.jl:188-346) as one batched library call ---------------------------
+function floquet_call(which::Integer, cqs::CompositeQSystem, ts::AbstractVector{<:Real}, params::AbstractMatrix{<:Real},
+                      periods::Vector{Float64}, rise::Real, fall::Real, rtol::Real)
+    @assert issorted(ts)
+    n_traj, n_params = size(params)
+    prob = Problem(cqs, n_params)
+    n = which == 0 ? dimension(cqs) : dimension(cqs)^2
+    tsv = collect(Float64, ts)
+    ptab = Matrix{Float64}(transpose(Float64.(params)))
+    out = Array{ComplexF64}(undef, n, n, length(tsv), n_traj)
+    stats = Vector{TrajStats}(undef, n_traj)
+    opts = Ref(default_opts())
+    GC.@preserve prob tsv ptab out stats periods begin
+        check(ccall((:qsim_floquet_propagator, libqsim), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ptr{Float64}, Int64,
+                     Cdouble, Cdouble, Cdouble, Ref{SolverOpts}, Ptr{ComplexF64}, Ptr{TrajStats}),
+                    context(), prob.handle, which, n_traj, ptab, tsv, length(tsv), 0, periods, length(periods) == 1 ? 0 : 1,
+                    rise, fall, rtol, opts, out, stats))
+    end
+    return out
+end
+floquet_which(f) = f === unitary_propagator ? 0 : f === me_propagator ? 2 :
+    error("the Floquet wrappers take this module's unitary_propagator or me_propagator")
+
+"""
+    floquet_propagator(propagator_func, t_period[, rtol])
+
+As src/time_evolution.jl:188-228: a propagator function for systems periodic with `t_period`.  The returned function
+also has a batched method `p(cqs, ts, params)`; `t_period` may then be a vector with one period per sweep point.
+"""
+floquet_propagator(f::Function, t_period, rtol::Real=0.0) = floquet_rise_fall_propagator(f, t_period, 0.0, 0.0, rtol)
+
+"As src/time_evolution.jl:312-346; rtol = 0 selects the reference's default eps(t_period)."
+function floquet_rise_fall_propagator(f::Function, t_period, rise_time::Real, fall_time::Real, rtol::Real=0.0)
+    which = floquet_which(f)
+    periods = Float64[t_period...]
+    p(cqs::CompositeQSystem, ts::AbstractVector{<:Real}) =
+        split_results(floquet_call(which, cqs, ts, no_params(cqs), periods, rise_time, fall_time, rtol), 1)
+    function p(cqs::CompositeQSystem, ts::AbstractVector{<:Real}, params::AbstractMatrix{<:Real})
+        out = floquet_call(which, cqs, ts, params, periods, rise_time, fall_time, rtol)
+        return [split_results(out, i) for i in 1:size(params, 1)]
+    end
+    return p
 end
 
 end # module
