@@ -92,4 +92,41 @@ let
     end
     write_case("cfg4_short", params, ts, [me_propagator(cqs, ts)])
 end
+# benchmark/benchmarks.jl:162-196 (rotating frame at each qubit's own frequency) with the drive amp*sin(2 pi f t)
+function rotating_frame_gate(n, amp, freq)
+    q0 = DuffingTransmon("q0", 3, DuffingSpec(3.94015, -0.1807))
+    q1 = PerturbativeTransmon("q1", 3, TransmonSpec(0.172, 16.4, 0.55))
+    spectators = [DuffingTransmon("q$ct", 3, DuffingSpec(4.0 + 0.1 * ct, -(0.2 + 0.01 * ct))) for ct = 2:(n-1)]
+    all_qs = [q0, q1, spectators...]
+    cqs = CompositeQSystem(all_qs)
+    add_hamiltonian!(cqs, q0)
+    add_hamiltonian!(cqs, -spec(q0).frequency * number(q0), q0)
+    q1_freq = hamiltonian(q1, 0.0)[2, 2]
+    add_hamiltonian!(cqs, -q1_freq * number(q1), q1)
+    d01 = spec(q0).frequency - q1_freq
+    add_hamiltonian!(cqs, t -> 0.006 * .5 * X_Y([q0, q1], [d01 * t, 0.0]), [q0, q1])
+    add_hamiltonian!(cqs, parametric_drive(q1, t -> amp * sin(2π * freq * t)), q1)
+    for q in all_qs[3:end]
+        add_hamiltonian!(cqs, q)
+        add_hamiltonian!(cqs, -spec(q).frequency * number(q), q)
+        dq = q1_freq - spec(q).frequency
+        add_hamiltonian!(cqs, t -> 0.006 * .5 * X_Y([q1, q], [dq * t, 0.0]), [q1, q])
+    end
+    return cqs, all_qs
+end
+
+# cfg5: three transmons in the rotating frame, decay + dephasing on all three, me_propagator (729 x 729), short span;
+# parameters are (amp, f, sqrt(g1), sqrt(2 gphi)).  One RHS call of the reference is seven 729^3 GEMMs: minutes.
+let
+    T1, Tphi = 20e3, 30e3
+    g1, gphi = 1 / (2π * T1), 1 / (2π * Tphi)
+    params = [0.323 0.1221 sqrt(g1) sqrt(2 * gphi)]
+    ts = [0.0, 0.1, 0.2]
+    cqs, qs = rotating_frame_gate(3, 0.323, 0.1221)
+    for q in qs
+        add_lindblad!(cqs, decay(q, g1), [q])
+        add_lindblad!(cqs, dephasing(q, gphi), [q])
+    end
+    write_case("cfg5_short", params, ts, [me_propagator(cqs, ts)])
+end
 println("wrote reference vectors to ", outdir)
