@@ -117,7 +117,13 @@ enum {
      * Phi0; f(phi), a(phi) from the perturbative series
      * (perturbative_transmon.jl:187-261, systems.jl:79-83,213-216), then E_n
      * as above.                                                               */
-    QSIM_TERM_TRANSMON = 3
+    QSIM_TERM_TRANSMON = 3,
+    /* parametric_drive on a DiagonalChargeBasisTransmon (systems.jl:143-152, 231-237): H = diag(E_0 .. E_{dim-1}),
+     * the lowest eigenvalues of the charge-basis Hamiltonian at flux phi = s(t).  They depend on the flux only
+     * through z = cos(pi*phi) (EJ(phi)^2 = (EJ1 - EJ2)^2 + 4 EJ1 EJ2 z^2) and are smooth, even functions of z,
+     * so the host tabulates E_k(z) on [-1, 1] once (qsim_problem_add_table, one table per level) instead of the
+     * reference's 101 x 101 eigensolve per right-hand-side call; added with qsim_problem_add_spectrum_term.   */
+    QSIM_TERM_SPECTRUM = 4
 };
 
 typedef struct {
@@ -203,6 +209,11 @@ int qsim_problem_add_term(qsim_problem *prob, const qsim_term *term,
                           const int32_t *levels);
 /* One Lindblad operator L(t) = scale(t) * lind (d*d complex, embedded);
  * scale == NULL means 1 (fixed_Ls; add_lindblad!, composite_systems.jl:53-62). */
+/* parametric_drive on a DiagonalChargeBasisTransmon (QSIM_TERM_SPECTRUM above): flux = s(t) in Phi0; rot the
+ * RotatingFrameSystem rate (NULL: none); levels[d] as for DUFFING / TRANSMON; table_ids[n_levels] the tables of
+ * E_0(z) .. E_{n_levels-1}(z), z = cos(pi*flux) on [-1, 1], from qsim_problem_add_table.                    */
+int qsim_problem_add_spectrum_term(qsim_problem *prob, const qsim_signal *flux, const qsim_slot *rot,
+                                   const int32_t *levels, int n_levels, const int32_t *table_ids);
 int qsim_problem_add_lindblad(qsim_problem *prob, const double *lind,
                               const qsim_signal *scale);
 /* A tabulated envelope for QSIM_ENV_TABLE signals: the generic path for drives that are opaque closures in

@@ -46,6 +46,7 @@ def lib():
         L.qso_problem_set_h0.argtypes = [C.c_void_p, dp]
         L.qso_problem_add_term.argtypes = [C.c_void_p, C.POINTER(_abi.TermStruct), dp, dp, C.POINTER(C.c_int32)]
         L.qso_problem_add_lindblad.argtypes = [C.c_void_p, dp, C.POINTER(_abi.SignalStruct)]
+        L.qso_problem_add_charge_term.argtypes = [C.c_void_p, C.POINTER(_abi.TermStruct), C.POINTER(C.c_int32), C.c_int]
         L.qso_problem_add_table.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, dp]
         L.qso_problem_add_table.restype = C.c_int
         L.qso_problem_eval.argtypes = [C.c_void_p, C.c_int, C.c_double, dp, dp]
@@ -78,6 +79,10 @@ class OracleProblem:
             if levels is not None:
                 lv = np.ascontiguousarray(levels, dtype=np.int32)
                 pl = lv.ctypes.data_as(C.POINTER(C.c_int32))
+            if lt.kind == _abi.TERM_SPECTRUM:
+                # the oracle diagonalises the charge-basis Hamiltonian on every RHS call, like the reference
+                L.qso_problem_add_charge_term(self._h, C.byref(ts), pl, int(lt.dim))
+                continue
             L.qso_problem_add_term(self._h, C.byref(ts), pa, pb, pl)
         for op, scale in spec.lindblads:
             po, ko = _abi.cplx_ptr(op)

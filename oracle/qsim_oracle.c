@@ -87,6 +87,7 @@ typedef struct {
     qsim_term desc;
     double *atom_a, *atom_b; /* d*d complex or NULL */
     int32_t *levels;         /* d or NULL */
+    int n_levels;            /* SPECTRUM: dimension of the transmon (levels kept of the charge-basis spectrum) */
 } o_term;
 typedef struct {
     double *op; /* d*d complex */
@@ -157,11 +158,21 @@ int qso_problem_add_term(qso_problem *p, const qsim_term *t, const double *a, co
     ot->atom_a = dup_mat(a, p->d);
     ot->atom_b = dup_mat(b, p->d);
     ot->levels = NULL;
+    ot->n_levels = 0;
     if (levels) {
         ot->levels = (int32_t *)malloc(sizeof(int32_t) * p->d);
         memcpy(ot->levels, levels, sizeof(int32_t) * p->d);
     }
     return 0;
+}
+/* parametric_drive on a DiagonalChargeBasisTransmon (systems.jl:143-152, 231-237).  t->kind = QSIM_TERM_SPECTRUM,
+ * t->signal the flux, t->EC/EJ1/EJ2 the spec, t->num_terms the charge-basis size (101), t->rot the frame rate.
+ * Unlike the product (which reads host-built tables of the level energies), the oracle does what the reference
+ * does: an eigenvalue computation of the num_terms x num_terms charge-basis Hamiltonian on every RHS call.   */
+int qso_problem_add_charge_term(qso_problem *p, const qsim_term *t, const int32_t *levels, int n_levels) {
+    int rc = qso_problem_add_term(p, t, NULL, NULL, levels);
+    p->terms[p->n_terms - 1].n_levels = n_levels;
+    return rc;
 }
 int qso_problem_add_lindblad(qso_problem *p, const double *op, const qsim_signal *scale) {
     p->linds = (o_lind *)realloc(p->linds, sizeof(o_lind) * (p->n_lind + 1));
@@ -228,6 +239,39 @@ static void transmon_f_a(double EC, double EJ1, double EJ2, double phi, int num_
 }
 
 /* H(t) = H0 + sum of parametric terms, dense d x d (time_evolution.jl:32-34). */
+/* Lowest `k` eigenvalues of the charge-basis transmon Hamiltonian (systems.jl:220-229): symmetric tridiagonal,
+ * diagonal 4 EC n^2 for n = -N..N (size m = 2N + 1), off-diagonal -EJ/2.  Bisection on the Sturm count
+ * (number of eigenvalues below x = number of negative pivots of T - x I), which is what sorting eigvals does for
+ * the reference at :235, to the last bit the arithmetic allows.                                              */
+static int sturm_count(int m, const double *diag, double off2, double x) {
+    int cnt = 0;
+    double q = diag[0] - x;
+    if (q < 0) cnt++;
+    for (int i = 1; i < m; i++) {
+        if (q == 0.0) q = 1e-300;
+        q = (diag[i] - x) - off2 / q;
+        if (q < 0) cnt++;
+    }
+    return cnt;
+}
+static void charge_basis_levels(double EC, double EJ, int m, int k, double *out) {
+    const int N = m / 2;
+    double *diag = (double *)malloc(sizeof(double) * m);
+    for (int i = 0; i < m; i++) diag[i] = 4.0 * EC * (double)((i - N) * (i - N));
+    const double off = -0.5 * EJ, off2 = off * off;
+    const double lo0 = -2.0 * fabs(off) - 1.0, hi0 = diag[0] + 2.0 * fabs(off) + 1.0; /* Gershgorin */
+    for (int j = 0; j < k; j++) {
+        double lo = lo0, hi = hi0;
+        for (int it = 0; it < 200; it++) {
+            const double mid = 0.5 * (lo + hi);
+            if (mid <= lo || mid >= hi) break;
+            if (sturm_count(m, diag, off2, mid) > j) hi = mid; else lo = mid;
+        }
+        out[j] = 0.5 * (lo + hi);
+    }
+    free(diag);
+}
+
 static void assemble_h(const qso_problem *p, double t, const double *row, double *ham) {
     const int d = p->d, dd = d * d;
     memcpy(ham, p->h0, sizeof(double) * 2 * dd);
@@ -251,6 +295,18 @@ static void assemble_h(const qso_problem *p, double t, const double *row, double
                 double im = (c * ai + sn * ar) + (c * bi - sn * br);
                 ham[2 * i] += s * re;
                 ham[2 * i + 1] += s * im;
+            }
+        } else if (td->kind == QSIM_TERM_SPECTRUM) {
+            double lev[64];
+            const double e1 = slot(&td->EJ1, row), e2 = slot(&td->EJ2, row);
+            const double EJ = sqrt(e1 * e1 + e2 * e2 + 2.0 * e1 * e2 * cos(TWO_PI * s)); /* systems.jl:224 */
+            charge_basis_levels(slot(&td->EC, row), EJ, td->num_terms, ot->n_levels, lev);
+            double rot = slot(&td->rot, row);
+            for (int i = 0; i < d; i++) {
+                const int n = ot->levels[i];
+                double e = lev[n];
+                if (rot != 0) e -= (double)n * rot;                /* systems.jl:259-265 */
+                ham[2 * (i + i * d)] += e;
             }
         } else {
             double f, a;

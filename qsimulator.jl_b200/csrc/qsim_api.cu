@@ -387,6 +387,34 @@ int qsim_problem_add_term(qsim_problem *p, const qsim_term *t, const double *ato
     return QSIM_OK;
 }
 
+int qsim_problem_add_spectrum_term(qsim_problem *p, const qsim_signal *flux, const qsim_slot *rot, const int32_t *levels,
+                                   int n_levels, const int32_t *table_ids) {
+    if (int rc = check_open(p)) return rc;
+    if (!flux || !levels || !table_ids) return fail(QSIM_ERR_ARG, "NULL argument");
+    if (n_levels < 1) return fail(QSIM_ERR_ARG, "spectrum term: n_levels < 1");
+    if (int rc = check_signal(p, *flux)) return rc;
+    qsim_problem::Term term;
+    std::memset(&term.desc, 0, sizeof(term.desc));
+    term.desc.kind = QSIM_TERM_SPECTRUM;
+    term.desc.num_terms = n_levels;
+    term.desc.signal = *flux;
+    term.desc.rot.param = -1;
+    if (rot) {
+        if (int rc = check_slot(p, *rot, "rot")) return rc;
+        term.desc.rot = *rot;
+    }
+    for (qsim_slot *sl : {&term.desc.rate, &term.desc.anharm, &term.desc.EC, &term.desc.EJ1, &term.desc.EJ2}) sl->param = -1;
+    term.levels.assign(levels, levels + p->d);
+    for (int v : term.levels)
+        if (v < 0 || v >= n_levels) return fail(QSIM_ERR_ARG, "spectrum term: level without a table");
+    term.tables.assign(table_ids, table_ids + n_levels);
+    for (int v : term.tables)
+        if (v < 1 || v > (int)p->table_offset.size())
+            return fail(QSIM_ERR_ARG, "spectrum term: table id does not name a table added with qsim_problem_add_table");
+    p->terms.push_back(std::move(term));
+    return QSIM_OK;
+}
+
 int qsim_problem_add_lindblad(qsim_problem *p, const double *lind, const qsim_signal *scale) {
     if (int rc = check_open(p)) return rc;
     if (!lind) return fail(QSIM_ERR_ARG, "lind is NULL");

@@ -131,6 +131,25 @@ static void build_h_exprs(const qsim_problem &p, ChannelAlloc &ca, std::vector<E
                 expr_add(H[q], ch, t.a[q] + t.b[q]);            // cos th (A + B)
                 expr_add(H[q], ch + 1, I * (t.a[q] - t.b[q]));  // sin th i(A - B)
             }
+        } else if (td.kind == QSIM_TERM_SPECTRUM) {
+            // one channel per level: E_k(cos(pi phi(t))) from the level's table; - rot * n like the other diagonal terms
+            std::vector<int> ch(t.tables.size(), -1);
+            SlotRef rr = slot_channel(ca, td.rot);
+            for (int i = 0; i < d; i++) {
+                const int n = t.levels[i];
+                if (n < 0 || n >= (int)t.tables.size()) throw std::runtime_error("spectrum term: level without a table");
+                if (ch[(size_t)n] < 0) {
+                    EvalDesc e = blank_eval();
+                    e.kind = EV_SPECTRUM;
+                    e.sig = td.signal;
+                    e.num_terms = t.tables[(size_t)n];   // table id, translated to an offset with the other tables
+                    e.dynamic = sig_dyn;
+                    ch[(size_t)n] = ca.add(e, 1);
+                }
+                Expr &ex = H[(size_t)i + (size_t)i * d];
+                expr_add(ex, ch[(size_t)n], 1.0);
+                expr_add(ex, rr.chan, -rr.scale * (double)n);
+            }
         } else {
             int ch_f, ch_a;
             double a_scale = 1.0;
@@ -284,6 +303,11 @@ void build_generator(const qsim_problem &p, int which, Generator &g) {
     // tabulated envelopes: table id (1-based) -> 1 + offset into the flat table array
     g.tables = p.tables;
     for (auto &e : g.evals) {
+        if (e.kind == EV_SPECTRUM) {
+            if (e.num_terms < 1 || e.num_terms > (int)p.table_offset.size())
+                throw std::runtime_error("spectrum term refers to a table that was not added");
+            e.num_terms = 1 + p.table_offset[(size_t)e.num_terms - 1];
+        }
         if (e.sig.envelope == QSIM_ENV_TABLE) {
             if (e.sig.table < 1 || e.sig.table > (int)p.table_offset.size())
                 throw std::runtime_error("signal refers to a table that was not added");

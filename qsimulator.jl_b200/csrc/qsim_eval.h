@@ -32,7 +32,7 @@ struct ResolvedEval {
     double EC, EC2, EJs, EJp;                           // TRANSMON: EC, 2*EC, EJ1^2+EJ2^2, 2*EJ1*EJ2
     double slot;                                        // SLOT
     const double *tab;                                  // ENV_TABLE: {t_start, 1/h, n_seg, n_coef, coef...}
-    double _pad2;
+    const double *tab2;                                 // SPECTRUM: the level's table E(z), z = cos(pi phi)
 };
 static_assert(sizeof(ResolvedEval) == 160, "ResolvedEval is copied as ten 16-byte words");
 
@@ -86,7 +86,7 @@ QSIM_HD void resolve_eval(const EvalDesc &e, const double *row, const double *ta
     r.EJp = 2.0 * EJ1 * EJ2;
     r.slot = slot_value(e.slot, row);
     r.tab = (e.sig.envelope == QSIM_ENV_TABLE && e.sig.table > 0 && tables) ? tables + (e.sig.table - 1) : nullptr;
-    r._pad2 = 0.0;
+    r.tab2 = (e.kind == EV_SPECTRUM && e.num_terms > 0 && tables) ? tables + (e.num_terms - 1) : nullptr;
 }
 
 QSIM_HD double eval_signal(const ResolvedEval &s, double t) {
@@ -150,6 +150,9 @@ QSIM_HD void run_resolved(const ResolvedEval &e, const double *freq_tab, const d
             *o0 = s * s;
             break;
         }
+        case EV_SPECTRUM:
+            *o0 = e.tab2 ? eval_table(e.tab2, cos(0.5 * QSIM_TWO_PI * eval_signal(e, t))) : 0.0;
+            break;
         default:
             *o0 = e.slot;
             break;

@@ -31,7 +31,8 @@ enum EvalKind : int32_t {
     EV_ROTATING = 1,  // out[0] = s cos(th), out[1] = s sin(th), th = 2 pi (rate t)
     EV_TRANSMON = 2,  // out[0] = f01(phi), out[1] = anharm(phi), phi = s(t)
     EV_SQUARE = 3,    // out[0] = s(t)^2            (Lindblad rate |scale|^2)
-    EV_SLOT = 4       // out[0] = slot value        (per-trajectory constant)
+    EV_SLOT = 4,      // out[0] = slot value        (per-trajectory constant)
+    EV_SPECTRUM = 5   // out[0] = table(cos(pi s(t)))   (a level of a DiagonalChargeBasisTransmon; num_terms = table ref)
 };
 
 // One channel evaluator (plain data, copied to the device as-is).
@@ -76,6 +77,7 @@ struct qsim_problem {
         qsim_term desc;
         std::vector<qsim::cplx> a, b;
         std::vector<int32_t> levels;
+        std::vector<int32_t> tables;   // SPECTRUM: table id of every level
     };
     struct Lind {
         std::vector<qsim::cplx> op;

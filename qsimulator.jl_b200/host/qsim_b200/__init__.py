@@ -8,7 +8,8 @@ the CUDA shared library through the C ABI of include/qsim_b200.h.  There is no C
 from .signals import Param, Signal, ComplexSignal, Const, Cos, Sin, Table, tabulated
 from .systems import (HermitianSpec, ResonatorSpec, TransmonSpec, DuffingSpec, QSystem, LiteralHermitian,
                       Resonator, DuffingTransmon, PerturbativeTransmon, RotatingFrameSystem, label, dimension,
-                      spec, hamiltonian, duffing_hamiltonian, fit_transmon, transmon_spec_from_duffing)
+                      spec, hamiltonian, duffing_hamiltonian, fit_transmon, transmon_spec_from_duffing,
+                      ChargeBasisTransmon, DiagonalChargeBasisTransmon, charge_basis_levels, charge_spectrum_tables)
 from .transmon_series import (PERTURBATIVE_NUM_TERMS, xi_effective, perturbative_transmon_freq,
                               perturbative_transmon_anharm)
 from .operators import (raising, lowering, number, X, Y, X_Y, XY, flip_flop, decay, dephasing, dipole_drive,

@@ -14,6 +14,7 @@ OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_ALLOC = 0,
 RET_SUCCESS, RET_MAXITERS, RET_DT_UNDERFLOW, RET_NONFINITE = 0, 1, 2, 3
 FLAG_DEVICE_PTRS = 1
 FLAG_DIRECT_DRIVES = 2
+TERM_SPECTRUM = 4
 
 
 class Slot(C.Structure):

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("QSIM_B200_LIB", os.path.join(PKG_ROOT, "lib", "libqsi
 EXPORTS = [
     "qsim_version", "qsim_last_error", "qsim_default_opts", "qsim_create", "qsim_destroy", "qsim_device_info",
     "qsim_synchronize", "qsim_alloc_pinned", "qsim_free_pinned", "qsim_problem_create", "qsim_problem_destroy",
-    "qsim_problem_set_h0", "qsim_problem_add_term", "qsim_problem_add_lindblad", "qsim_problem_add_table",
+    "qsim_problem_set_h0", "qsim_problem_add_term", "qsim_problem_add_spectrum_term", "qsim_problem_add_lindblad", "qsim_problem_add_table",
     "qsim_problem_finalize",
     "qsim_problem_eval", "qsim_unitary_propagator", "qsim_unitary_state", "qsim_me_propagator", "qsim_me_state",
     "qsim_solve_selected", "qsim_solve_multi", "qsim_problem_flops_per_rhs", "qsim_problem_kernel_name", "qsim_launch_count",
@@ -63,6 +63,8 @@ def lib():
     L.qsim_problem_set_h0.argtypes = [vp, dp]
     L.qsim_problem_add_term.argtypes = [vp, C.POINTER(_abi.TermStruct), dp, dp, C.POINTER(C.c_int32)]
     L.qsim_problem_add_lindblad.argtypes = [vp, dp, C.POINTER(_abi.SignalStruct)]
+    L.qsim_problem_add_spectrum_term.argtypes = [vp, C.POINTER(_abi.SignalStruct), C.POINTER(_abi.Slot),
+                                                 C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32)]
     L.qsim_problem_add_table.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int, dp, C.POINTER(C.c_int32)]
     L.qsim_problem_finalize.argtypes = [vp]
     L.qsim_problem_eval.argtypes = [vp, C.c_int, C.c_double, dp, dp]
@@ -215,6 +217,11 @@ class Problem:
             if levels is not None:
                 lv = np.ascontiguousarray(levels, dtype=np.int32)
                 pl = lv.ctypes.data_as(C.POINTER(C.c_int32))
+            if lt.kind == _abi.TERM_SPECTRUM:
+                ids = np.array([table_ids[id(tb)] for tb in lt.level_tables], dtype=np.int32)
+                check(L.qsim_problem_add_spectrum_term(self._h, C.byref(ts.signal), C.byref(ts.rot), pl, len(ids),
+                                                       ids.ctypes.data_as(C.POINTER(C.c_int32))))
+                continue
             check(L.qsim_problem_add_term(self._h, C.byref(ts), pa, pb, pl))
         for op, scale in spec.lindblads:
             po, ko = _abi.cplx_ptr(op)

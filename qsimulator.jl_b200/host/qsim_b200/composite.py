@@ -233,5 +233,9 @@ def lower(cqs: CompositeQSystem, n_params: Optional[int] = None) -> ProblemSpec:
     for sig in [t[0].signal for t in terms] + [sc for _, sc in lind if sc is not None]:
         if sig.table is not None and all(sig.table is not tb for tb in tables):
             tables.append(sig.table)
+    for lt in [t[0] for t in terms]:
+        for tb in lt.level_tables or []:     # spectra of DiagonalChargeBasisTransmon drives
+            if all(tb is not x for x in tables):
+                tables.append(tb)
     return ProblemSpec(d=d, n_params=n_params, h0=composite_hamiltonian(cqs), terms=terms, lindblads=lind,
                        tables=tables)

@@ -21,10 +21,11 @@ from typing import Callable, List, Optional, Sequence, Union
 import numpy as np
 
 from .signals import ComplexSignal, Const, Param, Scalar, Signal, max_param_index, resolve
-from .systems import (DuffingTransmon, PerturbativeTransmon, QSystem, RotatingFrameSystem,
+from .systems import (DiagonalChargeBasisTransmon, DuffingTransmon, PerturbativeTransmon, QSystem, RotatingFrameSystem,
+                      charge_spectrum_tables,
                       dimension, hamiltonian)
 
-TERM_SCALAR, TERM_ROTATING, TERM_DUFFING, TERM_TRANSMON = 0, 1, 2, 3
+TERM_SCALAR, TERM_ROTATING, TERM_DUFFING, TERM_TRANSMON, TERM_SPECTRUM = 0, 1, 2, 3, 4
 
 
 def _dim(q) -> int:
@@ -136,7 +137,8 @@ class LoweredTerm:
     EJ1: Scalar = 0.0
     EJ2: Scalar = 0.0
     num_terms: int = 0
-    dim: int = 0                           # level count (DUFFING / TRANSMON)
+    dim: int = 0                           # level count (DUFFING / TRANSMON / SPECTRUM)
+    level_tables: Optional[list] = None    # SPECTRUM: one signals.Table per level, E_k(cos(pi phi)) on [-1, 1]
 
     def max_param_index(self) -> int:
         return max_param_index(self.signal, self.rate, self.anharm, self.rot, self.EC, self.EJ1, self.EJ2)
@@ -231,6 +233,16 @@ def parametric_drive(q, drive) -> ParametricHamiltonian:
         s = base.spec
         term = LoweredTerm(TERM_TRANSMON, sig, rot=rot, EC=s.EC, EJ1=s.EJ1, EJ2=s.EJ2,
                            num_terms=base.num_terms, dim=base.dimension)
+    elif isinstance(base, DiagonalChargeBasisTransmon):
+        # systems.jl:231-237: the reference diagonalises the num_terms x num_terms charge-basis Hamiltonian on every
+        # call; the level energies depend on the flux only through cos(pi phi) and are tabulated once here
+        s = base.spec
+        if any(isinstance(x, Param) for x in (s.EC, s.EJ1, s.EJ2)):
+            raise TypeError("parametric_drive: the spec of a DiagonalChargeBasisTransmon must be literal "
+                            "(its spectrum is tabulated on the host)")
+        term = LoweredTerm(TERM_SPECTRUM, sig, rot=rot, EC=s.EC, EJ1=s.EJ1, EJ2=s.EJ2, num_terms=base.num_terms,
+                           dim=base.dimension,
+                           level_tables=charge_spectrum_tables(s.EC, s.EJ1, s.EJ2, base.num_terms, base.dimension))
     else:
         raise TypeError(f"parametric_drive: no hamiltonian(q, x) kernel form for {type(base).__name__}")
 

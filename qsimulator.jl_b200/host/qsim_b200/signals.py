@@ -93,9 +93,9 @@ class Table:
 
     @staticmethod
     def from_function(fn: Callable, t_start: float, t_end: float, n_coef: int = 12, tol: float = 1e-14,
-                      max_seg: int = 1 << 16) -> "Table":
+                      max_seg: int = 1 << 16, atol: float = 0.0) -> "Table":
         """Sample `fn` on [t_start, t_end]: the segment count doubles until the series matches `fn` at 2*n_coef
-        off-node points per segment to tol * max|fn|."""
+        off-node points per segment to max(tol * max|fn|, atol)."""
         def f(ts):
             try:
                 v = np.asarray(fn(ts), dtype=np.float64)
@@ -121,8 +121,8 @@ class Table:
             want = f(tc)
             err = np.max(np.abs(tab.eval(tc) - want))
             scale = max(np.max(np.abs(want)), 1e-300)
-            if err <= tol * scale or n_seg >= max_seg:
-                if err > 1e-9 * scale:
+            if err <= max(tol * scale, atol) or n_seg >= max_seg:
+                if err > max(1e-9 * scale, atol):
                     raise ValueError(f"could not tabulate the function to 1e-9 with {n_seg} segments (error {err / scale:.1e})")
                 return tab
             n_seg *= 2
