@@ -526,6 +526,7 @@ struct Plan {
     std::vector<uint32_t> split_ell;
     std::vector<uint8_t> split_info;
     int cu = 0, rpl = 1;               // column-per-lane mapping (LaunchArgs::cu_map); rows per lane of the variant
+    int lean = 0, off_park = 0;        // lean variant chosen (Kern<..., LEAN>); its park area inside the team region
     std::vector<uint8_t> slot_imag;    // value mode 4: per slot, 1 = purely imaginary, 0 = purely real
     // blocked variant (value mode 3): block rows, row table [1 + max blocks][n] and value slot ids
     int blk_rows = 0, blk_nnz = 0;
@@ -698,18 +699,18 @@ static bool build_split_rows(const Generator &g, Plan &pl) {
     return true;
 }
 
-static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int vm, int rs) {
+static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int block, int vm, int rs, int lean = 0) {
     const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c3_t128, variants_r1c3_t256,
                                               variants_r1c4_t256, variants_r2c1_t128,
                                               variants_r2c2_t256, variants_r3c1_t128, variants_r3c1_t256,
-                                              variants_rowsplit, variants_colperlane, variants_blocked};
+                                              variants_rowsplit, variants_colperlane, variants_blocked, variants_lean};
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
         int cnt = 0;
         const KernelVariant *v = fn(&cnt);
         for (int i = 0; i < cnt; i++)
             if (v[i].rpl == rpl && v[i].cpl == cpl && (rs || v[i].maxnnz >= max_nnz) && v[i].maxt >= block &&
-                v[i].vm == vm && v[i].rs == rs) {
+                v[i].vm == vm && v[i].rs == rs && v[i].lean == lean) {
                 // smallest row capacity, then smallest block bound, then the preferred occupancy target
                 auto key = [&](const KernelVariant &k) { return std::make_tuple(k.maxnnz, k.maxt); };
                 if (!best || key(v[i]) < key(*best)) best = &v[i];
@@ -978,6 +979,14 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     if (!pl.kv)
         return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
                                               std::to_string(g.max_nnz) + ")");
+    // Lean kernels (Kern<..., LEAN>: early-dying stage vectors, 168 registers, three warps per scheduler) for
+    // resident teams when the shape has one; QSIM_NO_LEAN=1 keeps the 255-register kernels (development A/B switch).
+    if (!pl.streamed && !pl.rowsplit && !blocked && !split && !std::getenv("QSIM_NO_LEAN")) {
+        if (const KernelVariant *lv = find_variant(rpl, cpl, eff_nnz, pl.block, vm, 0, 1)) {
+            pl.kv = lv;
+            pl.lean = 1;
+        }
+    }
     // stage-buffer layout: smallest-cost (row stride, group stride) near the dense one
     if (pl.cu) {
         pl.y_row_stride = 32;   // a row of the stage buffer = 32 columns of 16 bytes: every gather reads one aligned 512-byte row
@@ -1023,6 +1032,10 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     pl.common_bytes = pl.off_drec + (pl.dyn_fast ? 64 * std::max(g.n_dyn_slots, 1) : 16);
     pl.team_bytes = ((((pl.vm >= 1 && pl.vm <= 3) ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
                     (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride + 128 * pl.team_warps;
+    if (pl.lean) {   // park area: k2..k6 of a step with save points, 512 bytes per entry and warp
+        pl.off_park = (pl.team_bytes + 15) & ~15;
+        pl.team_bytes = pl.off_park + pl.team_warps * 5 * rpl * cpl * 512;
+    }
     const size_t smem_cap = 220 * 1024;
     if (pl.rowsplit) {
         build_rowsplit_table(g, pl, std::getenv("QSIM_DEBUG_LAYOUT") != nullptr);   // (debug: run the annealer without a GPU)
@@ -1439,6 +1452,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.dyn_fast = pl.dyn_fast;
     a.dyn_rec = dc->dyn_rec;
     a.team_bytes = pl.team_bytes;
+    a.off_park = pl.off_park;
     a.reltol = o.reltol; a.abstol = o.abstol; a.gamma = o.gamma; a.qmin = o.qmin; a.qmax = o.qmax;
     a.beta1 = o.beta1; a.beta2 = o.beta2; a.qoldinit = o.qoldinit; a.dtmax = o.dtmax;
     a.maxiters = o.maxiters > 0 ? o.maxiters : 1000000;

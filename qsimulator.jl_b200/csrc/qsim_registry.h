@@ -10,6 +10,7 @@ struct KernelVariant {
     const char *name;
     launch_fn launch;
     cudaError_t (*occupancy)(int block, size_t smem, int *ctas_per_sm);
+    int lean;  // 1: Kern<..., LEAN = true> (resident teams only; see qsim_solver.cuh)
 };
 
 // defined one per translation unit (qsim_inst_*.cu) so the variants compile in parallel
@@ -25,6 +26,7 @@ QSIM_DECLARE(variants_r3c1_t128) QSIM_DECLARE(variants_r3c1_t256)
 QSIM_DECLARE(variants_rowsplit)
 QSIM_DECLARE(variants_colperlane)
 QSIM_DECLARE(variants_blocked)
+QSIM_DECLARE(variants_lean)
 
 #define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \
     {                                                                                                     \

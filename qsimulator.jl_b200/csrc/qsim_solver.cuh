@@ -125,6 +125,7 @@ struct LaunchArgs {
     double pow_coef[2][16][10];
     double pow_exp2[2][128];
     int team_bytes;       // shared bytes per team
+    int off_park;         // lean kernels: offset of the park area inside the team region (5 * E * 512 bytes per warp)
     double reltol, abstol, gamma, qmin, qmax, beta1, beta2, qoldinit, dtmax;
     long long maxiters;
 };
@@ -348,6 +349,7 @@ struct Geo {
     uint32_t sm_V, sm_chan, sm_rev, sm_win, sm_red;  // team (sm_win: per channel 12 nodes, 3 checks, 12 coefficients)
     uint32_t sm_y0, sm_y1;                      // this warp's two stage buffers (+ column offset)
     uint32_t sm_ctl;                            // this warp's control block: step-loop scalars parked in shared memory
+    uint32_t sm_park;                           // lean kernels: this lane's slots for k2..k6 of a step with save points
     double stage_c;                             // kStageC[lane] for lanes 0..4 (fast_tables), set once per thread
     int blk_row;                                // blocked variants: this lane's block row
     uint32_t v_stride;                          // bytes between value tables
@@ -372,7 +374,12 @@ struct Geo {
 // VM (value mode): 0 complex value slots; 1 purely imaginary generator (slots hold Im A, 2 DFMA per
 // multiply-add); 2 as 1 with every off-diagonal entry time-independent: those values live in registers for
 // the whole trajectory and only the diagonal is read from the per-stage table.
-template <int RPL, int CPL, int MAXNNZ, int VM, bool RS>
+// LEAN (resident teams only): the Runge-Kutta stage vectors are consumed as early as the tableau allows -- after
+// stage 6 the combinations for u_new and for the error estimate are formed and k2..k6 die, so stage 7 runs with five
+// live vectors instead of ten -- and operands are requested two row entries at a time.  This fits the step in 168
+// registers (three warps per scheduler instead of two).  The k's a dense-output point needs are parked in
+// lane-private shared memory on the (rare) steps that contain a save point.
+template <int RPL, int CPL, int MAXNNZ, int VM, bool RS, bool LEAN = false>
 struct Kern {
     static constexpr bool IM = VM >= 1 && VM <= 3;
     static constexpr bool SV = VM == 2;
@@ -852,7 +859,7 @@ struct Kern {
 #ifndef QSIM_CH
 #define QSIM_CH 4
 #endif
-                constexpr int CH = QSIM_CH;
+                constexpr int CH = LEAN ? 2 : QSIM_CH;
 #pragma unroll
                 for (int j0 = 1; j0 < MAXNNZ; j0 += CH) {
                     double2 vv[CH], yy[CH][CPL];
@@ -983,6 +990,54 @@ struct Kern {
                     sx += k6[e].x * b6; sy += k6[e].y * b6;
                     sx += k7[e].x * b7; sy += k7[e].y * b7;
                     o[e] = make_double2(u[e].x + dt * sx, u[e].y + dt * sy);
+                }
+                write_out(a, traj, ks, col0, row_of, row_ok, o);
+            }
+        }
+    }
+
+    // Lean kernels: stage vector k_{v+2} of a step that contains save points, kept in lane-private shared-memory
+    // slots (512 bytes per entry: conflict-free) until the step is accepted.
+    static __device__ __forceinline__ void park(const Geo &g, int v, const Vec &k) {
+#pragma unroll
+        for (int e = 0; e < E; e++) sts2(g.sm_park + 512u * (uint32_t)(v * E + e), k[e]);
+    }
+    // Dense output of a lean step: k2..k6 come back from the park area, in the order of save_points' sums.
+    static __device__ __forceinline__ void save_points_lean(const LaunchArgs &a, const Geo &g, long long traj, const double *ts,
+                                                            int k_lo, int k_hi, double t, double dt, double tnew, int col0,
+                                                            const int (&row_of)[RPL], const bool (&row_ok)[RPL],
+                                                            const Vec &u, const Vec &k1, const Vec &k7, const Vec &unew) {
+        for (int ks = k_lo; ks < k_hi; ks++) {
+            const double tsv = ts[ks];
+            if (tsv == tnew) {
+                write_out(a, traj, ks, col0, row_of, row_ok, unew);
+            } else {
+                const double th = (tsv - t) / dt;
+                const double th2 = th * th;
+                double bb[7];
+                bb[0] = th * (1.0 + th * (-2.763706197274826 + th * (2.9132554618219126 + th * -1.0530884977290216)));
+                bb[1] = th2 * (0.13169999999999998 + th * (-0.2234 + th * 0.1017));
+                bb[2] = th2 * (3.9302962368947516 + th * (-5.941033872131505 + th * 2.490627285651253));
+                bb[3] = th2 * (-12.411077166933676 + th * (30.33818863028232 + th * -16.548102889244902));
+                bb[4] = th2 * (37.50931341651104 + th * (-88.1789048947664 + th * 47.37952196281928));
+                bb[5] = th2 * (-27.896526289197286 + th * (65.09189467479366 + th * -34.87065786149661));
+                bb[6] = th2 * (1.5 + th * (-4.0 + th * 2.5));
+                Vec o;
+#pragma unroll
+                for (int e = 0; e < E; e++) o[e] = make_double2(k1[e].x * bb[0], k1[e].y * bb[0]);
+#pragma unroll
+                for (int v = 0; v < 5; v++)
+#pragma unroll
+                    for (int e = 0; e < E; e++) {
+                        const double2 kk = lds2(g.sm_park + 512u * (uint32_t)(v * E + e));
+                        o[e].x += kk.x * bb[1 + v];
+                        o[e].y += kk.y * bb[1 + v];
+                    }
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    o[e].x += k7[e].x * bb[6];
+                    o[e].y += k7[e].y * bb[6];
+                    o[e] = make_double2(u[e].x + dt * o[e].x, u[e].y + dt * o[e].y);
                 }
                 write_out(a, traj, ks, col0, row_of, row_ok, o);
             }
@@ -1238,6 +1293,88 @@ struct Kern {
                     if (a.streamed)
                         fetch_uk(b, col0, sc_u0 + (size_t)(2 * cur) * sbuf, sc_k0 + (size_t)(2 * cur) * sbuf, u, k1);
                     Vec part;  // partial combination of the next stage, formed while the current stage's operands load
+                    double ex[E], ey[E];
+                    if (LEAN) {
+                        const bool saving = nsave_hi > nsave;   // warp-uniform: this step holds dense-output points
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const double ax = A21 * k1[e].x, ay = A21 * k1[e].y;
+                            tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
+                        }
+                        put_stage(a, g, tmp, yb0, my_off, row_ok);
+                        apply(a, g, V0, yb0, ell, vstat, row_of, tmp, k2, [&] {
+#pragma unroll
+                            for (int e = 0; e < E; e++) part[e] = make_double2(A31 * k1[e].x, A31 * k1[e].y);
+                        });
+                        if (saving) park(g, 0, k2);
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const double ax = fma(A32, k2[e].x, part[e].x), ay = fma(A32, k2[e].y, part[e].y);
+                            tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
+                        }
+                        put_stage(a, g, tmp, yb1, my_off, row_ok);
+                        apply(a, g, V1, yb1, ell, vstat, row_of, tmp, k3, [&] {
+#pragma unroll
+                            for (int e = 0; e < E; e++)
+                                part[e] = make_double2(fma(A42, k2[e].x, A41 * k1[e].x), fma(A42, k2[e].y, A41 * k1[e].y));
+                        });
+                        if (saving) park(g, 1, k3);
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const double ax = fma(A43, k3[e].x, part[e].x), ay = fma(A43, k3[e].y, part[e].y);
+                            tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
+                        }
+                        put_stage(a, g, tmp, yb0, my_off, row_ok);
+                        apply(a, g, V2, yb0, ell, vstat, row_of, tmp, k4, [&] {
+#pragma unroll
+                            for (int e = 0; e < E; e++)
+                                part[e] = make_double2(fma(A53, k3[e].x, fma(A52, k2[e].x, A51 * k1[e].x)),
+                                                       fma(A53, k3[e].y, fma(A52, k2[e].y, A51 * k1[e].y)));
+                        });
+                        if (saving) park(g, 2, k4);
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const double ax = fma(A54, k4[e].x, part[e].x), ay = fma(A54, k4[e].y, part[e].y);
+                            tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
+                        }
+                        put_stage(a, g, tmp, yb1, my_off, row_ok);
+                        apply(a, g, V3, yb1, ell, vstat, row_of, tmp, k5, [&] {
+#pragma unroll
+                            for (int e = 0; e < E; e++)
+                                part[e] = make_double2(
+                                    fma(A64, k4[e].x, fma(A63, k3[e].x, fma(A62, k2[e].x, A61 * k1[e].x))),
+                                    fma(A64, k4[e].y, fma(A63, k3[e].y, fma(A62, k2[e].y, A61 * k1[e].y))));
+                        });
+                        if (saving) park(g, 3, k5);
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const double ax = fma(A65, k5[e].x, part[e].x), ay = fma(A65, k5[e].y, part[e].y);
+                            tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
+                        }
+                        put_stage(a, g, tmp, yb0, my_off, row_ok);
+                        // stage 6; under its loads: the k1..k5 part of u_new's combination
+                        apply(a, g, V4, yb0, ell, vstat, row_of, tmp, k6, [&] {
+#pragma unroll
+                            for (int e = 0; e < E; e++)
+                                part[e] = make_double2(
+                                    fma(A75, k5[e].x, fma(A74, k4[e].x, fma(A73, k3[e].x, fma(A72, k2[e].x, A71 * k1[e].x)))),
+                                    fma(A75, k5[e].y, fma(A74, k4[e].y, fma(A73, k3[e].y, fma(A72, k2[e].y, A71 * k1[e].y)))));
+                        });
+                        if (saving) park(g, 4, k6);
+                        // u_new, then the k1..k6 part of the error combination: k2..k6 are dead before stage 7's loads
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const double ax = fma(A76, k6[e].x, part[e].x), ay = fma(A76, k6[e].y, part[e].y);
+                            tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);  // u_new
+                        }
+                        put_stage(a, g, tmp, yb1, my_off, row_ok);
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            ex[e] = fma(BT6, k6[e].x, fma(BT5, k5[e].x, fma(BT4, k4[e].x, fma(BT3, k3[e].x, fma(BT2, k2[e].x, BT1 * k1[e].x)))));
+                            ey[e] = fma(BT6, k6[e].y, fma(BT5, k5[e].y, fma(BT4, k4[e].y, fma(BT3, k3[e].y, fma(BT2, k2[e].y, BT1 * k1[e].y)))));
+                        }
+                        apply(a, g, V4, yb1, ell, vstat, row_of, tmp, k7);
+                    } else {
 #pragma unroll
                     for (int e = 0; e < E; e++) {
                         const double ax = A21 * k1[e].x, ay = A21 * k1[e].y;
@@ -1306,7 +1443,6 @@ struct Kern {
                     }
                     put_stage(a, g, tmp, yb1, my_off, row_ok);
                     // while stage 7's operands load: the k1..k6 part of the error combination
-                    double ex[E], ey[E];
                     apply(a, g, V4, yb1, ell, vstat, row_of, tmp, k7, [&] {
 #pragma unroll
                         for (int e = 0; e < E; e++) {
@@ -1314,6 +1450,7 @@ struct Kern {
                             ey[e] = fma(BT6, k6[e].y, fma(BT5, k5[e].y, fma(BT4, k4[e].y, fma(BT3, k3[e].y, fma(BT2, k2[e].y, BT1 * k1[e].y)))));
                         }
                     });
+                    }
                     QSIM_TICK(6)
                     {
                         // Error norm: sum over this lane's entries of |u~|^2 / (abstol + max(|u|,|u_new|) reltol)^2.
@@ -1357,12 +1494,12 @@ struct Kern {
 #pragma unroll
                         for (int e = 0; e < E; e++) err[0] += fma(ex[e], ex[e], ey[e] * ey[e]);
                     }
-                    if (a.streamed) {
+                    if (!LEAN && a.streamed) {
                         // tentative: the next buffers are adopted only if the step is accepted; dense-output
                         // slots are rewritten by the retried / a later step if it is not
                         store_batch(sc_u0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, sidx, row_ok, tmp);
                         store_batch(sc_k0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, sidx, row_ok, k7);
-                        if (nsave_hi > nsave)
+                        if (!LEAN && nsave_hi > nsave)
                             save_points(a, tout, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok, u, k1,
                                         k2, k3, k4, k5, k6, k7, tmp);
                     }
@@ -1396,10 +1533,15 @@ struct Kern {
                     const double r = pmin(a.qmax, pmax(a.qmin, a.gamma * ra * qold_pow));
                     CTL_ST(C_QOLDPOW, e2 >= qinit2 ? rb : qinit_pow);  // qold = max(EEst, qoldinit)
                     if (!a.streamed) {
-                        if (nsave_hi > nsave && (RS || g.warp_in_team < a.n_batches))
-                            save_points(a, tout, ts, nsave, nsave_hi, t, dt, tnew,
-                                        (RS ? 0 : g.warp_in_team) * g.cpb + g.colofs,
-                                        row_of, row_ok, u, k1, k2, k3, k4, k5, k6, k7, tmp);
+                        if (nsave_hi > nsave && (RS || g.warp_in_team < a.n_batches)) {
+                            if (LEAN)
+                                save_points_lean(a, g, tout, ts, nsave, nsave_hi, t, dt, tnew,
+                                                 g.warp_in_team * g.cpb + g.colofs, row_of, row_ok, u, k1, k7, tmp);
+                            else
+                                save_points(a, tout, ts, nsave, nsave_hi, t, dt, tnew,
+                                            (RS ? 0 : g.warp_in_team) * g.cpb + g.colofs,
+                                            row_of, row_ok, u, k1, k2, k3, k4, k5, k6, k7, tmp);
+                        }
 #pragma unroll
                         for (int e = 0; e < E; e++) {
                             u[e] = tmp[e];
@@ -1455,10 +1597,11 @@ struct Kern {
 // teams of nine warps (865 > n > 768), 168 registers).
 // MINB: minimum resident CTAs per SM the register allocation must allow; IM: purely imaginary generator
 // (unitary evolution under a real Hamiltonian): value slots hold Im(A) only, 2 DFMA per multiply-add.
-template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS, bool LEAN = false>
 __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant__ LaunchArgs a) {
     extern __shared__ __align__(16) double smem[];
-    typedef Kern<RPL, CPL, MAXNNZ, VM, RS> K;
+    typedef Kern<RPL, CPL, MAXNNZ, VM, RS, LEAN> K;
+    static_assert(!LEAN || (!RS && VM != 3), "lean kernels: resident row-per-lane teams");
     constexpr bool IM = K::IM;
     const int n = a.g.n;
     Geo g;
@@ -1520,6 +1663,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
               16u * g_idx * a.y_grp_stride;
     g.sm_y1 = g.sm_y0 + ybytes;
     g.sm_ctl = g.sm_red + 8u * (a.team_warps * 4 + 8) + (RS ? 1 : a.team_warps) * 2 * ybytes + 128u * g.warp_in_team;
+    g.sm_park = tbase + a.off_park + (uint32_t)g.warp_in_team * (5u * K::E * 512u) + 16u * g.lane;
     g.sm_ell = (RS && a.ell_in_smem) ? sbase + a.off_ell : 0u;
     g.sm_mbar = tbase + a.off_pf;                                   // three mbarriers (32 bytes reserved)
     g.sm_pf = (RS && a.rs_prefetch) ? g.sm_mbar + 32u : 0u;        // two buffers of 2 * n * 16 bytes
@@ -1630,23 +1774,23 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
 // Host-side launcher for one (RPL, CPL, MAXNNZ) instantiation.
 typedef cudaError_t (*launch_fn)(const LaunchArgs &, int grid, int block, size_t smem, cudaStream_t);
 
-template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS, bool LEAN = false>
 cudaError_t launch_solver(const LaunchArgs &a, int grid, int block, size_t smem, cudaStream_t stream) {
     if (block > MAXT) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS>,
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS, LEAN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS><<<grid, block, smem, stream>>>(a);
+    solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS, LEAN><<<grid, block, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS>
+template <int RPL, int CPL, int MAXNNZ, int MAXT, int MINB, int VM, bool RS, bool LEAN = false>
 cudaError_t occupancy_solver(int block, size_t smem, int *ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS>,
+    cudaError_t e = cudaFuncSetAttribute(solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS, LEAN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS>,
-                                                         block, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm,
+                                                         solve_kernel<RPL, CPL, MAXNNZ, MAXT, MINB, VM, RS, LEAN>, block, smem);
 }
 
 }  // namespace qsim
