@@ -109,6 +109,8 @@ struct qsim_problem::DeviceCopy {
     uint8_t *split_info = nullptr;
     uint32_t *blk_ell = nullptr;     // blocked kernels: row table and value slot ids (built by make_plan)
     uint16_t *blk_slot = nullptr;
+    uint32_t *tr_ell = nullptr;      // tiered kernels: row table over virtual rows, virtual -> state row
+    int *tr_perm = nullptr, *tr_pos = nullptr;
     ~DeviceCopy() { free_all(); }  // the owning device must be current
     void free_all() {
         for (auto &pk : packed) {
@@ -129,6 +131,11 @@ struct qsim_problem::DeviceCopy {
         cudaFree(blk_slot);
         blk_ell = nullptr;
         blk_slot = nullptr;
+        cudaFree(tr_ell);
+        cudaFree(tr_perm);
+        cudaFree(tr_pos);
+        tr_ell = nullptr;
+        tr_perm = tr_pos = nullptr;
         cudaFree(dyn_rec);
         dyn_rec = nullptr;
         cudaFree(tables);
@@ -527,6 +534,8 @@ struct Plan {
     std::vector<uint8_t> split_info;
     int cu = 0, rpl = 1;               // column-per-lane mapping (LaunchArgs::cu_map); rows per lane of the variant
     int lean = 0, off_park = 0;        // lean variant chosen (Kern<..., LEAN>); its park area inside the team region
+    int tiered = 0;                    // tiered variant (value mode 5): blk_rows / blk_nnz hold its geometry
+    const struct TieredForm *tf = nullptr;   // its table, row permutation and stage layout (cached in the problem)
     std::vector<uint8_t> slot_imag;    // value mode 4: per slot, 1 = purely imaginary, 0 = purely real
     // blocked variant (value mode 3): block rows, row table [1 + max blocks][n] and value slot ids
     int blk_rows = 0, blk_nnz = 0;
@@ -581,6 +590,174 @@ static bool build_blocked(const Generator &g, int R, int capacity, Plan &pl) {
     return true;
 }
 
+// Tiered form of a generator for the value-mode-5 kernels (three rows of one column per lane).  Rows are sorted by
+// their number of off-diagonal entries and cut into three tiers of n/3 rows; table row 3 b + i is the b-th row of
+// tier i, so row-slot i of every lane carries rows of (nearly) the same length and the lanes of a warp execute
+// caps[0] + caps[1] + caps[2] entries instead of 3 x the longest row.  Purely imaginary generators with static
+// off-diagonal values only (the condition of value mode 2).
+// The stage buffer holds state row r of column g at 16-byte unit pos[r] * S + g * Cg.  Which rows share a block,
+// the order of a row's entries (entry j of the three blocks' row-slot i is ONE load instruction across the warp),
+// the positions pos[] and the strides are chosen by a seeded annealing run against the exact wavefront count of the
+// executed loads and stores (quarter warps of 8 lanes, 8 bank groups of 16 bytes), so the gathers run without bank
+// conflicts where the pattern allows it.  The table is indexed like Generator::ell over table rows; the source
+// field of an entry holds the stage position of its source row.  Result cached per generator (TieredForm).
+struct TieredForm {
+    bool ok = false;
+    int caps[3] = {1, 1, 1}, nb = 0, nnz = 0, S = 1, Cg = 1;
+    long cost = 0, floor = 0;
+    std::vector<uint32_t> ell;   // [nnz][n] over table rows: stage position of the source | slot << 16
+    std::vector<int> perm, pos;  // table row -> state row; table row -> stage position
+};
+
+static bool build_tiered(const Generator &g, int groups, TieredForm &tf) {
+    const int n = g.n, R = 3;
+    if (n % R != 0 || !g.imag_only || n > 32) return false;
+    const int nb = n / R;
+    std::vector<std::vector<uint32_t>> off((size_t)n);
+    for (int r = 0; r < n; r++)
+        for (int j = 1; j < g.max_nnz; j++) {
+            const uint32_t e = g.ell[(size_t)j * n + r];
+            if ((e >> 16) == 0xFFFFu) continue;
+            if ((int)(e >> 16) < g.n_dyn_slots) return false;   // time-dependent off-diagonal entry
+            off[(size_t)r].push_back(e);
+        }
+    std::vector<int> order((size_t)n);
+    for (int r = 0; r < n; r++) order[(size_t)r] = r;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return off[(size_t)x].size() > off[(size_t)y].size(); });
+    for (int i = 0; i < R; i++) {
+        tf.caps[i] = 1;
+        for (int b = 0; b < nb; b++) tf.caps[i] = std::max(tf.caps[i], 1 + (int)off[(size_t)order[(size_t)(i * nb + b)]].size());
+    }
+    if (tf.caps[0] > 7) return false;
+    tf.nb = nb;
+    tf.nnz = tf.caps[0];
+
+    // search state: rows[i][b] = state row in (tier i, block b); ent[r] = entry order of row r; pos[r]; (S, Cg)
+    struct State {
+        std::vector<int> rows, pos;
+        std::vector<std::vector<uint32_t>> ent;
+        int S, Cg;
+    };
+    State cur;
+    cur.rows = order;   // index i * nb + b
+    cur.pos.resize((size_t)n);
+    for (int r = 0; r < n; r++) cur.pos[(size_t)r] = r;
+    cur.ent = off;
+    cur.S = groups;
+    cur.Cg = 1;
+    const int nlanes = groups * nb;
+    auto injective = [&](int S, int Cg) {
+        std::vector<char> used((size_t)(n * S + groups * Cg + 1), 0);
+        for (int r = 0; r < n; r++)
+            for (int c = 0; c < groups; c++) {
+                const int u = r * S + c * Cg;
+                if (16 * u > 65535 - 16 || used[(size_t)u]) return false;
+                used[(size_t)u] = 1;
+            }
+        return true;
+    };
+    auto cost_of = [&](const State &st) {
+        long cost = 0;
+        for (int i = 0; i < R; i++)
+            for (int j = 0; j < tf.caps[i]; j++)      // j == 0: the lane's own store of row-slot i
+                for (int q = 0; q < 4; q++) {
+                    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seen[8][8];
+                    bool any = false;
+                    for (int l = 8 * q; l < 8 * q + 8; l++) {
+                        const bool active = l < nlanes;
+                        if (!active && j == 0) continue;            // inactive lanes do not store
+                        const int le = active ? l : nlanes - 1;     // ... and mimic the last lane's loads
+                        const int b = le % nb, c = le / nb;
+                        const int r = st.rows[(size_t)(i * nb + b)];
+                        int src = r;
+                        if (j > 0) {
+                            const auto &e = st.ent[(size_t)r];
+                            src = j - 1 < (int)e.size() ? (int)(e[(size_t)(j - 1)] & 0xFFFFu) : r;   // padding: own row
+                        }
+                        const int unit = st.pos[(size_t)src] * st.S + c * st.Cg, bk = unit & 7;
+                        bool dup = false;
+                        for (int k = 0; k < cnt[bk]; k++) dup = dup || seen[bk][k] == unit;
+                        if (!dup) seen[bk][cnt[bk]++] = unit;
+                        any = true;
+                    }
+                    int w = 0;
+                    for (int bk = 0; bk < 8; bk++) w = std::max(w, cnt[bk]);
+                    cost += any ? w : 0;
+                }
+        return cost;
+    };
+    tf.floor = 0;
+    for (int i = 0; i < R; i++) tf.floor += (long)tf.caps[i] * ((nlanes + 7) / 8 > 4 ? 4 : (nlanes + 7) / 8);
+    // candidate strides: row-major (S >= groups) and column-major (Cg >= n) families with a little padding
+    std::vector<std::pair<int, int>> strides;
+    for (int pad = 0; pad <= 8; pad++) {
+        if (injective(groups + pad, 1)) strides.push_back({groups + pad, 1});
+        if (injective(1, n + pad)) strides.push_back({1, n + pad});
+    }
+    if (strides.empty()) return false;
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&](int m) {
+        rng ^= rng << 13;
+        rng ^= rng >> 7;
+        rng ^= rng << 17;
+        return (int)((rng >> 33) % (uint64_t)m);
+    };
+    State best = cur;
+    long best_cost = -1;
+    for (size_t sidx = 0; sidx < strides.size() && best_cost != tf.floor; sidx++) {
+        State st = cur;
+        st.S = strides[sidx].first;
+        st.Cg = strides[sidx].second;
+        long c = cost_of(st);
+        if (best_cost < 0 || c < best_cost) { best = st; best_cost = c; }
+        double temp = 2.0;
+        for (int it = 0; it < 4000 && best_cost != tf.floor; it++, temp *= 0.9985) {
+            State nx = st;
+            const int mv = rnd(3);
+            if (mv == 0) {                       // swap two stage positions
+                const int x = rnd(n), y = rnd(n);
+                std::swap(nx.pos[(size_t)x], nx.pos[(size_t)y]);
+            } else if (mv == 1) {                // swap two rows inside a tier (equal capacities: any two of the tier)
+                const int i = rnd(R), x = rnd(nb), y = rnd(nb);
+                std::swap(nx.rows[(size_t)(i * nb + x)], nx.rows[(size_t)(i * nb + y)]);
+            } else {                             // swap two entries of a row
+                const int r = rnd(n);
+                auto &e = nx.ent[(size_t)r];
+                if (e.size() >= 2) std::swap(e[(size_t)rnd((int)e.size())], e[(size_t)rnd((int)e.size())]);
+            }
+            const long cn = cost_of(nx);
+            // accept improvements always, deteriorations with a temperature-dependent chance (integer arithmetic: seeded, portable)
+            const long d = cn - c;
+            bool take = d <= 0;
+            if (!take && temp > 0.05) take = rnd(1000) < (int)(1000.0 * std::exp(-(double)d / temp));
+            if (take) {
+                st = nx;
+                c = cn;
+                if (c < best_cost) { best = st; best_cost = c; }
+            }
+        }
+    }
+    tf.cost = best_cost;
+    tf.S = best.S;
+    tf.Cg = best.Cg;
+    tf.perm.assign((size_t)n, 0);
+    tf.pos.assign((size_t)n, 0);
+    tf.ell.assign((size_t)tf.nnz * n, 0);
+    for (int i = 0; i < R; i++)
+        for (int b = 0; b < nb; b++) {
+            const int v = R * b + i, r = best.rows[(size_t)(i * nb + b)];
+            tf.perm[(size_t)v] = r;
+            tf.pos[(size_t)v] = best.pos[(size_t)r];
+            for (int j = 0; j < tf.nnz; j++) tf.ell[(size_t)j * n + v] = (uint32_t)best.pos[(size_t)r] | (0xFFFFu << 16);
+            tf.ell[(size_t)v] = (uint32_t)best.pos[(size_t)r] | (g.ell[(size_t)r] & 0xFFFF0000u);   // diagonal: own row, its slot
+            const auto &e = best.ent[(size_t)r];
+            for (size_t j = 0; j < e.size(); j++)
+                tf.ell[(1 + j) * (size_t)n + v] = (uint32_t)best.pos[(size_t)(e[j] & 0xFFFFu)] | (e[j] & 0xFFFF0000u);
+        }
+    tf.ok = true;
+    return true;
+}
+
 // Shared-memory wavefronts of the stage-vector gathers and stores for a candidate layout: the stage
 // buffer holds element (row, group g, column c) at 16-byte unit row*S + g*Cg + c.  A 128-bit shared
 // access is served a quarter warp (8 lanes) at a time; lanes hitting the same 16-byte bank group
@@ -610,10 +787,16 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
                         gi = le / blk_rows;
                         r = rpl * (le % blk_rows) + i;
                     } else if (groups > 1) {
-                        active = l < groups * n;
-                        const int le = active ? l : groups * n - 1;
-                        gi = le / n;
-                        r = le % n;
+                        const int nl = groups * n, nh = table_rows - n;   // split rows: groups * nh helper lanes follow
+                        active = l < nl + groups * nh;
+                        if (l >= nl && active) {
+                            gi = (l - nl) / nh;
+                            r = n + (l - nl) % nh;
+                        } else {
+                            const int le = active ? l : nl - 1;
+                            gi = le / n;
+                            r = le % n;
+                        }
                     }
                     const bool helper = active && r >= n && r < table_rows;
                     if (r >= n && !helper) {
@@ -647,8 +830,8 @@ static long layout_cost(const Generator &g, int rpl, int cpl, int groups, int S,
 // an idle lane.  Chooses the smallest row length M such that every row longer than M can get a helper (at most
 // 32 - n of them, each row at most 2 M long), and rebuilds the row table with n + helpers rows and 1 + M entries
 // per row (diagonal first; helpers carry a zero diagonal).  Returns false when nothing is gained.
-static bool build_split_rows(const Generator &g, Plan &pl) {
-    const int n = g.n, spare = 32 - n;
+static bool build_split_rows(const Generator &g, Plan &pl, int groups = 1) {
+    const int n = g.n, spare = (32 - groups * n) / groups;   // idle lanes per column group
     if (spare <= 0 || g.max_nnz < 3) return false;
     std::vector<std::vector<uint32_t>> off((size_t)n);
     int longest = 0;
@@ -692,8 +875,13 @@ static bool build_split_rows(const Generator &g, Plan &pl) {
             for (int j = first; j < (int)o.size(); j++) pl.split_ell[(size_t)(1 + j - first) * nv + h] = o[(size_t)j];
             for (int j = 0; j < pl.split_nnz; j++)   // helper's padding reads the owner's row (broadcast-friendly)
                 if ((pl.split_ell[(size_t)j * nv + h] >> 16) == 0xFFFFu) pl.split_ell[(size_t)j * nv + h] = (uint32_t)r | (0xFFFFu << 16);
-            pl.split_info[(size_t)r] = (uint8_t)(h | 64);
-            pl.split_info[(size_t)h] = (uint8_t)(r | 32);
+            // per-lane info: partner lane, helper / owner flags (lanes: group gi's rows at gi * n, its helpers after all rows)
+            const int nh = nv - n;
+            for (int gi = 0; gi < groups; gi++) {
+                const int lo = groups > 1 ? gi * n + r : r, lh = groups > 1 ? groups * n + gi * nh + (h - n) : h;
+                pl.split_info[(size_t)lo] = (uint8_t)(lh | 64);
+                pl.split_info[(size_t)lh] = (uint8_t)(lo | 32);
+            }
         }
     }
     return true;
@@ -918,15 +1106,82 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
             }
         }
     }
+    // Tiered variant (value mode 5) for small propagators that fit one warp with three rows of one column per
+    // lane (the 2-transmon gates of cfg1/cfg2: 9 rows, tier capacities 5 / 3 / 2): 10 instead of 15 entries per lane
+    // and stage, one complex operand per off-diagonal entry instead of three.  Opt-in (QSIM_TIERED=1): parity-green, but
+    // at 168 registers its 10 row entries + 7 static values per lane spill, which costs more than the gathers save
+    // (cfg2: 593 ms against 554 ms for the row-per-lane lean kernel; profiles/r2_cfg2_experiments.txt).
+    const KernelVariant *tiered_kv = nullptr;
+    if (pl.identity && !pl.rowsplit && !blocked && n % 3 == 0 && std::getenv("QSIM_TIERED") && !std::getenv("QSIM_NO_LEAN")) {
+        const int nb = n / 3, gb = std::min(32 / std::max(nb, 1), pl.ncols);
+        if (nb >= 1 && gb >= pl.ncols) {
+            TieredForm *tf = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(p->plan_mutex);
+                if (!p->tiered[pl.w]) {
+                    p->tiered[pl.w] = std::make_shared<TieredForm>();
+                    build_tiered(g, gb, *p->tiered[pl.w]);
+                    if (std::getenv("QSIM_DEBUG") && p->tiered[pl.w]->ok)
+                        std::fprintf(stderr, "[qsim] tiered form: caps %d/%d/%d, stage layout S=%d Cg=%d, %ld wavefronts per stage (floor %ld)\n",
+                                     p->tiered[pl.w]->caps[0], p->tiered[pl.w]->caps[1], p->tiered[pl.w]->caps[2], p->tiered[pl.w]->S,
+                                     p->tiered[pl.w]->Cg, p->tiered[pl.w]->cost, p->tiered[pl.w]->floor);
+                }
+                tf = p->tiered[pl.w].get();
+            }
+            if (tf->ok) {
+                int cnt = 0;
+                const KernelVariant *v = variants_lean(&cnt);
+                for (int i = 0; i < cnt; i++)
+                    if (v[i].vm == 5 && v[i].rpl == 3 && (v[i].maxnnz >> 6) >= tf->caps[0] && ((v[i].maxnnz >> 3) & 7) >= tf->caps[1] &&
+                        (v[i].maxnnz & 7) >= tf->caps[2] && !tiered_kv)
+                        tiered_kv = &v[i];
+            }
+            if (tiered_kv) {
+                pl.tiered = 1;
+                pl.tf = tf;
+                pl.blk_rows = tf->nb;
+                pl.blk_nnz = tf->nnz;
+                rpl = 3;
+                cpl = 1;
+                pl.groups = gb;
+                cpb = gb;
+                pl.n_batches = 1;
+            }
+        }
+    }
     // Split rows (one row per lane, spare lanes): halves the longest rows; see build_split_rows.  Opt-in
     // (build with -DQSIM_SPLIT_ROWS, run with QSIM_SPLIT_ROWS=1): parity-green, but on cfg3 (d = 27: rows of 1 + 4 instead of 1 + 8 entries) the saved operand
     // loads are paid back by the per-stage shuffles of the helpers' partial sums and by bank conflicts of the compacted
     // rows (profiles/r2_cfg3_experiments.txt: 953 ms against 937 ms for 1184 x 50 ns).
     bool split = false;
 #ifdef QSIM_SPLIT_ROWS   // experimental build (make EXTRA=-DQSIM_SPLIT_ROWS) + QSIM_SPLIT_ROWS=1 in the environment
-    if (!pl.rowsplit && !blocked && rpl == 1 && pl.groups == 1 && n < 32 && std::getenv("QSIM_SPLIT_ROWS"))
+    if (!pl.rowsplit && !blocked && !pl.tiered && rpl == 1 && pl.groups == 1 && n < 32 && std::getenv("QSIM_SPLIT_ROWS"))
         split = build_split_rows(g, pl);
 #endif
+    // Split rows in the lean value-mode-6 kernels (one-warp propagators with idle lanes: the 2-transmon gates run
+    // 9 rows x 3 column groups on 27 lanes, and their one 5-entry row is shared with the 3 spare lanes): every lane
+    // then executes rows of 1 + 2 entries instead of 1 + 4.  Opt-in (QSIM_SPLIT=1): parity-green and a third fewer
+    // shared-memory wavefronts, but the six shuffles + selects per stage that bring the helper's partial sums to the
+    // owner lengthen the dependent chain of the step (cfg2: 604 ms against 554 ms; profiles/r2_cfg2_experiments.txt).
+    bool split6 = false;
+    if (!split && !pl.rowsplit && !blocked && !pl.tiered && rpl == 1 && pl.n_batches == 1 && g.imag_only &&
+        std::getenv("QSIM_SPLIT") && !std::getenv("QSIM_NO_LEAN")) {
+        bool static_off = true;
+        for (int j = 1; j < g.max_nnz && static_off; j++)
+            for (int r = 0; r < n; r++) {
+                const uint32_t sl = g.ell[(size_t)j * n + r] >> 16;
+                if (sl != 0xFFFFu && (int)sl < g.n_dyn_slots) static_off = false;
+            }
+        if (static_off && build_split_rows(g, pl, pl.groups)) {
+            if (find_variant(rpl, cpl, pl.split_nnz, 128, 6, 0, 1))
+                split = split6 = true;
+            else {
+                pl.split_nv = pl.split_nnz = 0;
+                pl.split_ell.clear();
+                pl.split_info.clear();
+            }
+        }
+    }
     const int eff_nnz = split ? pl.split_nnz : g.max_nnz;
     pl.rpl = rpl;
     if (pl.cu) {
@@ -943,8 +1198,8 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.streamed = 1;
         pl.team_warps = 8;
     }
-    // one-warp teams: 4 per CTA (128 threads, 2 CTAs = 8 warps per SM when the kernel needs > 168 registers:
-    // no spills; spilled variants at 10-12 warps per SM are ~1.7x slower per warp)
+    // one-warp teams: 4 per CTA (128 threads; 2 CTAs = 8 warps per SM for the 255-register kernels, 3 CTAs = 12 warps
+    // for the lean 168-register ones)
     pl.teams_per_cta = pl.team_warps == 1 ? 4 : 1;
     if (const char *env = std::getenv("QSIM_TEAMS_PER_CTA")) {  // tuning knob (development)
         const int v = std::atoi(env);
@@ -955,6 +1210,10 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     int vm = g.imag_only ? 1 : 0;
     if (blocked) {
         vm = 3;
+    } else if (pl.tiered) {
+        vm = 5;
+    } else if (split6) {
+        vm = 6;
     } else if (vm == 1 && !pl.rowsplit) {
         bool static_off = true;
         for (int j = 1; j < g.max_nnz && static_off; j++)
@@ -970,7 +1229,10 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         if (mixed && find_variant(rpl, cpl, eff_nnz, pl.block, 4, pl.rowsplit)) vm = 4;
     }
     pl.vm = vm;
-    pl.kv = find_variant(rpl, cpl, blocked ? pl.blk_nnz : eff_nnz, pl.block, vm, pl.rowsplit);
+    pl.kv = pl.tiered ? tiered_kv
+            : split6  ? find_variant(rpl, cpl, pl.split_nnz, pl.block, 6, 0, 1)
+                      : find_variant(rpl, cpl, blocked ? pl.blk_nnz : eff_nnz, pl.block, vm, pl.rowsplit);
+    if (pl.tiered || split6) pl.lean = 1;
     if (!pl.kv && split) {   // (no variant with the shorter capacity and this value mode: fall back to whole rows)
         split = false;
         pl.split_nv = 0;
@@ -981,7 +1243,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
                                               std::to_string(g.max_nnz) + ")");
     // Lean kernels (Kern<..., LEAN>: early-dying stage vectors, 168 registers, three warps per scheduler) for
     // resident teams when the shape has one; QSIM_NO_LEAN=1 keeps the 255-register kernels (development A/B switch).
-    if (!pl.streamed && !pl.rowsplit && !blocked && !split && !std::getenv("QSIM_NO_LEAN")) {
+    if (!pl.streamed && !pl.rowsplit && !blocked && !split && !pl.tiered && !std::getenv("QSIM_NO_LEAN")) {
         if (const KernelVariant *lv = find_variant(rpl, cpl, eff_nnz, pl.block, vm, 0, 1)) {
             pl.kv = lv;
             pl.lean = 1;
@@ -991,6 +1253,9 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     if (pl.cu) {
         pl.y_row_stride = 32;   // a row of the stage buffer = 32 columns of 16 bytes: every gather reads one aligned 512-byte row
         pl.y_grp_stride = 1;
+    } else if (pl.tiered) {
+        pl.y_row_stride = pl.tf->S;     // chosen together with the row positions (build_tiered)
+        pl.y_grp_stride = pl.tf->Cg;
     } else {
         long best = -1;
         for (int Cg = cpl; Cg <= cpl + 16; Cg++)
@@ -1030,7 +1295,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     for (int sl = 0; sl < g.n_dyn_slots; sl++)
         if (g.slot_ptr[sl + 1] - g.slot_ptr[sl] > 3) pl.dyn_fast = 0;
     pl.common_bytes = pl.off_drec + (pl.dyn_fast ? 64 * std::max(g.n_dyn_slots, 1) : 16);
-    pl.team_bytes = ((((pl.vm >= 1 && pl.vm <= 3) ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
+    pl.team_bytes = (((((pl.vm >= 1 && pl.vm <= 3) || pl.vm == 5 || pl.vm == 6) ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
                     (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride + 128 * pl.team_warps;
     if (pl.lean) {   // park area: k2..k6 of a step with save points, 512 bytes per entry and warp
         pl.off_park = (pl.team_bytes + 15) & ~15;
@@ -1252,6 +1517,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     const uint8_t *d_slot_imag = nullptr;
     const uint32_t *d_blk_ell = nullptr;
     const uint16_t *d_blk_slot = nullptr;
+    const int *d_tr_perm = nullptr, *d_tr_pos = nullptr;
     {
         std::lock_guard<std::mutex> packed_lock(p->dev_mutex);
         if (pl.rowsplit) {
@@ -1276,17 +1542,24 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
             }
         }
         if (pl.vm == 4 && !dc->slot_imag) CU(upload(&dc->slot_imag, pl.slot_imag));
-        if (pl.blk_rows > 0 && !dc->blk_ell) {
+        if (pl.blk_rows > 0 && !pl.tiered && !dc->blk_ell) {
             CU(upload(&dc->blk_ell, pl.blk_ell));
             CU(upload(&dc->blk_slot, pl.blk_slot));
+        }
+        if (pl.tiered && !dc->tr_ell) {
+            CU(upload(&dc->tr_ell, pl.tf->ell));
+            CU(upload(&dc->tr_perm, pl.tf->perm));
+            CU(upload(&dc->tr_pos, pl.tf->pos));
         }
         if (pl.split_nv > 0 && !dc->split_ell) {
             CU(upload(&dc->split_ell, pl.split_ell));
             CU(upload(&dc->split_info, pl.split_info));
         }
         d_slot_imag = dc->slot_imag;
-        d_blk_ell = dc->blk_ell;
+        d_blk_ell = pl.tiered ? dc->tr_ell : dc->blk_ell;
         d_blk_slot = dc->blk_slot;
+        d_tr_perm = dc->tr_perm;
+        d_tr_pos = dc->tr_pos;
     }
     cudaStream_t stream = o.stream ? (cudaStream_t)o.stream : c->stream;
 
@@ -1334,9 +1607,15 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     const bool stats_direct = zero_copy && stats && host_pointer_is_pinned(stats, &stats_alias);
     const int64_t capacity = (int64_t)ctas_per_sm * c->prop.multiProcessorCount * pl.teams_per_cta;  // teams in flight
     int n_chunks = 1;
-    if (!dev_ptrs && !zero_copy && !o.stream && (double)traj_bytes * (double)n_traj > 64e6 && !std::getenv("QSIM_NO_PIPELINE"))
-        n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(8, n_traj / std::max<int64_t>(capacity, 1)));
-    const int64_t per_chunk = (n_traj + n_chunks - 1) / n_chunks;
+    int64_t per_chunk = n_traj;
+    if (!dev_ptrs && !zero_copy && !o.stream && (double)traj_bytes * (double)n_traj > 64e6 && !std::getenv("QSIM_NO_PIPELINE") &&
+        n_traj > capacity) {
+        // whole waves per chunk (a multiple of the teams the device holds), at most eight chunks; the last chunk is the
+        // remainder, so the copy that nothing overlaps is as small as the sweep allows
+        const int64_t waves = (n_traj + capacity - 1) / capacity;
+        per_chunk = capacity * ((waves + 7) / 8);
+        n_chunks = (int)((n_traj + per_chunk - 1) / per_chunk);
+    }
     if (dev_ptrs) {
         a.params = params;
         a.ts = ts;
@@ -1408,6 +1687,8 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         a.g.max_nnz = pl.blk_nnz;
         a.blk_slot = d_blk_slot;
         a.n_blk_rows = pl.blk_rows;
+        a.row_perm = d_tr_perm;
+        a.row_pos = d_tr_pos;
     }
     if (pl.split_nv > 0) {
         a.g.ell = dc->split_ell;
@@ -1488,32 +1769,48 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         }
         return QSIM_OK;
     }
-    // pipelined: chunk k on stream k % 2 into result buffer k % 2 (its own scratch and work counter), followed on the
-    // same stream by a copy into page-locked staging buffer k % 2; while chunk k integrates and chunk k - 1's copy
-    // drains, this thread moves chunk k - 1 from its staging buffer to the caller's (pageable, possibly strided)
-    // positions.  Inputs were queued on `stream`: make the second stream wait for them.
+    // pipelined: chunk k runs on stream k % 2 into device result buffer k % 2 (its own scratch and work counter).
+    // While chunk k integrates, this thread drains chunk k - 1: pieces of at most QSIM_STAGE_BYTES are copied into two
+    // small page-locked staging buffers (DMA at full rate) and moved from there to the caller's pageable, possibly
+    // strided positions, double-buffered.  Inputs were queued on `stream`: make the second stream wait for them.
+    const size_t stage_bytes = std::max<size_t>(traj_bytes, (size_t)32 << 20);
     for (int i = 0; i < 2; i++) {
-        const size_t need_b = traj_bytes * (size_t)per_chunk;
-        if (c->stage_cap[i] < need_b) {
+        if (c->stage_cap[i] < stage_bytes) {
             if (c->stage[i]) CU(cudaFreeHost(c->stage[i]));
             c->stage[i] = nullptr;
             c->stage_cap[i] = 0;
-            CU(cudaHostAlloc(&c->stage[i], need_b, cudaHostAllocDefault));
-            c->stage_cap[i] = need_b;
+            CU(cudaHostAlloc(&c->stage[i], stage_bytes, cudaHostAllocDefault));
+            c->stage_cap[i] = stage_bytes;
         }
     }
     CU(cudaEventRecord(c->ev1, stream));
     CU(cudaStreamWaitEvent(c->stream2, c->ev1, 0));
     cudaStream_t streams[2] = {stream, c->stream2};
-    auto move_out = [&](int k) -> int {   // staging buffer k % 2 -> the caller's arrays (host memcpy)
+    const int64_t traj_per_piece = std::max<int64_t>(1, (int64_t)(stage_bytes / traj_bytes));
+    auto move_out = [&](int k) -> int {   // device result buffer k % 2 -> staging -> the caller's arrays
         const int64_t lo = (int64_t)k * per_chunk, cnt = std::min<int64_t>(per_chunk, n_traj - lo);
-        CU(cudaEventSynchronize(c->ev_copy[k % 2]));
-        const char *src = (const char *)c->stage[k % 2];
-        char *dst = (char *)out + traj_bytes * (size_t)(sh.first + lo * sh.step);
-        if (sh.step == 1)
-            std::memcpy(dst, src, traj_bytes * (size_t)cnt);
-        else
-            for (int64_t j = 0; j < cnt; j++) std::memcpy(dst + traj_bytes * (size_t)(j * sh.step), src + traj_bytes * (size_t)j, traj_bytes);
+        const char *dev = (const char *)((k % 2) ? c->out2.p : c->out.p);
+        cudaStream_t cs = streams[k % 2];   // ordered behind chunk k's kernel; the next launch on it comes after this drain
+        const int64_t n_pieces = (cnt + traj_per_piece - 1) / traj_per_piece;
+        auto issue = [&](int64_t q) -> int {
+            const int64_t p0 = q * traj_per_piece, pc = std::min<int64_t>(traj_per_piece, cnt - p0);
+            CU(cudaMemcpyAsync(c->stage[q % 2], dev + traj_bytes * (size_t)p0, traj_bytes * (size_t)pc, cudaMemcpyDeviceToHost, cs));
+            CU(cudaEventRecord(c->ev_copy[q % 2], cs));
+            return QSIM_OK;
+        };
+        if (int rc = issue(0)) return rc;
+        for (int64_t q = 0; q < n_pieces; q++) {
+            if (q + 1 < n_pieces)
+                if (int rc = issue(q + 1)) return rc;
+            CU(cudaEventSynchronize(c->ev_copy[q % 2]));
+            const int64_t p0 = q * traj_per_piece, pc = std::min<int64_t>(traj_per_piece, cnt - p0);
+            const char *src = (const char *)c->stage[q % 2];
+            char *dst = (char *)out + traj_bytes * (size_t)(sh.first + (lo + p0) * sh.step);
+            if (sh.step == 1)
+                std::memcpy(dst, src, traj_bytes * (size_t)pc);
+            else
+                for (int64_t j = 0; j < pc; j++) std::memcpy(dst + traj_bytes * (size_t)(j * sh.step), src + traj_bytes * (size_t)j, traj_bytes);
+        }
         return QSIM_OK;
     };
     int last = -1;
@@ -1533,8 +1830,6 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         CU(pl.kv->launch(ak, grid_k, pl.block, pl.smem, streams[k % 2]));
         c->launches++;
         CU(cudaEventRecord(c->ev1, streams[k % 2]));   // (kept from the last chunk: end of the kernels)
-        CU(cudaMemcpyAsync(c->stage[k % 2], ak.out, traj_bytes * (size_t)cnt, cudaMemcpyDeviceToHost, streams[k % 2]));
-        CU(cudaEventRecord(c->ev_copy[k % 2], streams[k % 2]));
         last = k;
         if (k >= 1)
             if (int rc = move_out(k - 1)) return rc;

@@ -1,11 +1,17 @@
 // Instantiates the lean Tsit5 kernels (Kern<..., LEAN = true>): one-warp resident teams, four per CTA, three CTAs =
-// 12 warps per SM at no more than 168 registers per thread.
+// 12 warps per SM at no more than 168 registers per thread.  Row-per-lane (value mode 2), row-per-lane with split
+// rows (value mode 6) and tiered (value mode 5: three rows of one column per lane, tier capacities 5 / 3 / 2 packed
+// as 0532) forms.
 #include "qsim_registry.h"
 namespace qsim {
 const KernelVariant *variants_lean(int *count) {
     static const KernelVariant v[] = {
         {1, 3, 5, 128, 3, 2, 0, "tsit5_lean_r1c3_nnz5_t128_vm2", launch_solver<1, 3, 5, 128, 3, 2, false, true>,
          occupancy_solver<1, 3, 5, 128, 3, 2, false, true>, 1},
+        {1, 3, 3, 128, 3, 6, 0, "tsit5_lean_split_r1c3_nnz3_t128_vm6", launch_solver<1, 3, 3, 128, 3, 6, false, true>,
+         occupancy_solver<1, 3, 3, 128, 3, 6, false, true>, 1},
+        {3, 1, 0532, 128, 3, 5, 0, "tsit5_lean_tiered_r3c1_nnz532_t128_vm5", launch_solver<3, 1, 0532, 128, 3, 5, false, true>,
+         occupancy_solver<3, 1, 0532, 128, 3, 5, false, true>, 1},
     };
     *count = (int)(sizeof(v) / sizeof(v[0]));
     return v;

@@ -75,7 +75,9 @@ struct LaunchArgs {
     unsigned long long *work_counter;
     double2 *scratch;     // streamed mode: [n_teams_total][4][n_batches*cpb*n]
     const uint16_t *blk_slot;    // blocked variants: [n_blk_rows][(max_nnz-1)*RPL*RPL] slot ids of the block values
-    int n_blk_rows;              // blocked variants: block rows (= lanes per column)
+    int n_blk_rows;              // blocked and tiered variants: block rows (= lanes per column)
+    const int *row_perm;         // tiered variants: state row of table row v (lane's block row * RPL + row-slot)
+    const int *row_pos;          // tiered variants: position of table row v in the stage buffer (host-chosen against bank conflicts)
     // Row-split mode.  Rows are sorted by descending length and dealt out in chunks of 32: chunk c = slot * team_warps
     // + warp holds sorted rows [32c, 32c + 32), so every (warp, slot) group is homogeneous in length and the
     // warps of a team carry equal work.  ell_packed[j][q]: entry j of sorted row q, translated (source offset |
@@ -364,7 +366,7 @@ struct Geo {
 // Stops the compiler from hoisting per-entry address arithmetic out of the step loop (register pressure).
 #define QSIM_LAUNDER_ELL()                                                      \
     _Pragma("unroll") for (int i_ = 0; i_ < RPL; i_++) {                        \
-        _Pragma("unroll") for (int j_ = 0; j_ < MAXNNZ; j_++)                   \
+        _Pragma("unroll") for (int j_ = 0; j_ < cap(i_); j_++)                  \
             asm volatile("" : "+r"(const_cast<uint32_t &>(ell[i_][j_])));       \
     }
 
@@ -381,8 +383,21 @@ struct Geo {
 // lane-private shared memory on the (rare) steps that contain a save point.
 template <int RPL, int CPL, int MAXNNZ, int VM, bool RS, bool LEAN = false>
 struct Kern {
-    static constexpr bool IM = VM >= 1 && VM <= 3;
-    static constexpr bool SV = VM == 2;
+    // VM == 5, "tiered": a lane owns RPL rows of one column (like the blocked variants), the rows sorted by length
+    // into RPL tiers so that row-slot i of every lane has about the same number of entries; MAXNNZ packs the three
+    // tier capacities as octal digits (0532: 5, 3 and 2 entries).  Purely imaginary generator, static off-diagonal
+    // values in registers.  Against one row x three columns per lane every gathered operand is one complex number
+    // instead of three and no row is padded to the longest row of the matrix.
+    static constexpr bool TR = VM == 5;
+    // VM == 6: value mode 2 with split rows (LaunchArgs::split_info): the longest rows are cut in two, the second
+    // half runs on an otherwise idle lane of the same column group and reaches the owner by one shuffle per stage.
+    static constexpr bool SPL = VM == 6;
+    static constexpr bool IM = (VM >= 1 && VM <= 3) || TR || SPL;
+    static constexpr bool SV = VM == 2 || TR || SPL;
+    static constexpr int NZ = TR ? (MAXNNZ >> 6) : MAXNNZ;   // capacity of the per-lane row tables
+    static __host__ __device__ constexpr int cap(int i) {
+        return !TR ? MAXNNZ : i == 0 ? (MAXNNZ >> 6) : i == 1 ? ((MAXNNZ >> 3) & 7) : (MAXNNZ & 7);
+    }
     // VM == 4, "mixed": a complex generator whose every OFF-DIAGONAL entry is purely real or purely imaginary
     // (Lindblad generators of real Hamiltonians and real collapse operators: couplings come from the commutator and
     // are imaginary, the sandwich terms L rho L' are real; only the diagonal mixes both).  A value table is stored
@@ -390,15 +405,16 @@ struct Kern {
     // it has (its byte offset points into the right half, bit 31 of the entry says which half) and costs 2 DFMA
     // instead of 4; the diagonal entry loads both halves.
     static constexpr bool MX = VM == 4;
-    static constexpr uint32_t VSTRIDE = (VM >= 1 && VM <= 3) ? 8u : 16u;  // table bytes per slot
+    static constexpr uint32_t VSTRIDE = ((VM >= 1 && VM <= 3) || VM == 5 || VM == 6) ? 8u : 16u;  // table bytes per slot
     // VM == 3, "blocked": a lane owns RPL consecutive rows of one column and the off-diagonal part of the
     // generator is stored as dense RPL x RPL blocks (static, purely imaginary, values in registers).  Entry
     // 1 + b of row-slot k names row k of neighbour block b, so the RPL row-slots together load each
     // neighbour block exactly once: RPL * (MAXNNZ - 1) operand loads serve RPL * RPL * (MAXNNZ - 1)
     // multiply-adds (Kronecker-structured couplings reuse every operand RPL times).
     static constexpr bool BLK = VM == 3;
-    static constexpr int NVS = BLK ? (MAXNNZ - 1) * RPL * RPL : RPL * MAXNNZ;  // static values held per lane
-    static_assert(!BLK || CPL == 1, "blocked variants hold one column per lane");
+    static constexpr int NVS = BLK ? (MAXNNZ - 1) * RPL * RPL : RPL * NZ;  // static values held per lane
+    static_assert(!(BLK || TR) || CPL == 1, "blocked and tiered variants hold one column per lane");
+    static_assert(!TR || RPL == 3, "tiered variants: three rows per lane");
     static constexpr int E = RPL * CPL;
     static constexpr uint32_t VB = (IM || MX) ? 8u : 16u;  // bytes per value slot (IM / MX: one real number)
     typedef double2 Vec[E];
@@ -767,7 +783,7 @@ struct Kern {
     // there (the next stage's partial combination) executes under the shared-memory latency.
     template <typename Hook = NoHook>
     static __device__ __forceinline__ void apply(const LaunchArgs &a, const Geo &g, uint32_t Vs, uint32_t yb,
-                                                 const uint32_t (&ell)[RPL][MAXNNZ], const double (&vstat)[NVS],
+                                                 const uint32_t (&ell)[RPL][NZ], const double (&vstat)[NVS],
                                                  const int (&row_of)[RPL], const Vec &yreg, Vec &k, Hook hook = Hook()) {
         if (BLK) {
             constexpr int MB = MAXNNZ > 1 ? MAXNNZ - 1 : 1;  // (row-split variants instantiate MAXNNZ = 1; never blocked)
@@ -796,6 +812,45 @@ struct Kern {
                         acc[i].x = fma(-v, yy[b][kk].y, acc[i].x);
                         acc[i].y = fma(v, yy[b][kk].x, acc[i].y);
                     }
+#pragma unroll
+            for (int i = 0; i < RPL; i++) k[i] = acc[i];
+            return;
+        }
+        if (TR) {
+            // diagonal values (time-dependent: from the stage's table), then the operands of row-slot 0 and, as a
+            // second group, of the shorter row-slots; `hook` runs under the first group's loads
+            double vd[RPL];
+            double2 acc[RPL];
+#pragma unroll
+            for (int i = 0; i < RPL; i++) vd[i] = lds1(Vs + (ell[i][0] >> 16));
+            double2 ya[NZ > 1 ? NZ - 1 : 1];
+#pragma unroll
+            for (int j = 1; j < cap(0); j++) ya[j - 1] = lds2(yb + (ell[0][j] & 0xFFFFu));
+            hook();
+#pragma unroll
+            for (int i = 0; i < RPL; i++) {
+                acc[i].x = -vd[i] * yreg[i].y;
+                acc[i].y = vd[i] * yreg[i].x;
+            }
+            double2 yr[RPL > 1 ? RPL - 1 : 1][NZ > 1 ? NZ - 1 : 1];
+#pragma unroll
+            for (int i = 1; i < RPL; i++)
+#pragma unroll
+                for (int j = 1; j < cap(i); j++) yr[i - 1][j - 1] = lds2(yb + (ell[i][j] & 0xFFFFu));
+#pragma unroll
+            for (int j = 1; j < cap(0); j++) {
+                const double v = vstat[j];
+                acc[0].x = fma(-v, ya[j - 1].y, acc[0].x);
+                acc[0].y = fma(v, ya[j - 1].x, acc[0].y);
+            }
+#pragma unroll
+            for (int i = 1; i < RPL; i++)
+#pragma unroll
+                for (int j = 1; j < cap(i); j++) {
+                    const double v = vstat[i * NZ + j];
+                    acc[i].x = fma(-v, yr[i - 1][j - 1].y, acc[i].x);
+                    acc[i].y = fma(v, yr[i - 1][j - 1].x, acc[i].y);
+                }
 #pragma unroll
             for (int i = 0; i < RPL; i++) k[i] = acc[i];
             return;
@@ -869,7 +924,7 @@ struct Kern {
                         if (j < MAXNNZ) {
                             const uint32_t e = ell[i][j];
                             if (SV)
-                                vv[q] = make_double2(0.0, vstat[i * MAXNNZ + j]);  // time-independent, loaded once per trajectory
+                                vv[q] = make_double2(0.0, vstat[i * NZ + j]);  // time-independent, loaded once per trajectory
                             else
                                 vv[q] = ldv(Vs, e);
 #pragma unroll
@@ -886,8 +941,12 @@ struct Kern {
                     }
                 }
             }
-#ifdef QSIM_SPLIT_ROWS   // (experimental build only: a run-time test here would split the gather's basic block)
-            if (!RS && !BLK && a.split_info) {
+#ifdef QSIM_SPLIT_ROWS   // (experimental build: run-time switch for every row-per-lane kernel; it splits the gather's basic block)
+            const bool do_split = !RS && !BLK && (SPL || a.split_info);
+#else
+            constexpr bool do_split = SPL;
+#endif
+            if (do_split) {
                 // split rows: the owner adds its helper's half, the helper keeps no state of its own
 #pragma unroll
                 for (int c = 0; c < CPL; c++) {
@@ -897,7 +956,6 @@ struct Kern {
                     acc[c].y = g.split_helper ? 0.0 : acc[c].y + (g.split_owner ? py : 0.0);
                 }
             }
-#endif
 #pragma unroll
             for (int c = 0; c < CPL; c++) k[i * CPL + c] = acc[c];
         }
@@ -1064,7 +1122,7 @@ struct Kern {
 
     // ---- one trajectory -----------------------------------------------------------------
     static __device__ __forceinline__ void run(const LaunchArgs &a, const Geo &g, const double *smem_gen,
-                                               const uint32_t (&ell)[RPL][MAXNNZ], const uint32_t (&my_off)[RPL],
+                                               const uint32_t (&ell)[RPL][NZ], const uint32_t (&my_off)[RPL],
                                                const int (&row_of)[RPL], const bool (&row_ok)[RPL],
                                                const int (&sidx)[RPL], double2 *sc_base, long long traj) {
         // sidx: this lane's row indices inside the scratch buffers (row-split teams keep the scratch in their
@@ -1135,8 +1193,8 @@ struct Kern {
 #pragma unroll
             for (int i = 0; i < RPL; i++)
 #pragma unroll
-                for (int j = 0; j < MAXNNZ; j++)
-                    vstat[i * MAXNNZ + j] = (SV && j > 0) ? lds1(g.sm_V + (ell[i][j] >> 16)) : 0.0;
+                for (int j = 0; j < NZ; j++)
+                    vstat[i * NZ + j] = (SV && j > 0 && j < cap(i)) ? lds1(g.sm_V + (ell[i][j] >> 16)) : 0.0;
         }
 
         Vec u, k1, k2, k3, k4, k5, k6, k7, tmp;
@@ -1617,8 +1675,8 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     int g_idx = 0, row0 = g.lane;
     bool lane_active = true;
     g.blk_row = 0;
-    if (K::BLK) {
-        // lane -> (block row, column group): RPL consecutive rows of one column
+    if (K::BLK || K::TR) {
+        // lane -> (block row, column group): RPL consecutive (virtual) rows of one column
         lane_active = g.lane < a.groups * a.n_blk_rows;
         const int le = lane_active ? g.lane : a.groups * a.n_blk_rows - 1;
         g_idx = le / a.n_blk_rows;
@@ -1626,10 +1684,19 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     } else if (RS && a.cu_map) {
         g_idx = g.lane;            // column (within the batch of 32); rows come from the table (rs_perm)
     } else if (a.groups > 1) {
-        lane_active = g.lane < a.groups * n;
-        const int le = lane_active ? g.lane : a.groups * n - 1;
-        g_idx = le / n;
-        row0 = le - g_idx * n;
+        // lanes [0, groups * n): (column group, row); split rows: the next groups * nh lanes are the groups' helpers
+        // (table rows n .. n + nh - 1, no state of their own); the rest mimic the last row lane
+        const int nl = a.groups * n, nh = a.g.n_vrows - n;
+        lane_active = g.lane < nl + a.groups * nh;
+        if (g.lane >= nl && lane_active) {
+            const int h = g.lane - nl;
+            g_idx = h / nh;
+            row0 = n + (h - g_idx * nh);
+        } else {
+            const int le = lane_active ? g.lane : nl - 1;
+            g_idx = le / n;
+            row0 = le - g_idx * n;
+        }
     }
     g.colofs = g_idx * CPL;
     g.split_partner = g.lane;
@@ -1710,7 +1777,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
     int row_of[RPL], sidx[RPL];
     bool row_ok[RPL];
     uint32_t my_off[RPL];
-    uint32_t ell[RPL][MAXNNZ];
+    uint32_t ell[RPL][K::NZ];
 #pragma unroll
     for (int i = 0; i < RPL; i++) {
         if (RS) {
@@ -1731,16 +1798,17 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
             continue;
         }
         sidx[i] = 0;
-        row_of[i] = K::BLK ? g.blk_row * RPL + i : row0 + 32 * i;
+        row_of[i] = (K::BLK || K::TR) ? g.blk_row * RPL + i : row0 + 32 * i;   // (tiered: the virtual row, until below)
         row_ok[i] = lane_active && row_of[i] < n;
         sidx[i] = row_of[i];
         const int row_eff = row_of[i] < n ? row_of[i] : n - 1;
-        my_off[i] = 16u * (row_eff * a.y_row_stride);
+        my_off[i] = 16u * ((K::TR ? __ldg(a.row_pos + row_eff) : row_eff) * a.y_row_stride);
         // the row table may hold more rows than the state (helper lanes of split rows): those lanes gather too
         const bool ell_ok = lane_active && row_of[i] < a.g.n_vrows;
-        const int ell_row = ell_ok ? row_of[i] : n - 1;
+        // (tiered: lanes without a row repeat the last lane's table rows, zero slot: their loads coincide with its loads)
+        const int ell_row = (ell_ok || (K::TR && row_of[i] < n)) ? row_of[i] : n - 1;
 #pragma unroll
-        for (int j = 0; j < MAXNNZ; j++) {
+        for (int j = 0; j < K::NZ; j++) {
             // rows shorter than the variant's capacity: own row, zero slot
             uint32_t e = (uint32_t)row_eff | (0xFFFFu << 16);
             if (!RS && j < a.g.max_nnz) e = a.g.ell[(size_t)j * a.g.n_vrows + ell_row];
@@ -1751,6 +1819,8 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
             if (K::MX && j > 0 && sl < (uint32_t)a.g.n_slots && __ldg(a.slot_imag + sl))
                 ell[i][j] = (ell[i][j] + ((8u * a.nvp) << 16)) | 0x80000000u;
         }
+        // tiered: stage buffer and row table are indexed by the virtual row, initial state and results by the state row
+        if (K::TR) row_of[i] = row_ok[i] ? __ldg(a.row_perm + row_of[i]) : 0;
     }
     double2 *sc_base = nullptr;
     if (a.streamed)

@@ -10,6 +10,7 @@
 // Channels are produced by evaluators: one per time-dependent term (qsim_term) or Lindblad rate.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <mutex>
 #include <vector>
 #include <complex>
@@ -95,4 +96,7 @@ struct qsim_problem {
     struct DeviceCopy;
     std::vector<DeviceCopy *> dev[2];
     std::mutex dev_mutex;
+    // tiered form of each generator (qsim_api.cu, build_tiered): built on first use, under plan_mutex
+    std::shared_ptr<struct TieredForm> tiered[2];
+    std::mutex plan_mutex;
 };

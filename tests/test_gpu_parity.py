@@ -367,6 +367,34 @@ def test_repeated_runs_are_bitwise_identical():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("env,tag", [("QSIM_NO_LEAN", "tsit5_r1c3_nnz5_t128_vm2"), ("QSIM_TIERED", "lean_tiered_r3c1"),
+                                     ("QSIM_SPLIT", "lean_split_r1c3_nnz3")])
+def test_cfg2_kernel_variants(monkeypatch, env, tag):
+    """The default cfg2 kernel is the lean row-per-lane one (168 registers, 12 warps per SM).  The 255-register
+    kernel (QSIM_NO_LEAN=1) and the two opt-in mappings -- three rows of one column per lane sorted into tiers
+    (QSIM_TIERED=1), split rows with helper lanes (QSIM_SPLIT=1) -- take the same step sequence and agree with it to
+    rounding and with the oracle to 1e-8, including dense-output points inside steps (parked stage vectors)."""
+    from qsim_b200 import workloads as W
+    from qsim_b200._ffi import Problem
+    cqs, params, _, fn = W.config("cfg2")
+    pr = np.ascontiguousarray(params[np.linspace(0, len(params) - 1, 40).astype(int)])
+    ts = np.linspace(0.0, 5.0, 11)
+    P = Problem(cqs)
+    assert "tsit5_lean_r1c3_nnz5_t128_vm2" in P.kernel_name(fn)
+    base, st0 = P.solve(fn, ts, params=pr)
+    monkeypatch.setenv(env, "1")
+    P2 = Problem(cqs)
+    assert tag in P2.kernel_name(fn)
+    alt, st1 = P2.solve(fn, ts, params=pr)
+    assert np.all(st1["retcode"] == 0)
+    assert np.array_equal(st0["n_accept"], st1["n_accept"]) and np.array_equal(st0["n_reject"], st1["n_reject"])
+    assert np.max(np.abs(alt - base)) <= 1e-9
+    want, _ = co.OracleProblem(cqs).solve(co.UNITARY_PROPAGATOR, ts, pr, mode=0, n_threads=4)
+    assert np.max(np.abs(alt - want) / np.maximum(np.abs(want), 1e-3)) <= 1e-8
+    assert np.max(np.abs(base - want) / np.maximum(np.abs(want), 1e-3)) <= 1e-8
+
+
+@pytest.mark.gpu
 def test_blocked_variant_opt_in(monkeypatch):
     """QSIM_BLOCKED=1 selects the blocked kernels (3 consecutive rows per lane, dense 3 x 3 coupling blocks with
     values in registers) for the 2-transmon propagators: same step sequence, results within rounding of the
