@@ -1058,9 +1058,14 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.cu = 1;
         pl.groups = 32;
     } else if (n <= 32) {
-        // three columns per lane up to 24 rows, four above: at most eight warps per trajectory
+        // three columns per lane up to 24 rows, four above: at most eight warps per trajectory.  Opt-in (QSIM_LEAN9=1):
+        // 25..27 rows (the 3-transmon gates of cfg3) as nine-warp teams of the lean kernels with three columns per lane;
+        // at the 168 registers nine warps leave each thread that variant spills and measures 5 % slower than the
+        // seven-warp kernel on cfg3 (1.042 s against 0.994 s for 1184 x 50 ns).
         rpl = 1;
-        cpl = pl.ncols > 1 ? (n <= 24 ? 3 : 4) : 1;
+        const bool nine = n > 24 && n <= 27 && pl.ncols > 1 && g.imag_only && std::getenv("QSIM_LEAN9") && !std::getenv("QSIM_NO_LEAN") &&
+                          find_variant(1, 3, g.max_nnz, 288, 1, 0, 1) != nullptr;
+        cpl = pl.ncols > 1 ? ((n <= 24 || nine) ? 3 : 4) : 1;
     } else if (n <= 64) {
         rpl = 2;
         cpl = pl.ncols > 1 ? 2 : 1;
@@ -1190,7 +1195,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     } else if (pl.rowsplit) {
         pl.team_warps = (n + 95) / 96;
         pl.streamed = pl.n_batches > 1 ? 1 : 0;
-    } else if (pl.n_batches <= 8) {
+    } else if (pl.n_batches <= 8 || (pl.n_batches == 9 && rpl == 1 && cpl == 3 && n > 24)) {
         pl.streamed = 0;
         pl.team_warps = pl.n_batches;
     } else {
@@ -1238,9 +1243,6 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.split_nv = 0;
         pl.kv = find_variant(rpl, cpl, g.max_nnz, pl.block, vm, pl.rowsplit);
     }
-    if (!pl.kv)
-        return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
-                                              std::to_string(g.max_nnz) + ")");
     // Lean kernels (Kern<..., LEAN>: early-dying stage vectors, 168 registers, three warps per scheduler) for
     // resident teams when the shape has one; QSIM_NO_LEAN=1 keeps the 255-register kernels (development A/B switch).
     if (!pl.streamed && !pl.rowsplit && !blocked && !split && !pl.tiered && !std::getenv("QSIM_NO_LEAN")) {
@@ -1249,6 +1251,9 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
             pl.lean = 1;
         }
     }
+    if (!pl.kv)
+        return fail(QSIM_ERR_UNSUPPORTED, "generator rows with more than 16 entries have no kernel yet (row length " +
+                                              std::to_string(g.max_nnz) + ")");
     // stage-buffer layout: smallest-cost (row stride, group stride) near the dense one
     if (pl.cu) {
         pl.y_row_stride = 32;   // a row of the stage buffer = 32 columns of 16 bytes: every gather reads one aligned 512-byte row

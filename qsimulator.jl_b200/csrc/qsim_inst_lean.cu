@@ -8,6 +8,11 @@ const KernelVariant *variants_lean(int *count) {
     static const KernelVariant v[] = {
         {1, 3, 5, 128, 3, 2, 0, "tsit5_lean_r1c3_nnz5_t128_vm2", launch_solver<1, 3, 5, 128, 3, 2, false, true>,
          occupancy_solver<1, 3, 5, 128, 3, 2, false, true>, 1},
+        // nine-warp teams (25..27-level propagators, three columns per lane): one team per SM, up to 224 registers
+        {1, 3, 9, 288, 1, 1, 0, "tsit5_lean_r1c3_nnz9_t288_vm1", launch_solver<1, 3, 9, 288, 1, 1, false, true>,
+         occupancy_solver<1, 3, 9, 288, 1, 1, false, true>, 1},
+        {1, 3, 9, 288, 1, 2, 0, "tsit5_lean_r1c3_nnz9_t288_vm2", launch_solver<1, 3, 9, 288, 1, 2, false, true>,
+         occupancy_solver<1, 3, 9, 288, 1, 2, false, true>, 1},
         {1, 3, 3, 128, 3, 6, 0, "tsit5_lean_split_r1c3_nnz3_t128_vm6", launch_solver<1, 3, 3, 128, 3, 6, false, true>,
          occupancy_solver<1, 3, 3, 128, 3, 6, false, true>, 1},
         {3, 1, 0532, 128, 3, 5, 0, "tsit5_lean_tiered_r3c1_nnz532_t128_vm5", launch_solver<3, 1, 0532, 128, 3, 5, false, true>,
