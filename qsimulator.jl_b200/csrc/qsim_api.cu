@@ -1245,6 +1245,8 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     }
     // Lean kernels (Kern<..., LEAN>: early-dying stage vectors, 168 registers, three warps per scheduler) for
     // resident teams when the shape has one; QSIM_NO_LEAN=1 keeps the 255-register kernels (development A/B switch).
+    // (streamed teams stay on the 255-register kernels: the lean form of the d^2 = 81 kernel keeps its spills and
+    // measures 3 % slower on cfg4, 776 ms against 751 ms for 1184 x 5 ns)
     if (!pl.streamed && !pl.rowsplit && !blocked && !split && !pl.tiered && !std::getenv("QSIM_NO_LEAN")) {
         if (const KernelVariant *lv = find_variant(rpl, cpl, eff_nnz, pl.block, vm, 0, 1)) {
             pl.kv = lv;
@@ -1652,7 +1654,8 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.out_first = (dev_ptrs || zero_copy) ? sh.first : 0;
     a.out_step = (dev_ptrs || zero_copy) ? sh.step : 1;
     if (pl.streamed) {
-        CU(c->scratch.reserve(pl.scratch_per_team * (size_t)pl.grid * pl.teams_per_cta));
+        const size_t scratch_bytes = pl.scratch_per_team * (size_t)pl.grid * pl.teams_per_cta;
+        CU(c->scratch.reserve(scratch_bytes));
         a.scratch = (double2 *)c->scratch.p;
         if (n_chunks > 1) CU(c->scratch2.reserve(pl.scratch_per_team * (size_t)pl.grid * pl.teams_per_cta));
     }

@@ -376,7 +376,7 @@ struct Geo {
 // VM (value mode): 0 complex value slots; 1 purely imaginary generator (slots hold Im A, 2 DFMA per
 // multiply-add); 2 as 1 with every off-diagonal entry time-independent: those values live in registers for
 // the whole trajectory and only the diagonal is read from the per-stage table.
-// LEAN (resident teams only): the Runge-Kutta stage vectors are consumed as early as the tableau allows -- after
+// LEAN: the Runge-Kutta stage vectors are consumed as early as the tableau allows -- after
 // stage 6 the combinations for u_new and for the error estimate are formed and k2..k6 die, so stage 7 runs with five
 // live vectors instead of ten -- and operands are requested two row entries at a time.  This fits the step in 168
 // registers (three warps per scheduler instead of two).  The k's a dense-output point needs are parked in
@@ -1552,14 +1552,19 @@ struct Kern {
 #pragma unroll
                         for (int e = 0; e < E; e++) err[0] += fma(ex[e], ex[e], ey[e] * ey[e]);
                     }
-                    if (!LEAN && a.streamed) {
+                    if (a.streamed) {
                         // tentative: the next buffers are adopted only if the step is accepted; dense-output
                         // slots are rewritten by the retried / a later step if it is not
                         store_batch(sc_u0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, sidx, row_ok, tmp);
                         store_batch(sc_k0 + (size_t)(2 * (cur ^ 1)) * sbuf, n, col0, sidx, row_ok, k7);
-                        if (!LEAN && nsave_hi > nsave)
-                            save_points(a, tout, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok, u, k1,
-                                        k2, k3, k4, k5, k6, k7, tmp);
+                        if (nsave_hi > nsave) {
+                            if (LEAN)
+                                save_points_lean(a, g, tout, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok,
+                                                 u, k1, k7, tmp);
+                            else
+                                save_points(a, tout, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok, u, k1,
+                                            k2, k3, k4, k5, k6, k7, tmp);
+                        }
                     }
                 }
                 n_attempt++;

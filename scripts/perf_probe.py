@@ -22,8 +22,9 @@ for item in which:
     t0 = time.perf_counter()
     out, st = P.solve(fn, ts, params=pr, ctx=ctx)
     dt = time.perf_counter() - t0
+    kms = ctx.last_kernel_ms()
     steps = int(st["n_accept"].sum() + st["n_reject"].sum())
     flops = P.flops_per_rhs(fn) * 6.0 * steps
-    print(json.dumps({"cfg": name, "n_traj": n, "t_final": tf, "kernel": P.kernel_name(fn), "seconds": dt,
+    print(json.dumps({"cfg": name, "n_traj": n, "t_final": tf, "kernel": P.kernel_name(fn), "seconds": dt, "kernel_ms": kms,
                       "traj_per_s": n / dt, "steps": steps, "steps_per_s": steps / dt, "rejects": int(st["n_reject"].sum()),
                       "spmv_tflops": flops / dt / 1e12, "retcodes": np.unique(st["retcode"]).tolist()}))
