@@ -179,6 +179,11 @@ int qsim_create(int device, qsim_ctx **out) {
     CU(cudaSetDevice(device));
     qsim_ctx *c = new qsim_ctx();
     c->device = device;
+    // (a failing step below returns through this guard: the partially built ctx is released, not leaked)
+    struct Guard {
+        qsim_ctx *c;
+        ~Guard() { if (c) qsim_destroy(c); }
+    } guard{c};
     CU(cudaGetDeviceProperties(&c->prop, device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&c->d_tab, sizeof(SeriesTables)));
@@ -204,6 +209,7 @@ int qsim_create(int device, qsim_ctx **out) {
         CU(cudaMalloc(&c->d_cheb, sizeof(double) * cheb.size()));
         CU(cudaMemcpy(c->d_cheb, cheb.data(), sizeof(double) * cheb.size(), cudaMemcpyHostToDevice));
     }
+    guard.c = nullptr;
     *out = c;
     return QSIM_OK;
 }
@@ -211,22 +217,22 @@ int qsim_create(int device, qsim_ctx **out) {
 int qsim_destroy(qsim_ctx *c) {
     if (!c) return QSIM_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    cudaStreamSynchronize(c->stream2);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     c->params.release(); c->ts.release(); c->init.release(); c->out.release(); c->out2.release(); c->stats.release();
     c->scratch.release(); c->scratch2.release(); c->sel.release();
     c->fl_seg.release(); c->fl_work.release(); c->fl_idx.release();
-    cudaEventDestroy(c->ev0);
-    cudaEventDestroy(c->ev1);
+    if (c->ev0) cudaEventDestroy(c->ev0);      // (members are null when qsim_create failed half way)
+    if (c->ev1) cudaEventDestroy(c->ev1);
     for (int i = 0; i < 2; i++) {
-        cudaEventDestroy(c->ev_copy[i]);
+        if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
     }
-    cudaStreamDestroy(c->stream2);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaFree(c->d_tab);
     cudaFree(c->d_cheb);
     cudaFree(c->d_counter);
-    cudaStreamDestroy(c->stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return QSIM_OK;
 }
