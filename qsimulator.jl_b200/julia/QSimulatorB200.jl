@@ -28,8 +28,8 @@ module QSimulatorB200
 
 using QSimulator
 using Libdl
-using LinearAlgebra: I
-import QSimulator: CompositeQSystem, QSystem, DuffingTransmon, PerturbativeTransmon, RotatingFrameSystem,
+using LinearAlgebra: I, diag
+import QSimulator: CompositeQSystem, QSystem, DuffingTransmon, PerturbativeTransmon, DiagonalChargeBasisTransmon, RotatingFrameSystem,
                    dimension, spec, hamiltonian, raising, lowering, X, Y, embed
 
 export Param, Signal, CosSignal, SinSignal, ConstSignal, gaussian, erf_squared
@@ -136,7 +136,8 @@ end
 drive closures of src/composite_systems.jl:40-50.  `f` is sampled into a piecewise Chebyshev series whose segment
 count doubles until it reproduces `f` at 2*n_coef off-node points per segment to `tol * max|f|`.
 """
-function tabulated(f::Function, t_start::Real, t_end::Real; amp=1.0, offset=0.0, n_coef::Int=12, tol::Real=1e-14)
+function tabulated(f::Function, t_start::Real, t_end::Real; amp=1.0, offset=0.0, n_coef::Int=12, tol::Real=1e-14,
+                   atol::Real=0.0, max_seg::Int=1 << 16)
     N = n_coef
     nodes = [cos(pi * (j + 0.5) / N) for j in 0:N-1]
     dct = [(k == 0 ? 1.0 : 2.0) / N * cos(pi * k * (j + 0.5) / N) for k in 0:N-1, j in 0:N-1]
@@ -156,8 +157,8 @@ function tabulated(f::Function, t_start::Real, t_end::Real; amp=1.0, offset=0.0,
             want = Float64(f(t))
             err = max(err, abs(tb(t) - want)); scale = max(scale, abs(want))
         end
-        if err <= tol * scale || n_seg >= (1 << 16)
-            err <= 1e-9 * scale || error("could not tabulate the function to 1e-9 with $n_seg segments")
+        if err <= max(tol * scale, atol) || n_seg >= max_seg
+            err <= max(1e-9 * scale, atol) || error("could not tabulate the function to 1e-9 with $n_seg segments")
             return Signal(CARRIER_NONE, ENV_TABLE, 0, offset, amp, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, tb)
         end
         n_seg *= 2
@@ -202,8 +203,27 @@ struct Lowered
     atom_b::Union{Nothing,Matrix{ComplexF64}}
     rate::Scalar; anharm::Scalar; rot::Scalar; EC::Scalar; EJ1::Scalar; EJ2::Scalar
     num_terms::Int
+    level_tables::Vector{Table}      # TERM_SPECTRUM: E_k(z), z = cos(pi*flux) on [-1, 1], one table per level
 end
-const TERM_SCALAR, TERM_ROTATING, TERM_DUFFING, TERM_TRANSMON = Int32(0), Int32(1), Int32(2), Int32(3)
+Lowered(kind, signal, a, b, rate, anharm, rot, EC, EJ1, EJ2, num_terms) =
+    Lowered(kind, signal, a, b, rate, anharm, rot, EC, EJ1, EJ2, num_terms, Table[])
+const TERM_SCALAR, TERM_ROTATING, TERM_DUFFING, TERM_TRANSMON, TERM_SPECTRUM = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
+
+"""
+Level energies of a DiagonalChargeBasisTransmon (src/systems.jl:143-152, 231-237) as tables in z = cos(pi*flux):
+the spectrum depends on the flux only through EJ(flux)^2 = (EJ1 - EJ2)^2 + 4 EJ1 EJ2 z^2 and is a smooth even
+function of z.  Built once per problem; the reference diagonalises the charge-basis Hamiltonian in every RHS call.
+"""
+function charge_spectrum_tables(base::DiagonalChargeBasisTransmon)
+    sp = spec(base)
+    cache = Dict{Float64,Vector{Float64}}()
+    levels(z) = get!(cache, z) do
+        real.(diag(hamiltonian(base, acos(clamp(z, -1.0, 1.0)) / pi)))
+    end
+    atol = 4e-15 * max(4 * abs(sp.EC) * (base.num_terms ÷ 2)^2, abs(sp.EJ1) + abs(sp.EJ2), 1.0)
+    [tabulated(z -> levels(z)[k], -1.0, 1.0; n_coef=14, tol=1e-14, atol=atol, max_seg=1 << 10).table
+     for k in 1:dimension(base)]
+end
 
 "Time-dependent subsystem Hamiltonian: `ham(t)` like the reference's closures, plus descriptors."
 struct ParametricHamiltonian <: Function
@@ -244,6 +264,10 @@ function parametric_drive_b200(q::QSystem, drive)
     elseif base isa PerturbativeTransmon
         sp = spec(base)
         Lowered(TERM_TRANSMON, s, nothing, nothing, 0.0, 0.0, rot, sp.EC, sp.EJ1, sp.EJ2, base.num_terms)
+    elseif base isa DiagonalChargeBasisTransmon
+        sp = spec(base)
+        Lowered(TERM_SPECTRUM, s, nothing, nothing, 0.0, 0.0, rot, sp.EC, sp.EJ1, sp.EJ2, base.num_terms,
+                charge_spectrum_tables(base))
     else
         error("parametric_drive_b200: no kernel form for $(typeof(base))")
     end
@@ -305,8 +329,8 @@ function Problem(cqs::CompositeQSystem, n_params::Integer)
     check(ccall((:qsim_problem_set_h0, libqsim), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), prob.handle, h0))
     # tabulated envelopes: one qsim_problem_add_table per distinct Table, ids handed to the signals below
     table_ids = Dict{UInt,Int32}()
-    function register(sig::Signal)
-        tb = sig.table
+    register(sig::Signal) = register(sig.table)
+    function register(tb::Union{Nothing,Table})
         (tb === nothing || haskey(table_ids, objectid(tb))) && return
         n_coef, n_seg = size(tb.coef)
         id = Ref{Int32}(0)
@@ -316,7 +340,7 @@ function Problem(cqs::CompositeQSystem, n_params::Integer)
         table_ids[objectid(tb)] = id[]
     end
     for (ham, _) in cqs.parametric_Hs
-        ham isa ParametricHamiltonian && foreach(lo -> register(lo.signal), ham.lowered)
+        ham isa ParametricHamiltonian && foreach(lo -> (register(lo.signal); foreach(register, lo.level_tables)), ham.lowered)
     end
     for (lf, _) in cqs.parametric_Ls
         lf isa ScaledLindblad && register(lf.scale)
@@ -332,6 +356,14 @@ function Problem(cqs::CompositeQSystem, n_params::Integer)
                 check(ccall((:qsim_problem_add_term, libqsim), Cint,
                             (Ptr{Cvoid}, Ref{CTerm}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Int32}),
                             prob.handle, term, a, b === nothing ? C_NULL : b, C_NULL))
+            elseif lo.kind == TERM_SPECTRUM
+                # flux drive on a DiagonalChargeBasisTransmon: the level tables registered above
+                lv = levels_from_indices(cqs, idxs)
+                ids = Int32[table_ids[objectid(tb)] for tb in lo.level_tables]
+                rot = Ref(Slot(lo.rot))
+                check(ccall((:qsim_problem_add_spectrum_term, libqsim), Cint,
+                            (Ptr{Cvoid}, Ref{CSignal}, Ref{Slot}, Ptr{Int32}, Cint, Ptr{Int32}),
+                            prob.handle, Ref(csignal(lo.signal, table_ids)), rot, lv, length(ids), ids))
             else
                 lv = levels_from_indices(cqs, idxs)
                 check(ccall((:qsim_problem_add_term, libqsim), Cint,

@@ -1,5 +1,6 @@
-"""Summarise the full-size ncu capture (gpurun_out/prof_r1_final_full.ncu-rep) into profiles/: key raw-page metrics,
-per-step instruction and wavefront counts, and profiles/traffic.json (DRAM bytes per launch for bench.py)."""
+"""Summarise a full-size ncu capture into profiles/: key raw-page metrics, per-step instruction and wavefront counts,
+and profiles/traffic.json (DRAM bytes per launch, bench.py's cross-check).
+usage: full_capture_summary.py <rep> <plain bench log of the same command> <output name under profiles/>"""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "prof_r1_final_full.ncu-rep")
@@ -25,7 +26,8 @@ wr = float(d['dram__bytes_write.sum'][1]) * unit[d['dram__bytes_write.sum'][0]]
 plain = json.loads(open(plain_log).read().strip().splitlines()[-1])
 steps = plain['config']['attempted_steps_per_launch']
 kernel = plain['config']['kernel']
-out = os.path.join(ROOT, "profiles", "r1_ncu_cfg2full_final.txt")
+out_name = sys.argv[3] if len(sys.argv) > 3 else "r1_ncu_cfg2full_final.txt"
+out = os.path.join(ROOT, "profiles", out_name)
 with open(out, "w") as f:
     f.write(f"# ncu --set full --clock-control none, kernel {d['Kernel Name'][1].strip()} ({kernel})\n")
     f.write("# command: python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline  (-k regex:solve_kernel -s 3 -c 1: the timed full-size launch)\n")
@@ -39,7 +41,9 @@ with open(out, "w") as f:
     f.write(f"# DRAM traffic per launch = {rd / 1e6:.1f} MB read + {wr / 1e6:.1f} MB written = {(rd + wr) / 1e9:.3f} GB vs 1.067 GB algorithmic\n"
             "# (the result stream; the few tens of MB on top are dirty lines of the 256 MB L2-flush buffer written before the\n"
             "# launch and evicted during it, and varies from capture to capture); no re-reads of the state.\n")
-json.dump([{"kernel": kernel, "points": 4096, "n_ts": 201, "dram_bytes_read": rd, "dram_bytes_write": wr,
-            "source": "profiles/r1_ncu_cfg2full_final.txt (ncu --set full of the timed full-size launch)"}],
-          open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+tj = os.path.join(ROOT, "profiles", "traffic.json")
+recs = [r for r in (json.load(open(tj)) if os.path.exists(tj) else []) if r.get("kernel") != kernel]
+recs.append({"kernel": kernel, "points": 4096, "n_ts": 201, "dram_bytes_read": rd, "dram_bytes_write": wr,
+             "source": f"profiles/{out_name} (ncu --set full of the timed full-size launch)"})
+json.dump(recs, open(tj, "w"), indent=1)
 print(open(out).read())
