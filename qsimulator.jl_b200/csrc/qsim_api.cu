@@ -111,6 +111,9 @@ struct qsim_problem::DeviceCopy {
     uint16_t *blk_slot = nullptr;
     uint32_t *tr_ell = nullptr;      // tiered kernels: row table over virtual rows, virtual -> state row
     int *tr_perm = nullptr, *tr_pos = nullptr;
+    uint32_t *as_ell = nullptr;      // additively split rows: row table over the table rows, table row -> state row, lane info
+    int *as_phys = nullptr;
+    uint8_t *as_info = nullptr;
     ~DeviceCopy() { free_all(); }  // the owning device must be current
     void free_all() {
         for (auto &pk : packed) {
@@ -136,6 +139,12 @@ struct qsim_problem::DeviceCopy {
         cudaFree(tr_pos);
         tr_ell = nullptr;
         tr_perm = tr_pos = nullptr;
+        cudaFree(as_ell);
+        cudaFree(as_phys);
+        cudaFree(as_info);
+        as_ell = nullptr;
+        as_phys = nullptr;
+        as_info = nullptr;
         cudaFree(dyn_rec);
         dyn_rec = nullptr;
         cudaFree(tables);
@@ -542,6 +551,7 @@ struct Plan {
     int lean = 0, off_park = 0;        // lean variant chosen (Kern<..., LEAN>); its park area inside the team region
     int tiered = 0;                    // tiered variant (value mode 5): blk_rows / blk_nnz hold its geometry
     const struct TieredForm *tf = nullptr;   // its table, row permutation and stage layout (cached in the problem)
+    const struct AddSplitForm *af = nullptr; // additively split rows (value mode 7): table-row generator, maps (cached in the problem)
     std::vector<uint8_t> slot_imag;    // value mode 4: per slot, 1 = purely imaginary, 0 = purely real
     // blocked variant (value mode 3): block rows, row table [1 + max blocks][n] and value slot ids
     int blk_rows = 0, blk_nnz = 0;
@@ -761,6 +771,113 @@ static bool build_tiered(const Generator &g, int groups, TieredForm &tf) {
                 tf.ell[(1 + j) * (size_t)n + v] = (uint32_t)best.pos[(size_t)(e[j] & 0xFFFFu)] | (e[j] & 0xFFFF0000u);
         }
     tf.ok = true;
+    return true;
+}
+
+// Additively split rows (value mode 7, Kern::AS).  With idle lanes in a grouped warp (groups * n < 32) the longest
+// rows of the generator are carried as two table rows whose states add up to the physical entry: each part keeps the
+// diagonal term on itself and half of the row's couplings, and every row that couples to a split row reads both parts
+// (one more entry).  A row is split while that lowers the longest row of the table.  The form holds a generator copy
+// over the n_v table rows (for the layout search), the table-row -> state-row map and the per-lane partner info.
+struct AddSplitForm {
+    bool ok = false;
+    int n_v = 0, groups = 0, nnz = 0;
+    Generator gv;                      // n = n_v, ell over table rows, everything else as the physical generator
+    std::vector<int> phys;             // table row -> state row
+    std::vector<uint8_t> lane_info;    // [32]: partner lane | 32 helper | 64 owner (as LaunchArgs::split_info)
+};
+
+static bool build_addsplit(const Generator &g, int ncols, AddSplitForm &af) {
+    const int n = g.n;
+    if (!g.imag_only) return false;
+    std::vector<std::vector<uint32_t>> off((size_t)n);
+    for (int r = 0; r < n; r++)
+        for (int j = 1; j < g.max_nnz; j++) {
+            const uint32_t e = g.ell[(size_t)j * n + r];
+            if ((e >> 16) == 0xFFFFu) continue;
+            if ((int)(e >> 16) < g.n_dyn_slots) return false;   // time-dependent off-diagonal entry
+            off[(size_t)r].push_back(e);
+        }
+    // greedy: split the longest unsplit row while lanes remain and the longest table row gets shorter
+    std::vector<int> split;   // physical rows carried as two parts
+    auto lengths = [&](const std::vector<int> &sp, std::vector<int> *len_out) {
+        int longest = 0;
+        std::vector<int> len((size_t)n, 0);
+        for (int r = 0; r < n; r++) {
+            int L = 0;
+            for (uint32_t e : off[(size_t)r])
+                L += std::find(sp.begin(), sp.end(), (int)(e & 0xFFFFu)) != sp.end() ? 2 : 1;
+            len[(size_t)r] = std::find(sp.begin(), sp.end(), r) != sp.end() ? (L + 1) / 2 : L;
+            longest = std::max(longest, len[(size_t)r]);
+        }
+        if (len_out) *len_out = len;
+        return longest;
+    };
+    int best = lengths(split, nullptr);
+    for (;;) {
+        const int n_v = n + (int)split.size() + 1;
+        const int groups = std::min(32 / n_v, ncols);
+        if (groups < 1 || groups * (ncols > 1 ? 3 : 1) < ncols) break;   // the whole propagator must stay in one warp
+        std::vector<int> len;
+        lengths(split, &len);
+        int cand = -1;
+        for (int r = 0; r < n; r++)
+            if (std::find(split.begin(), split.end(), r) == split.end() && (cand < 0 || len[(size_t)r] > len[(size_t)cand])) cand = r;
+        if (cand < 0) break;
+        std::vector<int> trial = split;
+        trial.push_back(cand);
+        const int L = lengths(trial, nullptr);
+        if (L >= best) break;
+        best = L;
+        split = trial;
+    }
+    if (split.empty()) return false;
+    const int n_v = n + (int)split.size();
+    af.n_v = n_v;
+    af.groups = std::min(32 / n_v, ncols);
+    af.nnz = 1 + best;
+    af.phys.assign((size_t)n_v, 0);
+    std::vector<int> helper_of((size_t)n, -1);
+    for (int r = 0; r < n; r++) af.phys[(size_t)r] = r;
+    for (size_t k = 0; k < split.size(); k++) {
+        helper_of[(size_t)split[k]] = n + (int)k;
+        af.phys[(size_t)n + k] = split[k];
+    }
+    af.gv = g;
+    af.gv.n = n_v;
+    af.gv.max_nnz = af.nnz;
+    af.gv.ell.assign((size_t)af.nnz * n_v, 0);
+    af.gv.row_len.assign((size_t)n_v, 0);
+    for (int v = 0; v < n_v; v++)
+        for (int j = 0; j < af.nnz; j++) af.gv.ell[(size_t)j * n_v + v] = (uint32_t)v | (0xFFFFu << 16);
+    for (int r = 0; r < n; r++) {
+        std::vector<uint32_t> ex;   // expanded entries: a split source appears as both of its parts
+        for (uint32_t e : off[(size_t)r]) {
+            const int src = (int)(e & 0xFFFFu);
+            ex.push_back(e);
+            if (helper_of[(size_t)src] >= 0) ex.push_back((uint32_t)helper_of[(size_t)src] | (e & 0xFFFF0000u));
+        }
+        const uint32_t dslot = g.ell[(size_t)r] & 0xFFFF0000u;
+        const int h = helper_of[(size_t)r];
+        const size_t first = h >= 0 ? (ex.size() + 1) / 2 : ex.size();
+        af.gv.ell[(size_t)r] = (uint32_t)r | dslot;
+        for (size_t j = 0; j < first; j++) af.gv.ell[(1 + j) * (size_t)n_v + r] = ex[j];
+        af.gv.row_len[(size_t)r] = (uint8_t)(1 + first);
+        if (h >= 0) {
+            af.gv.ell[(size_t)h] = (uint32_t)h | dslot;   // the diagonal term acts on each part
+            for (size_t j = first; j < ex.size(); j++) af.gv.ell[(1 + j - first) * (size_t)n_v + h] = ex[j];
+            af.gv.row_len[(size_t)h] = (uint8_t)(1 + ex.size() - first);
+        }
+    }
+    af.lane_info.assign(32, 0);
+    for (int l = 0; l < 32; l++) af.lane_info[(size_t)l] = (uint8_t)l;
+    for (int gi = 0; gi < af.groups; gi++)
+        for (size_t k = 0; k < split.size(); k++) {
+            const int lo = gi * n_v + split[k], lh = gi * n_v + n + (int)k;
+            af.lane_info[(size_t)lo] = (uint8_t)(lh | 64);
+            af.lane_info[(size_t)lh] = (uint8_t)(lo | 32);
+        }
+    af.ok = true;
     return true;
 }
 
@@ -1043,10 +1160,27 @@ static void build_rowsplit_table(const Generator &g, Plan &pl, bool full) {
 static int make_plan(qsim_problem *p, int which, Plan &pl) {
     pl.w = which >= 2 ? 1 : 0;
     if (int rc = ensure_generator(p, pl.w)) return rc;
-    const Generator &g = p->gen[pl.w];
-    const int n = g.n;
+    const Generator &gp = p->gen[pl.w];
     pl.identity = (which == 0 || which == 2) ? 1 : 0;
-    pl.ncols = pl.identity ? n : 1;
+    pl.ncols = pl.identity ? gp.n : 1;
+    // Additively split rows (value mode 7) for small propagators that leave lanes idle in their warp (the 2-transmon
+    // gates: 9 rows x 3 column groups on 27 lanes; split, 10 table rows of 1 + 2 entries on 30 lanes instead of rows
+    // padded to 1 + 4).  From here on the plan is made for the generator over the table rows; only the number of
+    // columns, the results and the norms refer to the physical rows.  Opt-in (QSIM_ADDSPLIT=1): parity-green, 40 % fewer
+    // generator multiply-adds and half the operand loads per stage, and still 2 % slower than the padded lean kernel
+    // (cfg2: 566 ms against 555 ms) -- the shuffles that combine the parts for the error norm sit on the step's chain.
+    if (pl.identity && gp.n <= 15 && gp.imag_only && std::getenv("QSIM_ADDSPLIT") && !std::getenv("QSIM_NO_LEAN") &&
+        !std::getenv("QSIM_BLOCKED") && !std::getenv("QSIM_TIERED") && !std::getenv("QSIM_SPLIT")) {
+        std::lock_guard<std::mutex> lk(p->plan_mutex);
+        if (!p->addsplit[pl.w]) {
+            p->addsplit[pl.w] = std::make_shared<AddSplitForm>();
+            build_addsplit(gp, pl.ncols, *p->addsplit[pl.w]);
+        }
+        const AddSplitForm *af = p->addsplit[pl.w].get();
+        if (af->ok && find_variant(1, 3, af->nnz, 128, 7, 0, 1)) pl.af = af;
+    }
+    const Generator &g = pl.af ? pl.af->gv : gp;
+    const int n = g.n;
     int rpl, cpl;
     if (n <= 16) {
         rpl = 1;
@@ -1225,6 +1359,8 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         vm = 5;
     } else if (split6) {
         vm = 6;
+    } else if (pl.af) {
+        vm = 7;
     } else if (vm == 1 && !pl.rowsplit) {
         bool static_off = true;
         for (int j = 1; j < g.max_nnz && static_off; j++)
@@ -1241,9 +1377,10 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     }
     pl.vm = vm;
     pl.kv = pl.tiered ? tiered_kv
+            : pl.af   ? find_variant(rpl, cpl, pl.af->nnz, pl.block, 7, 0, 1)
             : split6  ? find_variant(rpl, cpl, pl.split_nnz, pl.block, 6, 0, 1)
                       : find_variant(rpl, cpl, blocked ? pl.blk_nnz : eff_nnz, pl.block, vm, pl.rowsplit);
-    if (pl.tiered || split6) pl.lean = 1;
+    if (pl.tiered || split6 || pl.af) pl.lean = 1;
     if (!pl.kv && split) {   // (no variant with the shorter capacity and this value mode: fall back to whole rows)
         split = false;
         pl.split_nv = 0;
@@ -1308,7 +1445,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     for (int sl = 0; sl < g.n_dyn_slots; sl++)
         if (g.slot_ptr[sl + 1] - g.slot_ptr[sl] > 3) pl.dyn_fast = 0;
     pl.common_bytes = pl.off_drec + (pl.dyn_fast ? 64 * std::max(g.n_dyn_slots, 1) : 16);
-    pl.team_bytes = (((((pl.vm >= 1 && pl.vm <= 3) || pl.vm == 5 || pl.vm == 6) ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
+    pl.team_bytes = (((((pl.vm >= 1 && pl.vm <= 3) || pl.vm >= 5) ? 8 : 16) * 5 * pl.nvp + 15) & ~15) + 8 * 5 * pl.ncp + (int)sizeof(ResolvedEval) * n_ev + 256 * pl.ncp + 8 * (pl.team_warps * 4 + 8) +
                     (pl.rowsplit ? 1 : pl.team_warps) * 2 * 16 * n * pl.y_row_stride + 128 * pl.team_warps;
     if (pl.lean) {   // park area: k2..k6 of a step with save points, 512 bytes per entry and warp
         pl.off_park = (pl.team_bytes + 15) & ~15;
@@ -1559,6 +1696,11 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
             CU(upload(&dc->blk_ell, pl.blk_ell));
             CU(upload(&dc->blk_slot, pl.blk_slot));
         }
+        if (pl.af && !dc->as_ell) {
+            CU(upload(&dc->as_ell, pl.af->gv.ell));
+            CU(upload(&dc->as_phys, pl.af->phys));
+            CU(upload(&dc->as_info, pl.af->lane_info));
+        }
         if (pl.tiered && !dc->tr_ell) {
             CU(upload(&dc->tr_ell, pl.tf->ell));
             CU(upload(&dc->tr_perm, pl.tf->perm));
@@ -1667,6 +1809,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     }
 
     a.g.n = g.n;
+    a.n_out = g.n;
     a.g.max_nnz = g.max_nnz;
     a.g.n_slots = g.n_slots;
     a.g.n_dyn_slots = g.n_dyn_slots;
@@ -1703,6 +1846,14 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         a.n_blk_rows = pl.blk_rows;
         a.row_perm = d_tr_perm;
         a.row_pos = d_tr_pos;
+    }
+    if (pl.af) {   // the kernel runs over the table rows; results, norms and the initial state refer to the state rows
+        a.g.n = pl.af->n_v;
+        a.g.n_vrows = pl.af->n_v;
+        a.g.ell = dc->as_ell;
+        a.g.max_nnz = pl.af->nnz;
+        a.row_perm = dc->as_phys;
+        a.split_info = dc->as_info;
     }
     if (pl.split_nv > 0) {
         a.g.ell = dc->split_ell;

@@ -57,6 +57,7 @@ struct DevGenerator {
 struct LaunchArgs {
     DevGenerator g;
     int ncols;            // columns of the state (1 for *_state)
+    int n_out;            // rows of the state as the caller sees it (= g.n except with additively split rows, where g.n counts table rows)
     int identity_init;    // 1: u0 = I (propagators); 0: u0 = init (column 0)
     int n_params, n_ts;
     long long ts_stride, init_stride, n_traj;
@@ -392,8 +393,16 @@ struct Kern {
     // VM == 6: value mode 2 with split rows (LaunchArgs::split_info): the longest rows are cut in two, the second
     // half runs on an otherwise idle lane of the same column group and reaches the owner by one shuffle per stage.
     static constexpr bool SPL = VM == 6;
-    static constexpr bool IM = (VM >= 1 && VM <= 3) || TR || SPL;
-    static constexpr bool SV = VM == 2 || TR || SPL;
+    // VM == 7: value mode 2 on a generator with ADDITIVELY split rows.  A long row p is carried as two table rows whose
+    // states add up to the physical entry, u_p = u_pa + u_pb: each part integrates the diagonal term on itself plus its
+    // half of the row's couplings (the equation is linear, so the sum obeys the original one), and every row that
+    // couples to p reads both parts.  The parts live on different lanes (the second on an otherwise idle one) and
+    // exchange nothing during the stages; only the error norm, the initial-step norms and the results need the
+    // physical entry and combine the parts by shuffles (once per step instead of once per stage as in mode 6).
+    // LaunchArgs::split_info marks owner / helper lanes, row_perm maps table rows to state rows, n_out counts them.
+    static constexpr bool AS = VM == 7;
+    static constexpr bool IM = (VM >= 1 && VM <= 3) || TR || SPL || AS;
+    static constexpr bool SV = VM == 2 || TR || SPL || AS;
     static constexpr int NZ = TR ? (MAXNNZ >> 6) : MAXNNZ;   // capacity of the per-lane row tables
     static __host__ __device__ constexpr int cap(int i) {
         return !TR ? MAXNNZ : i == 0 ? (MAXNNZ >> 6) : i == 1 ? ((MAXNNZ >> 3) & 7) : (MAXNNZ & 7);
@@ -405,7 +414,7 @@ struct Kern {
     // it has (its byte offset points into the right half, bit 31 of the entry says which half) and costs 2 DFMA
     // instead of 4; the diagonal entry loads both halves.
     static constexpr bool MX = VM == 4;
-    static constexpr uint32_t VSTRIDE = ((VM >= 1 && VM <= 3) || VM == 5 || VM == 6) ? 8u : 16u;  // table bytes per slot
+    static constexpr uint32_t VSTRIDE = ((VM >= 1 && VM <= 3) || VM >= 5) ? 8u : 16u;  // table bytes per slot
     // VM == 3, "blocked": a lane owns RPL consecutive rows of one column and the off-diagonal part of the
     // generator is stored as dense RPL x RPL blocks (static, purely imaginary, values in registers).  Entry
     // 1 + b of row-slot k names row k of neighbour block b, so the RPL row-slots together load each
@@ -415,6 +424,13 @@ struct Kern {
     static constexpr int NVS = BLK ? (MAXNNZ - 1) * RPL * RPL : RPL * NZ;  // static values held per lane
     static_assert(!(BLK || TR) || CPL == 1, "blocked and tiered variants hold one column per lane");
     static_assert(!TR || RPL == 3, "tiered variants: three rows per lane");
+    static_assert(!AS || (LEAN && !RS && RPL == 1), "additively split rows: lean one-row-per-lane kernels");
+
+    // the physical entry of an additively split row: the owner lane's part plus its helper's (other lanes: unchanged)
+    static __device__ __forceinline__ double as_sum(const Geo &g, double v) {
+        const double p = __shfl_sync(0xffffffffu, v, g.split_partner);
+        return g.split_owner ? v + p : v;
+    }
     static constexpr int E = RPL * CPL;
     static constexpr uint32_t VB = (IM || MX) ? 8u : 16u;  // bytes per value slot (IM / MX: one real number)
     typedef double2 Vec[E];
@@ -961,15 +977,23 @@ struct Kern {
         }
     }
 
-    static __device__ __forceinline__ void write_out(const LaunchArgs &a, long long traj, int ksave, int col0,
-                                                     const int (&row_of)[RPL], const bool (&row_ok)[RPL], const Vec &x) {
-        const int n = a.g.n;
+    static __device__ __forceinline__ void write_out(const LaunchArgs &a, const Geo &g, long long traj, int ksave, int col0,
+                                                     const int (&row_of)[RPL], const bool (&row_ok)[RPL], const Vec &x_in) {
+        const int n = a.n_out;
+        Vec xs;
+        bool ok[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; i++) ok[i] = row_ok[i] && !(AS && g.split_helper);
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            xs[e] = AS ? make_double2(as_sum(g, x_in[e].x), as_sum(g, x_in[e].y)) : x_in[e];
+        const Vec &x = xs;
         if (a.sel_index) {
             // reduced output: only the selected entries leave the chip
             const size_t base = ((size_t)traj * a.n_ts + ksave) * (size_t)a.n_sel;
 #pragma unroll
             for (int i = 0; i < RPL; i++)
-                if (row_ok[i]) {
+                if (ok[i]) {
 #pragma unroll
                     for (int c = 0; c < CPL; c++) {
                         const int col = col0 + c;
@@ -990,7 +1014,7 @@ struct Kern {
         double2 *dst = a.out + ((size_t)traj * a.n_ts + ksave) * (size_t)a.ncols * n;
 #pragma unroll
         for (int i = 0; i < RPL; i++)
-            if (row_ok[i]) {
+            if (ok[i]) {
 #pragma unroll
                 for (int c = 0; c < CPL; c++) {
                     const int col = col0 + c;
@@ -999,14 +1023,14 @@ struct Kern {
             }
     }
 
-    static __device__ __forceinline__ void initial_state(const LaunchArgs &a, long long traj, int col0,
+    static __device__ __forceinline__ void initial_state(const LaunchArgs &a, const Geo &g, long long traj, int col0,
                                                          const int (&row_of)[RPL], const bool (&row_ok)[RPL], Vec &u) {
 #pragma unroll
         for (int i = 0; i < RPL; i++)
 #pragma unroll
             for (int c = 0; c < CPL; c++) {
                 double2 v = make_double2(0.0, 0.0);
-                if (row_ok[i] && col0 + c < a.ncols) {
+                if (row_ok[i] && col0 + c < a.ncols && !(AS && g.split_helper)) {   // (a helper part starts at zero)
                     if (a.identity_init)
                         v.x = (row_of[i] == col0 + c) ? 1.0 : 0.0;
                     else
@@ -1017,7 +1041,7 @@ struct Kern {
     }
 
     // Dense output (Tsit5 free interpolant) for save points [k_lo, k_hi) of the step [t, t+dt].
-    static __device__ __forceinline__ void save_points(const LaunchArgs &a, long long traj, const double *ts, int k_lo,
+    static __device__ __forceinline__ void save_points(const LaunchArgs &a, const Geo &g, long long traj, const double *ts, int k_lo,
                                                        int k_hi, double t, double dt, double tnew, int col0,
                                                        const int (&row_of)[RPL], const bool (&row_ok)[RPL],
                                                        const Vec &u, const Vec &k1, const Vec &k2, const Vec &k3,
@@ -1026,7 +1050,7 @@ struct Kern {
         for (int ks = k_lo; ks < k_hi; ks++) {
             const double tsv = ts[ks];
             if (tsv == tnew) {
-                write_out(a, traj, ks, col0, row_of, row_ok, unew);
+                write_out(a, g, traj, ks, col0, row_of, row_ok, unew);
             } else {
                 const double th = (tsv - t) / dt;
                 const double th2 = th * th;
@@ -1049,7 +1073,7 @@ struct Kern {
                     sx += k7[e].x * b7; sy += k7[e].y * b7;
                     o[e] = make_double2(u[e].x + dt * sx, u[e].y + dt * sy);
                 }
-                write_out(a, traj, ks, col0, row_of, row_ok, o);
+                write_out(a, g, traj, ks, col0, row_of, row_ok, o);
             }
         }
     }
@@ -1068,7 +1092,7 @@ struct Kern {
         for (int ks = k_lo; ks < k_hi; ks++) {
             const double tsv = ts[ks];
             if (tsv == tnew) {
-                write_out(a, traj, ks, col0, row_of, row_ok, unew);
+                write_out(a, g, traj, ks, col0, row_of, row_ok, unew);
             } else {
                 const double th = (tsv - t) / dt;
                 const double th2 = th * th;
@@ -1097,7 +1121,7 @@ struct Kern {
                     o[e].y += k7[e].y * bb[6];
                     o[e] = make_double2(u[e].x + dt * o[e].x, u[e].y + dt * o[e].y);
                 }
-                write_out(a, traj, ks, col0, row_of, row_ok, o);
+                write_out(a, g, traj, ks, col0, row_of, row_ok, o);
             }
         }
     }
@@ -1132,7 +1156,7 @@ struct Kern {
         const double *ts = a.ts + (size_t)tin * a.ts_stride;
         const double *prow = a.params + (size_t)tin * a.n_params;
         const double t0 = ts[0], tend = ts[a.n_ts - 1];
-        const double ntot = (double)n * (double)a.ncols;
+        const double ntot = (double)a.n_out * (double)a.ncols;
         const uint32_t V0 = g.sm_V, V1 = V0 + g.v_stride, V2 = V1 + g.v_stride, V3 = V2 + g.v_stride, V4 = V3 + g.v_stride;
         const uint32_t yb0 = g.sm_y0, yb1 = g.sm_y1;
         const size_t sbuf = (size_t)a.n_batches * g.cpb * n;
@@ -1211,8 +1235,8 @@ struct Kern {
             double acc2[2] = {0.0, 0.0};
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                 const int col0 = b * g.cpb + g.colofs;
-                initial_state(a, tin, col0, row_of, row_ok, u);
-                for (int ks = 0; ks < nsave; ks++) write_out(a, tout, ks, col0, row_of, row_ok, u);
+                initial_state(a, g, tin, col0, row_of, row_ok, u);
+                for (int ks = 0; ks < nsave; ks++) write_out(a, g, tout, ks, col0, row_of, row_ok, u);
                 put_stage(a, g, u, yb0, my_off, row_ok);
                 apply(a, g, V0, yb0, ell, vstat, row_of, u, k1);
                 if (a.streamed) {
@@ -1221,10 +1245,15 @@ struct Kern {
                 }
 #pragma unroll
                 for (int e = 0; e < E; e++) {
-                    const double sk = a.abstol + sqrt(u[e].x * u[e].x + u[e].y * u[e].y) * a.reltol;
-                    const double ux = u[e].x / sk, uy = u[e].y / sk, fx = k1[e].x / sk, fy = k1[e].y / sk;
-                    acc2[0] += ux * ux + uy * uy;
-                    acc2[1] += fx * fx + fy * fy;
+                    // (additively split rows: norms are taken over the physical entries; a helper part counts nothing)
+                    const double2 up = AS ? make_double2(as_sum(g, u[e].x), as_sum(g, u[e].y)) : u[e];
+                    const double2 kp = AS ? make_double2(as_sum(g, k1[e].x), as_sum(g, k1[e].y)) : k1[e];
+                    const double sk = a.abstol + sqrt(up.x * up.x + up.y * up.y) * a.reltol;
+                    const double ux = up.x / sk, uy = up.y / sk, fx = kp.x / sk, fy = kp.y / sk;
+                    if (!(AS && g.split_helper)) {
+                        acc2[0] += ux * ux + uy * uy;
+                        acc2[1] += fx * fx + fy * fy;
+                    }
                 }
             }
             if (RS && g.sm_pf) fence_async_proxy();  // scratch stores above -> bulk-copy reads below
@@ -1247,9 +1276,12 @@ struct Kern {
                 apply(a, g, V1, yb1, ell, vstat, row_of, tmp, k2);
 #pragma unroll
                 for (int e = 0; e < E; e++) {
-                    const double sk = a.abstol + sqrt(u[e].x * u[e].x + u[e].y * u[e].y) * a.reltol;
-                    const double fx = (k2[e].x - k1[e].x) / sk, fy = (k2[e].y - k1[e].y) / sk;
-                    acc1[0] += fx * fx + fy * fy;
+                    const double2 up = AS ? make_double2(as_sum(g, u[e].x), as_sum(g, u[e].y)) : u[e];
+                    const double dx = k2[e].x - k1[e].x, dy = k2[e].y - k1[e].y;
+                    const double2 dp = AS ? make_double2(as_sum(g, dx), as_sum(g, dy)) : make_double2(dx, dy);
+                    const double sk = a.abstol + sqrt(up.x * up.x + up.y * up.y) * a.reltol;
+                    const double fx = dp.x / sk, fy = dp.y / sk;
+                    if (!(AS && g.split_helper)) acc1[0] += fx * fx + fy * fy;
                 }
             }
             team_sum<1>(acc1, g.sm_red, a.team_warps, g.warp_in_team, g.lane, g.bar_id);
@@ -1518,10 +1550,25 @@ struct Kern {
                         double m2[E], ys[E], hx[E], dn[E], yr[E];
 #pragma unroll
                         for (int e = 0; e < E; e++) { ex[e] = fma(BT7, k7[e].x, ex[e]); ey[e] = fma(BT7, k7[e].y, ey[e]); }
+                        // additively split rows: error estimate and scale of the PHYSICAL entry (owner + helper part);
+                        // the helper part itself counts nothing
+                        double2 uc[E], tc[E];
 #pragma unroll
                         for (int e = 0; e < E; e++) {
-                            const double au = fma(u[e].x, u[e].x, u[e].y * u[e].y);
-                            const double an = fma(tmp[e].x, tmp[e].x, tmp[e].y * tmp[e].y);
+                            uc[e] = u[e];
+                            tc[e] = tmp[e];
+                            if (AS) {
+                                uc[e] = make_double2(as_sum(g, u[e].x), as_sum(g, u[e].y));
+                                tc[e] = make_double2(as_sum(g, tmp[e].x), as_sum(g, tmp[e].y));
+                                const double sx = as_sum(g, ex[e]), sy = as_sum(g, ey[e]);   // (every lane shuffles)
+                                ex[e] = g.split_helper ? 0.0 : sx;
+                                ey[e] = g.split_helper ? 0.0 : sy;
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const double au = fma(uc[e].x, uc[e].x, uc[e].y * uc[e].y);
+                            const double an = fma(tc[e].x, tc[e].x, tc[e].y * tc[e].y);
                             // max of non-negative doubles through their bit patterns (entries below 1e-140 count as that)
                             const long long bu = __double_as_longlong(au), bn = __double_as_longlong(an);
                             const long long bm = bu > bn ? bu : bn;
@@ -1562,7 +1609,7 @@ struct Kern {
                                 save_points_lean(a, g, tout, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok,
                                                  u, k1, k7, tmp);
                             else
-                                save_points(a, tout, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok, u, k1,
+                                save_points(a, g, tout, ts, nsave, nsave_hi, t, dt, CTL_LD(C_TNEW), col0, row_of, row_ok, u, k1,
                                             k2, k3, k4, k5, k6, k7, tmp);
                         }
                     }
@@ -1601,7 +1648,7 @@ struct Kern {
                                 save_points_lean(a, g, tout, ts, nsave, nsave_hi, t, dt, tnew,
                                                  g.warp_in_team * g.cpb + g.colofs, row_of, row_ok, u, k1, k7, tmp);
                             else
-                                save_points(a, tout, ts, nsave, nsave_hi, t, dt, tnew,
+                                save_points(a, g, tout, ts, nsave, nsave_hi, t, dt, tnew,
                                             (RS ? 0 : g.warp_in_team) * g.cpb + g.colofs,
                                             row_of, row_ok, u, k1, k2, k3, k4, k5, k6, k7, tmp);
                         }
@@ -1638,8 +1685,8 @@ struct Kern {
             // zero-length span: only the start saves
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
                 const int col0 = b * g.cpb + g.colofs;
-                initial_state(a, tin, col0, row_of, row_ok, u);
-                for (int ks = 0; ks < nsave; ks++) write_out(a, tout, ks, col0, row_of, row_ok, u);
+                initial_state(a, g, tin, col0, row_of, row_ok, u);
+                for (int ks = 0; ks < nsave; ks++) write_out(a, g, tout, ks, col0, row_of, row_ok, u);
             }
         }
         // unreached save points of a failed trajectory: NaN
@@ -1648,7 +1695,7 @@ struct Kern {
 #pragma unroll
             for (int e = 0; e < E; e++) tmp[e] = make_double2(qnan, qnan);
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps)
-                for (int ks = nsave; ks < a.n_ts; ks++) write_out(a, tout, ks, b * g.cpb + g.colofs, row_of, row_ok, tmp);
+                for (int ks = nsave; ks < a.n_ts; ks++) write_out(a, g, tout, ks, b * g.cpb + g.colofs, row_of, row_ok, tmp);
         }
         st.t_final = t;
         if (g.team_thread == 0 && a.stats) a.stats[tout] = st;
@@ -1825,7 +1872,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
                 ell[i][j] = (ell[i][j] + ((8u * a.nvp) << 16)) | 0x80000000u;
         }
         // tiered: stage buffer and row table are indexed by the virtual row, initial state and results by the state row
-        if (K::TR) row_of[i] = row_ok[i] ? __ldg(a.row_perm + row_of[i]) : 0;
+        if (K::TR || K::AS) row_of[i] = row_ok[i] ? __ldg(a.row_perm + row_of[i]) : 0;
     }
     double2 *sc_base = nullptr;
     if (a.streamed)

@@ -98,5 +98,6 @@ struct qsim_problem {
     std::mutex dev_mutex;
     // tiered form of each generator (qsim_api.cu, build_tiered): built on first use, under plan_mutex
     std::shared_ptr<struct TieredForm> tiered[2];
+    std::shared_ptr<struct AddSplitForm> addsplit[2];   // additively split rows (build_addsplit)
     std::mutex plan_mutex;
 };

@@ -368,11 +368,12 @@ def test_repeated_runs_are_bitwise_identical():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("env,tag", [("QSIM_NO_LEAN", "tsit5_r1c3_nnz5_t128_vm2"), ("QSIM_TIERED", "lean_tiered_r3c1"),
-                                     ("QSIM_SPLIT", "lean_split_r1c3_nnz3")])
+                                     ("QSIM_SPLIT", "lean_split_r1c3_nnz3"), ("QSIM_ADDSPLIT", "lean_addsplit_r1c3_nnz3")])
 def test_cfg2_kernel_variants(monkeypatch, env, tag):
     """The default cfg2 kernel is the lean row-per-lane one (168 registers, 12 warps per SM).  The 255-register
-    kernel (QSIM_NO_LEAN=1) and the two opt-in mappings -- three rows of one column per lane sorted into tiers
-    (QSIM_TIERED=1), split rows with helper lanes (QSIM_SPLIT=1) -- take the same step sequence and agree with it to
+    kernel (QSIM_NO_LEAN=1) and the three opt-in mappings -- three rows of one column per lane sorted into tiers
+    (QSIM_TIERED=1), split rows with helper lanes (QSIM_SPLIT=1), additively split rows (QSIM_ADDSPLIT=1: the long row's
+    state carried as two parts that add up to the physical entry) -- take the same step sequence and agree with it to
     rounding and with the oracle to 1e-8, including dense-output points inside steps (parked stage vectors)."""
     from qsim_b200 import workloads as W
     from qsim_b200._ffi import Problem
