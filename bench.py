@@ -21,9 +21,9 @@ roofline: FP64 pipe.  achieved = executed algorithmic flop of the sparse generat
 cpu_baseline / --impl reference: the C oracle in reference-faithful mode on the host cores (threads over the
          sweep, the analogue of Threads.@threads) -- a C restatement of the reference algorithm, not Julia.
 
-configs block (cfg3, cfg4, cfg5 of BASELINE.json): each config's whole sweep, strong-sharded block-cyclically over
-the N ranks (rank r integrates points r, r + N, ...), ONE call through the host-buffer API per rank with page-locked
-buffers.  e2e = points / wall time of that call (max over ranks), value = points / device time of its kernels
+configs block (cfg3, cfg4, cfg5 of BASELINE.json): each config's whole sweep, strong-sharded over the N ranks (the
+sweep points dealt round-robin after a fixed pseudo-random permutation, so every shard samples the whole grid), ONE
+call through the host-buffer API per rank with page-locked buffers.  e2e = points / wall time of that call (max over ranks), value = points / device time of its kernels
 (qsim_last_kernel_ms, max over ranks); roofline as above; max_rel_err = elementwise error against the oracle on two
 points over a short span (identical step counts required); cpu = oracle on a stated, time-truncated sample.
 cfg3 and cfg5 deliver, of each saved result, the block of the computational (qubit) subspace (qsim_solve_selected: 8 x 8
@@ -219,6 +219,11 @@ def run_extra_config(name, ctx, world, rank, dev, dist, peak_tflops, deadline, r
               if name in ("cfg3", "cfg5") else None)
     per_rank = n_total // world
     info = prob.plan_info(which)
+    # the ranks' shards: sweep points dealt round-robin after a fixed pseudo-random permutation of the sweep order, so
+    # that every shard samples the whole grid (dealing the grid order itself gives rank r the same two values of the
+    # fastest grid axis, and step counts depend on them: 5 % imbalance on cfg5 at 8 ranks)
+    order = np.random.default_rng(20260101).permutation(n_total) if world > 1 else np.arange(n_total)
+    shard = params_all[order[rank::world]]
 
     def barrier():
         if world > 1:
@@ -231,6 +236,12 @@ def run_extra_config(name, ctx, world, rank, dev, dist, peak_tflops, deadline, r
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
+    def reduce_min(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t[0])
+
     def reduce_sum(x):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
@@ -239,7 +250,7 @@ def run_extra_config(name, ctx, world, rank, dev, dist, peak_tflops, deadline, r
 
     # warm-up + probe: two points per SM over the full span (builds the device tables, measures the rate)
     n_probe = min(per_rank, 2 * ctx.info()["sm_count"])
-    probe = np.ascontiguousarray(params_all[rank::world][:n_probe])
+    probe = np.ascontiguousarray(shard[:n_probe])
     t0 = time.perf_counter()
     prob.solve(which, ts, params=probe, ctx=ctx, select=select)
     probe_s = reduce_max(time.perf_counter() - t0)
@@ -251,7 +262,7 @@ def run_extra_config(name, ctx, world, rank, dev, dist, peak_tflops, deadline, r
     while n_run > n_probe and probe_s * n_run / n_probe * 0.9 > budget:
         n_run //= 2
         full = False
-    params = np.ascontiguousarray(params_all[rank::world][:n_run])
+    params = np.ascontiguousarray(shard[:n_run])
     n_state = len(select) if select is not None else int(np.prod(prob.state_shape(which)))
     pin_out = PinnedArray((n_run, len(ts), n_state), np.complex128)
     pin_par = PinnedArray(params.shape, np.float64)
@@ -262,7 +273,7 @@ def run_extra_config(name, ctx, world, rank, dev, dist, peak_tflops, deadline, r
     wall = time.perf_counter() - t0
     kernel_ms = ctx.last_kernel_ms()
     barrier()
-    wall_max, kernel_ms_max = reduce_max(wall), reduce_max(kernel_ms)
+    wall_max, kernel_ms_max, kernel_ms_min = reduce_max(wall), reduce_max(kernel_ms), reduce_min(kernel_ms)
     ok = bool(np.all(st["retcode"] == 0))
     attempts = reduce_sum(float(st["n_accept"].sum() + st["n_reject"].sum()))
     n_done = int(reduce_sum(float(n_run)))
@@ -280,13 +291,15 @@ def run_extra_config(name, ctx, world, rank, dev, dist, peak_tflops, deadline, r
         return None
     res = {
         "workload": spec["label"], "kernel": prob.kernel_name(which), "points": n_done, "points_in_config": n_total,
-        "full_config": bool(full and n_done == n_total), "sharding": f"block-cyclic over {world} rank(s), no collective",
+        "full_config": bool(full and n_done == n_total),
+        "sharding": f"round-robin over {world} rank(s) after a fixed permutation of the sweep order, no collective",
         "value": n_done / (kernel_ms_max * 1e-3), "e2e": n_done / wall_max, "unit": "propagators/s",
-        "kernel_s": kernel_ms_max * 1e-3, "call_s": wall_max, "all_succeeded": all_ok,
+        "kernel_s": kernel_ms_max * 1e-3, "kernel_s_fastest_rank": kernel_ms_min * 1e-3, "call_s": wall_max, "all_succeeded": all_ok,
         "attempted_steps": int(attempts), "steps_per_point": attempts / max(n_done, 1),
         "h2d_bytes": int(params.nbytes + ts.nbytes) * world, "d2h_bytes": int(n_done * len(ts) * n_state * 16 + n_done * 32),
-        "roofline": {"bound": "fp64", "achieved": flops / (kernel_ms_max * 1e-3) / 1e12, "peak": peak_tflops,
-                     "unit": "TFLOP/s", "frac": flops / (kernel_ms_max * 1e-3) / 1e12 / peak_tflops,
+        # (achieved: per GPU -- the ranks' flop summed, over the slowest rank's kernel time, divided by the ranks)
+        "roofline": {"bound": "fp64", "achieved": flops / (kernel_ms_max * 1e-3) / 1e12 / world, "peak": peak_tflops,
+                     "unit": "TFLOP/s", "frac": flops / (kernel_ms_max * 1e-3) / 1e12 / world / peak_tflops,
                      "flops_per_rhs": prob.flops_per_rhs(which), "generator_nnz": info["nnz"],
                      "scratch_stream_gbs": (info["scratch_bytes_per_team"] * attempts / max(kernel_ms_max * 1e-3, 1e-9) / 1e9
                                             if info["streamed"] else 0.0)},
@@ -489,7 +502,11 @@ def main():
     # ---- single-process fan-out over all N devices (qsim_solve_multi), rank 0 only ----
     fanout = None
     if world > 1 and not (SMALL or POINTS):
+        # rank 0 drives all devices from one process; the other ranks must leave their GPUs and host cores alone
+        # meanwhile: they wait in a gloo (socket) barrier, not in an NCCL one (a spinning kernel on every GPU) nor in
+        # a busy-waiting synchronize
         barrier()
+        idle = dist.new_group(backend="gloo")
         if rank == 0:
             try:
                 v, secs, first = run_fanout(world, n_ts, d, cqs, ts)
@@ -498,6 +515,7 @@ def main():
                                   "pageable caller buffers (pipelined device-to-host copies), N x 4096 cfg2 points"}
             except Exception as e:
                 fanout = {"error": f"{type(e).__name__}: {e}"}
+        dist.barrier(group=idle)
         barrier()
 
     if rank == 0:
