@@ -797,7 +797,9 @@ struct Kern {
     };
     // `hook` runs between the issue of a row's operand loads and their first use: independent work placed
     // there (the next stage's partial combination) executes under the shared-memory latency.
-    template <typename Hook = NoHook>
+    // CHN: off-diagonal entries whose operands are requested together (0: the kernel's default -- QSIM_CH, or 2 in the
+    // lean kernels, whose early stages, with few live vectors, ask for 4)
+    template <int CHN = 0, typename Hook = NoHook>
     static __device__ __forceinline__ void apply(const LaunchArgs &a, const Geo &g, uint32_t Vs, uint32_t yb,
                                                  const uint32_t (&ell)[RPL][NZ], const double (&vstat)[NVS],
                                                  const int (&row_of)[RPL], const Vec &yreg, Vec &k, Hook hook = Hook()) {
@@ -930,7 +932,16 @@ struct Kern {
 #ifndef QSIM_CH
 #define QSIM_CH 4
 #endif
-                constexpr int CH = LEAN ? 2 : QSIM_CH;
+#ifndef QSIM_LEAN_CH_EARLY   // lean kernels, stages 2-4 (few live vectors): entries requested together
+#define QSIM_LEAN_CH_EARLY 2     /* (4 measured slower on cfg2: 571 ms against 555 ms) */
+#endif
+#ifndef QSIM_LEAN_CH         // lean kernels, stages 6-7
+#define QSIM_LEAN_CH 2
+#endif
+#ifndef QSIM_LEAN_CH_MID     // lean kernels, stage 5
+#define QSIM_LEAN_CH_MID 2
+#endif
+                constexpr int CH = CHN > 0 ? CHN : (LEAN ? QSIM_LEAN_CH : QSIM_CH);
 #pragma unroll
                 for (int j0 = 1; j0 < MAXNNZ; j0 += CH) {
                     double2 vv[CH], yy[CH][CPL];
@@ -1392,7 +1403,7 @@ struct Kern {
                             tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                         }
                         put_stage(a, g, tmp, yb0, my_off, row_ok);
-                        apply(a, g, V0, yb0, ell, vstat, row_of, tmp, k2, [&] {
+                        apply<QSIM_LEAN_CH_EARLY>(a, g, V0, yb0, ell, vstat, row_of, tmp, k2, [&] {
 #pragma unroll
                             for (int e = 0; e < E; e++) part[e] = make_double2(A31 * k1[e].x, A31 * k1[e].y);
                         });
@@ -1403,7 +1414,7 @@ struct Kern {
                             tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                         }
                         put_stage(a, g, tmp, yb1, my_off, row_ok);
-                        apply(a, g, V1, yb1, ell, vstat, row_of, tmp, k3, [&] {
+                        apply<QSIM_LEAN_CH_EARLY>(a, g, V1, yb1, ell, vstat, row_of, tmp, k3, [&] {
 #pragma unroll
                             for (int e = 0; e < E; e++)
                                 part[e] = make_double2(fma(A42, k2[e].x, A41 * k1[e].x), fma(A42, k2[e].y, A41 * k1[e].y));
@@ -1415,7 +1426,7 @@ struct Kern {
                             tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                         }
                         put_stage(a, g, tmp, yb0, my_off, row_ok);
-                        apply(a, g, V2, yb0, ell, vstat, row_of, tmp, k4, [&] {
+                        apply<QSIM_LEAN_CH_EARLY>(a, g, V2, yb0, ell, vstat, row_of, tmp, k4, [&] {
 #pragma unroll
                             for (int e = 0; e < E; e++)
                                 part[e] = make_double2(fma(A53, k3[e].x, fma(A52, k2[e].x, A51 * k1[e].x)),
@@ -1428,7 +1439,7 @@ struct Kern {
                             tmp[e] = make_double2(u[e].x + dt * ax, u[e].y + dt * ay);
                         }
                         put_stage(a, g, tmp, yb1, my_off, row_ok);
-                        apply(a, g, V3, yb1, ell, vstat, row_of, tmp, k5, [&] {
+                        apply<QSIM_LEAN_CH_MID>(a, g, V3, yb1, ell, vstat, row_of, tmp, k5, [&] {
 #pragma unroll
                             for (int e = 0; e < E; e++)
                                 part[e] = make_double2(
