@@ -1014,7 +1014,8 @@ static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int bloc
     const KernelVariant *(*lists[])(int *) = {variants_r1c1_t128, variants_r1c3_t128, variants_r1c3_t256,
                                               variants_r1c4_t256, variants_r2c1_t128,
                                               variants_r2c2_t256, variants_r3c1_t128, variants_r3c1_t256,
-                                              variants_rowsplit, variants_colperlane, variants_blocked, variants_lean};
+                                              variants_rowsplit, variants_colperlane, variants_blocked, variants_lean,
+                                              variants_lean_t256};
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
         int cnt = 0;
@@ -1368,8 +1369,11 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
                 const uint32_t sl = g.ell[(size_t)j * n + r] >> 16;
                 if (sl != 0xFFFFu && (int)sl < g.n_dyn_slots) static_off = false;
             }
-        // (with four entries per lane the extra value registers would spill: stay in mode 1)
+        // (with four entries per lane the extra value registers spill in the 255-register kernels: mode 1 there; the
+        // lean kernels of resident teams have room for them.  QSIM_LEAN_VM1=1: development A/B switch)
+        const bool lean_ok = !pl.streamed && !split && !std::getenv("QSIM_NO_LEAN");
         if (static_off && rpl * cpl <= 3 && find_variant(rpl, cpl, eff_nnz, pl.block, 2, 0)) vm = 2;
+        else if (static_off && lean_ok && !std::getenv("QSIM_LEAN_VM1") && find_variant(rpl, cpl, eff_nnz, pl.block, 2, 0, 1)) vm = 2;
     }
     if (vm == 0) {
         const bool mixed = generator_is_mixed(g, pl.slot_imag);

@@ -13,10 +13,6 @@ const KernelVariant *variants_lean(int *count) {
          occupancy_solver<1, 3, 9, 288, 1, 1, false, true>, 1},
         {1, 3, 9, 288, 1, 2, 0, "tsit5_lean_r1c3_nnz9_t288_vm2", launch_solver<1, 3, 9, 288, 1, 2, false, true>,
          occupancy_solver<1, 3, 9, 288, 1, 2, false, true>, 1},
-        // multi-warp resident teams, one per SM (no occupancy to gain: the shorter live ranges remove the spills of the
-        // 255-register kernel): 25..32-level propagators (cfg3: 946 -> 934 ms for 1184 x 50 ns)
-        {1, 4, 9, 256, 1, 1, 0, "tsit5_lean_r1c4_nnz9_t256_vm1", launch_solver<1, 4, 9, 256, 1, 1, false, true>,
-         occupancy_solver<1, 4, 9, 256, 1, 1, false, true>, 1},
         // additively split rows (value mode 7): the 2-transmon gates as 10 table rows of 1 + 2 entries on 30 lanes
         {1, 3, 3, 128, 3, 7, 0, "tsit5_lean_addsplit_r1c3_nnz3_t128_vm7", launch_solver<1, 3, 3, 128, 3, 7, false, true>,
          occupancy_solver<1, 3, 3, 128, 3, 7, false, true>, 1},

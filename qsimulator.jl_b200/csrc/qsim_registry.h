@@ -27,6 +27,7 @@ QSIM_DECLARE(variants_rowsplit)
 QSIM_DECLARE(variants_colperlane)
 QSIM_DECLARE(variants_blocked)
 QSIM_DECLARE(variants_lean)
+QSIM_DECLARE(variants_lean_t256)
 
 #define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \
     {                                                                                                     \
