@@ -6,7 +6,8 @@ namespace qsim {
 
 struct KernelVariant {
     int rpl, cpl, maxnnz, maxt, minb, vm, rs;  // vm: value mode (0 complex, 1 imaginary, 2 imaginary + static off-diagonals,
-                                               // 3 blocked, 4 mixed real/imaginary entries)
+                                               // 3 blocked, 4 mixed real/imaginary entries; opt-in experiments: 5 tiered
+                                               // rows (maxnnz packs the tier capacities), 6 split rows, 7 additively split rows)
     const char *name;
     launch_fn launch;
     cudaError_t (*occupancy)(int block, size_t smem, int *ctas_per_sm);
@@ -16,7 +17,8 @@ struct KernelVariant {
 // defined one per translation unit (qsim_inst_*.cu) so the variants compile in parallel
 #define QSIM_DECLARE(FN) const KernelVariant *FN(int *count);
 // t128: four one-warp teams per CTA, two CTAs per SM.  t256: teams of 2-8 warps, one CTA per SM.  Both leave
-// 255 registers per thread (two warps per scheduler); nine warps would be held to 168 and spill.
+// 255 registers per thread (two warps per scheduler).  The lean kernels (variants_lean*, qsim_inst_lean*.cu) fit the
+// one-warp teams into 168 registers: three CTAs, 12 warps per SM.
 QSIM_DECLARE(variants_r1c1_t128)
 QSIM_DECLARE(variants_r1c3_t128) QSIM_DECLARE(variants_r1c3_t256)
 QSIM_DECLARE(variants_r1c4_t256)

@@ -28,6 +28,11 @@
 //     time-dependent value slots are refreshed (QSIM_FLAG_DIRECT_DRIVES: direct evaluation instead).
 //   * step controller: EEst^b1 and qold^b2 from mantissa-interval Taylor tables passed in the
 //     kernel parameters (constant bank); libm only outside the tables' range.
+//   * lean kernels (Kern<..., LEAN>, resident teams): the stage vectors die as early as the tableau allows (five
+//     live vectors in stage 7 instead of ten), which fits the step into 168 registers -- three warps per scheduler,
+//     12 one-warp teams per SM -- and, for the seven-warp teams of 25..32-level propagators, makes room for the
+//     static off-diagonal values next to four entries per lane.  The k's a dense-output point needs are parked in
+//     lane-private shared memory on the steps that contain one.
 //   * work distribution: persistent CTAs, dynamic queue over trajectories (atomic counter).
 // No reductions use atomics, so results are bitwise reproducible and independent of the save grid.
 #pragma once
