@@ -13,6 +13,12 @@ const KernelVariant *variants_lean(int *count) {
          occupancy_solver<1, 3, 9, 288, 1, 1, false, true>, 1},
         {1, 3, 9, 288, 1, 2, 0, "tsit5_lean_r1c3_nnz9_t288_vm2", launch_solver<1, 3, 9, 288, 1, 2, false, true>,
          occupancy_solver<1, 3, 9, 288, 1, 2, false, true>, 1},
+        // state evolution of small systems (unitary_state / me_state, one column): 168 registers without spills
+#define QSIM_LEAN_R1C1(M, I)                                                                                              \
+        {1, 1, M, 128, 3, I, 0, "tsit5_lean_r1c1_nnz" #M "_t128_vm" #I, launch_solver<1, 1, M, 128, 3, I, false, true>,   \
+         occupancy_solver<1, 1, M, 128, 3, I, false, true>, 1},
+        QSIM_LEAN_R1C1(5, 0) QSIM_LEAN_R1C1(5, 1) QSIM_LEAN_R1C1(5, 2)
+        QSIM_LEAN_R1C1(9, 0) QSIM_LEAN_R1C1(9, 1) QSIM_LEAN_R1C1(9, 2) QSIM_LEAN_R1C1(9, 4)
         // additively split rows (value mode 7): the 2-transmon gates as 10 table rows of 1 + 2 entries on 30 lanes
         {1, 3, 3, 128, 3, 7, 0, "tsit5_lean_addsplit_r1c3_nnz3_t128_vm7", launch_solver<1, 3, 3, 128, 3, 7, false, true>,
          occupancy_solver<1, 3, 3, 128, 3, 7, false, true>, 1},
