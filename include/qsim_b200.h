@@ -338,7 +338,9 @@ int qsim_last_kernel_ms(qsim_ctx *ctx, double *ms);
  * [3] longest row, [4] value slots, [5] time-dependent value slots, [6] channels, [7] warps per trajectory,
  * [8] trajectories (teams) per CTA, [9] threads per CTA, [10] dynamic shared memory per CTA in bytes,
  * [11] 1 when the columns stream through scratch memory, [12] scratch bytes per trajectory in flight,
- * [13] value mode of the kernel, [14] 1 for the row-split kernels, [15] reserved (0).                   */
+ * [13] value mode of the kernel, [14] 1 for the row-split kernels, [15] connected components of the generator's
+ * graph when the propagator is integrated block by block (component pruning: entries that couple different
+ * components are exactly zero in the reference too and are written as zeros), 0 when the whole state is integrated. */
 int qsim_problem_plan_info(qsim_problem *prob, int which, int64_t info[16]);
 
 /* FP64 FMA micro-benchmark: sustained DFMA TFLOP/s of the ctx's device,

@@ -114,6 +114,8 @@ struct qsim_problem::DeviceCopy {
     uint32_t *as_ell = nullptr;      // additively split rows: row table over the table rows, table row -> state row, lane info
     int *as_phys = nullptr;
     uint8_t *as_info = nullptr;
+    uint32_t *cf_ell = nullptr;      // component form: per-warp row table, local row -> state row, (batch, local row, c) -> state
+    int *cf_vrow = nullptr, *cf_vcol = nullptr, *cf_zeros = nullptr;   // column, structurally zero entries
     ~DeviceCopy() { free_all(); }  // the owning device must be current
     void free_all() {
         for (auto &pk : packed) {
@@ -145,6 +147,12 @@ struct qsim_problem::DeviceCopy {
         as_ell = nullptr;
         as_phys = nullptr;
         as_info = nullptr;
+        cudaFree(cf_ell);
+        cudaFree(cf_vrow);
+        cudaFree(cf_vcol);
+        cudaFree(cf_zeros);
+        cf_ell = nullptr;
+        cf_vrow = cf_vcol = cf_zeros = nullptr;
         cudaFree(dyn_rec);
         dyn_rec = nullptr;
         cudaFree(tables);
@@ -552,6 +560,7 @@ struct Plan {
     int tiered = 0;                    // tiered variant (value mode 5): blk_rows / blk_nnz hold its geometry
     const struct TieredForm *tf = nullptr;   // its table, row permutation and stage layout (cached in the problem)
     const struct AddSplitForm *af = nullptr; // additively split rows (value mode 7): table-row generator, maps (cached in the problem)
+    const ComponentForm *cf = nullptr;       // component pruning of a propagator (qsim_components.cpp; cached in the problem)
     std::vector<uint8_t> slot_imag;    // value mode 4: per slot, 1 = purely imaginary, 0 = purely real
     // blocked variant (value mode 3): block rows, row table [1 + max blocks][n] and value slot ids
     int blk_rows = 0, blk_nnz = 0;
@@ -1015,16 +1024,18 @@ static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int bloc
                                               variants_r1c4_t256, variants_r2c1_t128,
                                               variants_r2c2_t256, variants_r3c1_t128, variants_r3c1_t256,
                                               variants_rowsplit, variants_colperlane, variants_blocked, variants_lean,
-                                              variants_lean_t256};
+                                              variants_lean_t256, variants_r1c2_t128, variants_lean_c2};
+    // (development: QSIM_MAX_MINB caps the occupancy target of the chosen variant, e.g. 3 keeps the 168-register lean kernels)
+    const int max_minb = std::getenv("QSIM_MAX_MINB") ? std::atoi(std::getenv("QSIM_MAX_MINB")) : 99;
     const KernelVariant *best = nullptr;
     for (auto fn : lists) {
         int cnt = 0;
         const KernelVariant *v = fn(&cnt);
         for (int i = 0; i < cnt; i++)
             if (v[i].rpl == rpl && v[i].cpl == cpl && (rs || v[i].maxnnz >= max_nnz) && v[i].maxt >= block &&
-                v[i].vm == vm && v[i].rs == rs && v[i].lean == lean) {
-                // smallest row capacity, then smallest block bound, then the preferred occupancy target
-                auto key = [&](const KernelVariant &k) { return std::make_tuple(k.maxnnz, k.maxt); };
+                v[i].vm == vm && v[i].rs == rs && v[i].lean == lean && v[i].minb <= max_minb) {
+                // smallest row capacity, then smallest block bound, then the highest occupancy target
+                auto key = [&](const KernelVariant &k) { return std::make_tuple(k.maxnnz, k.maxt, -k.minb); };
                 if (!best || key(v[i]) < key(*best)) best = &v[i];
             }
     }
@@ -1158,6 +1169,61 @@ static void build_rowsplit_table(const Generator &g, Plan &pl, bool full) {
 }
 
 // which: 0 unitary_propagator, 1 unitary_state, 2 me_propagator, 3 me_state
+// every off-diagonal entry of the generator is a per-trajectory constant (only diagonal slots depend on time)
+static bool offdiag_static(const Generator &g) {
+    for (int j = 1; j < g.max_nnz; j++)
+        for (int r = 0; r < g.n; r++) {
+            const uint32_t sl = g.ell[(size_t)j * g.n + r] >> 16;
+            if (sl != 0xFFFFu && (int)sl < g.n_dyn_slots) return false;
+        }
+    return true;
+}
+
+// Component pruning of a propagator problem: the kernel shape (rows x columns per lane), the packing and the kernel
+// variant with the best estimated throughput, or nothing when the generator is connected.  The estimate: a Tsit5 step
+// of a warp costs about 2200 + 650 E cycles (E = entries per lane; measured on cfg2); one-warp
+// teams run 12 per SM in the lean kernels (E <= 3) and 8 otherwise, multi-warp resident teams floor(8 / warps) per
+// SM, streamed teams one per SM with their batches in sequence.
+static void choose_component_form(const Generator &gp, std::shared_ptr<ComponentForm> &out) {
+    const bool no_lean = std::getenv("QSIM_NO_LEAN") != nullptr;
+    const bool stat = gp.imag_only && offdiag_static(gp);
+    std::vector<uint8_t> slot_imag;
+    const bool mixed = !gp.imag_only && generator_is_mixed(gp, slot_imag);
+    double best = 0.0;
+    for (int rpl = 1; rpl <= 3; rpl++)
+        for (int cpl = 1; cpl <= (rpl == 1 ? 4 : rpl == 2 ? 2 : 1); cpl++) {
+            auto cf = std::make_shared<ComponentForm>();
+            if (!build_component_form(gp, rpl, cpl, 8, *cf)) continue;
+            const int W = cf->team_warps, E = rpl * cpl;
+            const int tpc = cf->streamed ? 1 : (W == 1 ? 4 : 8 / W);
+            const int block = W * 32 * tpc;
+            // the variant make_plan will pick for this shape
+            int vm = gp.imag_only ? 1 : 0;
+            const bool lean_ok = !cf->streamed && !no_lean;
+            if (vm == 1 && stat && ((E <= 3 && find_variant(rpl, cpl, gp.max_nnz, block, 2, 0, 0)) ||
+                                    (lean_ok && find_variant(rpl, cpl, gp.max_nnz, block, 2, 0, 1))))
+                vm = 2;
+            if (vm == 0 && mixed && find_variant(rpl, cpl, gp.max_nnz, block, 4, 0, 0)) vm = 4;
+            const KernelVariant *lv = lean_ok ? find_variant(rpl, cpl, gp.max_nnz, block, vm, 0, 1) : nullptr;
+            const KernelVariant *kv = lv ? lv : find_variant(rpl, cpl, gp.max_nnz, block, vm, 0, 0);
+            if (!kv) continue;
+            double score;
+            if (cf->streamed)
+                score = 1.0 / (2200.0 + (double)(cf->n_batches / W) * (650.0 * E + 400.0));
+            else {
+                const int warps_per_sm = (W == 1 && lv && E <= 3) ? 12 : 8;
+                score = (double)(warps_per_sm / W) / (2200.0 + 650.0 * E);
+            }
+            if (std::getenv("QSIM_DEBUG"))
+                std::fprintf(stderr, "[qsim] component form r%dc%d: %d components, %d warps%s, %d batches, %d local rows, %s: score %.3g\n",
+                             rpl, cpl, cf->n_comp, W, cf->streamed ? " (streamed)" : "", cf->n_batches, cf->n_loc, kv->name, score * 1e3);
+            if (score > best) {
+                best = score;
+                out = cf;
+            }
+        }
+}
+
 static int make_plan(qsim_problem *p, int which, Plan &pl) {
     pl.w = which >= 2 ? 1 : 0;
     if (int rc = ensure_generator(p, pl.w)) return rc;
@@ -1180,10 +1246,28 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         const AddSplitForm *af = p->addsplit[pl.w].get();
         if (af->ok && find_variant(1, 3, af->nnz, 128, 7, 0, 1)) pl.af = af;
     }
-    const Generator &g = pl.af ? pl.af->gv : gp;
+    // Component pruning (propagators): integrate only the blocks of the connected components of the generator's graph
+    // (qsim_components.cpp).  QSIM_NO_PRUNE=1 keeps the full state (development A/B switch); the opt-in experiments
+    // above and below run on the full state.
+    if (pl.identity && !pl.af && !std::getenv("QSIM_NO_PRUNE") && !std::getenv("QSIM_BLOCKED") && !std::getenv("QSIM_TIERED") &&
+        !std::getenv("QSIM_SPLIT") && !std::getenv("QSIM_SPLIT_ROWS") && !std::getenv("QSIM_COLPERLANE") && !std::getenv("QSIM_LEAN9") &&
+        gp.n <= 96 && gp.max_nnz <= 16) {
+        std::lock_guard<std::mutex> lk(p->plan_mutex);
+        if (!p->cform_tried[pl.w]) {
+            p->cform_tried[pl.w] = true;
+            choose_component_form(gp, p->cform[pl.w]);
+        }
+        if (p->cform[pl.w] && p->cform[pl.w]->ok) pl.cf = p->cform[pl.w].get();
+    }
+    const Generator &g = pl.af ? pl.af->gv : pl.cf ? pl.cf->gv : gp;
+    const Generator &gs = pl.cf ? gp : g;   // the generator whose row table make_plan scans (a component form's table is per warp)
     const int n = g.n;
     int rpl, cpl;
-    if (n <= 16) {
+    if (pl.cf) {
+        rpl = pl.cf->rpl;
+        cpl = pl.cf->cpl;
+        pl.groups = 1;
+    } else if (n <= 16) {
         rpl = 1;
         pl.groups = std::min(32 / n, pl.ncols);
         cpl = (pl.ncols + pl.groups - 1) / pl.groups > 1 ? 3 : 1;
@@ -1230,7 +1314,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.rowsplit = 1;
     }
     int cpb = pl.groups * cpl;
-    pl.n_batches = (pl.ncols + cpb - 1) / cpb;
+    pl.n_batches = pl.cf ? pl.cf->n_batches : (pl.ncols + cpb - 1) / cpb;
     // Blocked variant (value mode 3) for small propagators whose couplings fall into 3 x 3 blocks (Kronecker
     // structure with a 3-level last subsystem: the 2-transmon gates of cfg1/cfg2): every lane owns 3 consecutive
     // rows of one column and each neighbour block is loaded once for its 9 multiply-adds, which cuts the
@@ -1330,7 +1414,10 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     }
     const int eff_nnz = split ? pl.split_nnz : g.max_nnz;
     pl.rpl = rpl;
-    if (pl.cu) {
+    if (pl.cf) {
+        pl.team_warps = pl.cf->team_warps;
+        pl.streamed = pl.cf->streamed;
+    } else if (pl.cu) {
         pl.team_warps = (n + 3) / 4;
         pl.streamed = 0;   // all n <= 32 columns in one batch: the state never leaves registers
     } else if (pl.rowsplit) {
@@ -1347,6 +1434,8 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     // one-warp teams: 4 per CTA (128 threads; 2 CTAs = 8 warps per SM for the 255-register kernels, 3 CTAs = 12 warps
     // for the lean 168-register ones)
     pl.teams_per_cta = pl.team_warps == 1 ? 4 : 1;
+    // (component forms: resident teams of 2-4 warps share the 256-thread CTA of the multi-warp kernels)
+    if (pl.cf && !pl.streamed && pl.team_warps > 1) pl.teams_per_cta = 8 / pl.team_warps;
     if (const char *env = std::getenv("QSIM_TEAMS_PER_CTA")) {  // tuning knob (development)
         const int v = std::atoi(env);
         if (v >= 1 && v <= 15 && v * pl.team_warps * 32 <= 288) pl.teams_per_cta = v;
@@ -1363,12 +1452,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     } else if (pl.af) {
         vm = 7;
     } else if (vm == 1 && !pl.rowsplit) {
-        bool static_off = true;
-        for (int j = 1; j < g.max_nnz && static_off; j++)
-            for (int r = 0; r < n; r++) {
-                const uint32_t sl = g.ell[(size_t)j * n + r] >> 16;
-                if (sl != 0xFFFFu && (int)sl < g.n_dyn_slots) static_off = false;
-            }
+        const bool static_off = offdiag_static(gs);
         // (with four entries per lane the extra value registers spill in the 255-register kernels: mode 1 there; the
         // lean kernels of resident teams have room for them.  QSIM_LEAN_VM1=1: development A/B switch)
         const bool lean_ok = !pl.streamed && !split && !std::getenv("QSIM_NO_LEAN");
@@ -1376,7 +1460,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         else if (static_off && lean_ok && !std::getenv("QSIM_LEAN_VM1") && find_variant(rpl, cpl, eff_nnz, pl.block, 2, 0, 1)) vm = 2;
     }
     if (vm == 0) {
-        const bool mixed = generator_is_mixed(g, pl.slot_imag);
+        const bool mixed = generator_is_mixed(gs, pl.slot_imag);
         if (mixed && find_variant(rpl, cpl, eff_nnz, pl.block, 4, pl.rowsplit)) vm = 4;
     }
     pl.vm = vm;
@@ -1410,6 +1494,14 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     } else if (pl.tiered) {
         pl.y_row_stride = pl.tf->S;     // chosen together with the row positions (build_tiered)
         pl.y_grp_stride = pl.tf->Cg;
+    } else if (pl.cf) {
+        pl.y_row_stride = pl.cf->stride;   // chosen together with the rows' positions (optimize_component_layout)
+        pl.y_grp_stride = cpl;
+        if (16 * n * pl.y_row_stride > 65535) return fail(QSIM_ERR_UNSUPPORTED, "state too large for the packed 16-bit row offsets");
+        if (std::getenv("QSIM_DEBUG"))
+            std::fprintf(stderr, "[qsim] component form: %d components, r%dc%d, %d warps x %d local rows, %d batches%s: stage stride %d, "
+                                 "%ld wavefronts per stage\n", pl.cf->n_comp, rpl, cpl, pl.team_warps, n, pl.n_batches,
+                         pl.streamed ? " (streamed)" : "", pl.y_row_stride, component_layout_cost(*pl.cf, pl.y_row_stride));
     } else {
         long best = -1;
         for (int Cg = cpl; Cg <= cpl + 16; Cg++)
@@ -1508,7 +1600,7 @@ extern "C" int qsim_problem_plan_info(qsim_problem *p, int which, int64_t info[1
     const Generator &g = p->gen[pl.w];
     const int64_t v[16] = {g.n, pl.ncols, g.nnz, g.max_nnz, g.n_slots, g.n_dyn_slots, g.n_chan, pl.team_warps,
                            pl.teams_per_cta, pl.block, (int64_t)pl.smem, pl.streamed, (int64_t)pl.scratch_per_team, pl.vm,
-                           pl.rowsplit, 0};
+                           pl.rowsplit, pl.cf ? pl.cf->n_comp : 0};
     std::memcpy(info, v, sizeof(v));
     return QSIM_OK;
 }
@@ -1522,6 +1614,8 @@ extern "C" int qsim_problem_flops_per_rhs(qsim_problem *p, int which, double *fl
     // a complex multiply-add is 4 DFMA (8 flop); value modes 1-4 (entries purely imaginary, or each purely
     // real or purely imaginary) issue 2 (4 flop)
     *flops = (pl.vm >= 1 ? 4.0 : 8.0) * (double)g.nnz * ncols;
+    // component pruning: only the entries inside the components' blocks are integrated
+    if (pl.cf) *flops = (pl.vm >= 1 ? 4.0 : 8.0) * (double)pl.cf->nnz_cols;
     return QSIM_OK;
 }
 
@@ -1705,6 +1799,12 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
             CU(upload(&dc->as_phys, pl.af->phys));
             CU(upload(&dc->as_info, pl.af->lane_info));
         }
+        if (pl.cf && !dc->cf_ell) {
+            CU(upload(&dc->cf_ell, pl.cf->ell));
+            CU(upload(&dc->cf_vrow, pl.cf->vrow));
+            CU(upload(&dc->cf_vcol, pl.cf->vcol));
+            CU(upload(&dc->cf_zeros, pl.cf->zeros));
+        }
         if (pl.tiered && !dc->tr_ell) {
             CU(upload(&dc->tr_ell, pl.tf->ell));
             CU(upload(&dc->tr_perm, pl.tf->perm));
@@ -1745,10 +1845,20 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
             if (index[(size_t)cc * g.n + r] >= 0) return fail(QSIM_ERR_ARG, "selected entries must be distinct");
             index[(size_t)cc * g.n + r] = i;
         }
-        CU(c->sel.reserve(sizeof(int) * n_state));
-        CU(cudaMemcpyAsync(c->sel.p, index.data(), sizeof(int) * n_state, cudaMemcpyHostToDevice, stream));
+        // component pruning: the selected entries that are structurally zero (positions inside the selection)
+        size_t n_sel_zero = 0;
+        if (pl.cf)
+            for (int i = 0; i < sel->n_sel; i++)
+                if (pl.cf->comp_of[(size_t)sel->rows[i]] != pl.cf->comp_of[(size_t)(sel->cols ? sel->cols[i] : 0)]) {
+                    index.push_back(i);
+                    n_sel_zero++;
+                }
+        CU(c->sel.reserve(sizeof(int) * index.size()));
+        CU(cudaMemcpyAsync(c->sel.p, index.data(), sizeof(int) * index.size(), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));  // `index` is pageable and goes out of scope
         a.sel_index = (const int *)c->sel.p;
+        a.zero_pos = (const int *)c->sel.p + n_state;
+        a.n_zero = (int)n_sel_zero;
         a.n_sel = sel->n_sel;
         a.sel_abs2 = sel->abs2;
         traj_bytes = (sel->abs2 ? sizeof(double) : sizeof(double2)) * (size_t)sel->n_sel * n_ts;
@@ -1859,6 +1969,17 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         a.row_perm = dc->as_phys;
         a.split_info = dc->as_info;
     }
+    if (pl.cf) {   // the kernel runs over each warp's local rows; results, norms and the initial state refer to the state
+        a.g.n = pl.cf->n_loc;
+        a.g.n_vrows = pl.cf->team_warps * pl.cf->n_loc;
+        a.g.ell = dc->cf_ell;
+        a.cf_vrow = dc->cf_vrow;
+        a.cf_vcol = dc->cf_vcol;
+        if (!sel) {
+            a.zero_pos = dc->cf_zeros;
+            a.n_zero = (int)pl.cf->zeros.size();
+        }
+    }
     if (pl.split_nv > 0) {
         a.g.ell = dc->split_ell;
         a.g.max_nnz = pl.split_nnz;
@@ -1878,7 +1999,8 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     a.cu_map = pl.cu;
     a.off_pf = pl.off_pf;
     a.slot_imag = d_slot_imag;
-    a.ncols = pl.ncols;
+    a.ncols = pl.cf ? pl.n_batches * pl.cf->cpl : pl.ncols;   // (component form: virtual columns, batch b holds [b * cpl, b * cpl + cpl))
+    a.out_cols = pl.ncols;
     a.identity_init = pl.identity;
     a.n_params = p->n_params;
     a.n_ts = n_ts;

@@ -1,0 +1,402 @@
+// Component pruning of propagator problems: connected components of the generator's graph and the packing of
+// (component, column group) units into the warps of a team.  Host-side only.
+//
+// U(t) solves dU/dt = A(t) U, U(0) = I.  If the pattern of A (all stored entries, whatever their time dependence)
+// splits the rows into connected components C_1..C_m, then A is block diagonal after a permutation and so is U:
+// U[r, c] = 0 whenever r and c lie in different components.  The reference computes those entries too
+// (time_evolution.jl:31-37 dense H*u, :98-111 dense superoperator), but every term it adds there is 0 * x, so they
+// stay exactly zero, and they enter the error norms (DiffEqBase ODE_DEFAULT_NORM over all n^2 entries) as zeros.
+// The 2- and 3-transmon gates of benchmarks.jl conserve the parity of the total excitation number (two components:
+// half the entries), their rotating-frame exchange form conserves the excitation number itself (the d^2 = 729
+// Lindblad generator of cfg5 has 13 components and 14 % of the propagator's entries are non-zero).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <numeric>
+#include <vector>
+
+#include "qsim_types.h"
+
+namespace qsim {
+
+void generator_components(const Generator &g, std::vector<int> &comp_of, std::vector<std::vector<int>> &comps) {
+    const int n = g.n;
+    std::vector<int> parent((size_t)n);
+    std::iota(parent.begin(), parent.end(), 0);
+    auto find = [&](int x) {
+        while (parent[(size_t)x] != x) x = parent[(size_t)x] = parent[(size_t)parent[(size_t)x]];
+        return x;
+    };
+    for (int j = 0; j < g.max_nnz; j++)
+        for (int r = 0; r < n; r++) {
+            const uint32_t e = g.ell[(size_t)j * n + r];
+            if (e == 0xFFFFFFFFu || (e >> 16) == 0xFFFFu) continue;   // padding / zero entry
+            const int a = find(r), b = find((int)(e & 0xFFFFu));
+            if (a != b) parent[(size_t)std::max(a, b)] = std::min(a, b);
+        }
+    comp_of.assign((size_t)n, -1);
+    comps.clear();
+    for (int r = 0; r < n; r++) {
+        const int root = find(r);
+        if (comp_of[(size_t)root] < 0) {
+            comp_of[(size_t)root] = (int)comps.size();
+            comps.emplace_back();
+        }
+        comp_of[(size_t)r] = comp_of[(size_t)root];
+        comps[(size_t)comp_of[(size_t)r]].push_back(r);
+    }
+}
+
+// Shared-memory wavefronts per stage of a component form's gathers and stores for stage row stride S (16-byte units):
+// a 128-bit shared access is served a quarter warp at a time, and lanes of a quarter that hit the same bank group
+// (unit mod 8) at different addresses serialise.  Padding entries (zero slot) and lanes without a row are free: the
+// tables make them repeat an address their quarter reads anyway (resolve_padding below).
+static long warp_cost(const ComponentForm &cf, const std::vector<uint32_t> &ell, const std::vector<int> &vrow, int w, int S) {
+    const int W = cf.team_warps, nl = cf.n_loc;
+    long cost = 0;
+    for (int i = 0; i < cf.rpl; i++)
+        for (int q = 0; q < 4; q++) {
+            if (8 * q + 32 * i >= nl) {   // lanes past the last local row repeat its addresses: one wavefront per access
+                cost += cf.max_nnz;
+                continue;
+            }
+            for (int j = 1; j <= cf.max_nnz; j++) {   // j == max_nnz: the lanes' own stores
+                int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seen[8][8];
+                for (int l = 8 * q; l < 8 * q + 8; l++) {
+                    const int r = l + 32 * i;
+                    if (r >= nl || vrow[(size_t)w * nl + r] < 0) continue;
+                    int src = r;
+                    if (j < cf.max_nnz) {
+                        const uint32_t e = ell[((size_t)j * W + w) * nl + r];
+                        if ((e >> 16) == 0xFFFFu) continue;
+                        src = (int)(e & 0xFFFFu);
+                    }
+                    const int unit = src * S, b = unit & 7;
+                    bool dup = false;
+                    for (int k = 0; k < cnt[b]; k++) dup = dup || seen[b][k] == unit;
+                    if (!dup) seen[b][cnt[b]++] = unit;
+                }
+                int m = 1;
+                for (int b = 0; b < 8; b++) m = std::max(m, cnt[b]);
+                cost += m;
+            }
+        }
+    return cost * cf.cpl;
+}
+
+long component_layout_cost(const ComponentForm &cf, int S) {
+    long c = 0;
+    for (int w = 0; w < cf.team_warps; w++) c += warp_cost(cf, cf.ell, cf.vrow, w, S);
+    return c;
+}
+
+// Padding entries and rows without a state row read the first address their quarter warp really reads at that entry
+// (a broadcast: no extra wavefront), or their own position when the quarter reads nothing there.
+static void resolve_padding(ComponentForm &cf) {
+    const int W = cf.team_warps, nl = cf.n_loc;
+    for (int w = 0; w < W; w++)
+        for (int j = 1; j < cf.max_nnz; j++)
+            for (int r0 = 0; r0 < nl; r0 += 8) {
+                int real = -1;
+                for (int r = r0; r < std::min(nl, r0 + 8) && real < 0; r++) {
+                    const uint32_t e = cf.ell[((size_t)j * W + w) * nl + r];
+                    if (cf.vrow[(size_t)w * nl + r] >= 0 && (e >> 16) != 0xFFFFu) real = (int)(e & 0xFFFFu);
+                }
+                for (int r = r0; r < std::min(nl, r0 + 8); r++) {
+                    uint32_t &e = cf.ell[((size_t)j * W + w) * nl + r];
+                    if (cf.vrow[(size_t)w * nl + r] < 0 || (e >> 16) == 0xFFFFu) e = (uint32_t)(real >= 0 ? real : r) | (0xFFFFu << 16);
+                }
+            }
+    for (int w = 0; w < W; w++)   // the diagonal entry of a row without a state row: own position, zero slot
+        for (int r = 0; r < nl; r++)
+            if (cf.vrow[(size_t)w * nl + r] < 0) cf.ell[(size_t)w * nl + r] = (uint32_t)r | (0xFFFFu << 16);
+}
+
+// Chooses, per warp, which local row (= lane, = position in the stage buffer) every row of the warp's units takes, by
+// simulated annealing over swaps against warp_cost, and the stage row stride; then resolves the padding entries.
+// The local rows are first extended to a multiple of 8 (whole quarter warps), which gives the search room.
+void optimize_component_layout(ComponentForm &cf) {
+    const int W = cf.team_warps, cap = 32 * cf.rpl, old_nl = cf.n_loc;
+    const int nl = std::min(cap, (old_nl + 7) & ~7);
+    if (nl != old_nl) {
+        std::vector<uint32_t> ell((size_t)cf.max_nnz * W * nl);
+        std::vector<int> vrow((size_t)W * nl, -1), vcol((size_t)cf.n_batches * nl * cf.cpl, -1);
+        for (int w = 0; w < W; w++)
+            for (int r = 0; r < nl; r++)
+                for (int j = 0; j < cf.max_nnz; j++)
+                    ell[((size_t)j * W + w) * nl + r] = r < old_nl ? cf.ell[((size_t)j * W + w) * old_nl + r] : ((uint32_t)r | (0xFFFFu << 16));
+        for (int w = 0; w < W; w++)
+            for (int r = 0; r < old_nl; r++) vrow[(size_t)w * nl + r] = cf.vrow[(size_t)w * old_nl + r];
+        for (int b = 0; b < cf.n_batches; b++)
+            for (int r = 0; r < old_nl; r++)
+                for (int q = 0; q < cf.cpl; q++) vcol[((size_t)b * nl + r) * cf.cpl + q] = cf.vcol[((size_t)b * old_nl + r) * cf.cpl + q];
+        cf.ell.swap(ell);
+        cf.vrow.swap(vrow);
+        cf.vcol.swap(vcol);
+        cf.n_loc = nl;
+    }
+    // stride: odd strides keep the lanes' own stores conflict-free; take the best of a few before the search
+    int S = cf.cpl | 1;
+    {
+        long best = -1;
+        for (int s = cf.cpl; s <= cf.cpl + 8; s++) {
+            if (16 * nl * s > 65535) break;
+            const long c = component_layout_cost(cf, s) * 64 + s;
+            if (s % 2 == 1 && (best < 0 || c < best)) {
+                best = c;
+                S = s;
+            }
+        }
+    }
+    cf.stride = S;
+    const char *env = std::getenv("QSIM_CF_ANNEAL");   // development: search iterations per local row (0: none)
+    const long iters_per_row = env ? std::atol(env) : 400;
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto next = [&]() {
+        rng ^= rng << 13;
+        rng ^= rng >> 7;
+        rng ^= rng << 17;
+        return (uint32_t)(rng >> 32);
+    };
+    const std::vector<uint32_t> nat_ell = cf.ell;   // tables in the packing's natural order
+    const std::vector<int> nat_vrow = cf.vrow, nat_vcol = cf.vcol;
+    std::vector<uint32_t> ell = nat_ell;
+    std::vector<int> vrow = nat_vrow;
+    // perm[t] = local row of natural row t; writes warp w's part of ell / vrow
+    auto apply = [&](int w, const std::vector<int> &pm) {
+        for (int t = 0; t < nl; t++) {
+            vrow[(size_t)w * nl + pm[(size_t)t]] = nat_vrow[(size_t)w * nl + t];
+            for (int j = 0; j < cf.max_nnz; j++) {
+                const uint32_t e = nat_ell[((size_t)j * W + w) * nl + t];
+                ell[((size_t)j * W + w) * nl + pm[(size_t)t]] = (uint32_t)pm[(size_t)(e & 0xFFFFu)] | (e & 0xFFFF0000u);
+            }
+        }
+    };
+    std::vector<std::vector<int>> perms((size_t)W);
+    for (int w = 0; w < W; w++) {
+        std::vector<int> &perm = perms[(size_t)w];
+        // warps with identical tables (the warps of one streamed config) share one search
+        int like = -1;
+        for (int v = 0; v < w && like < 0; v++) {
+            bool same = true;
+            for (int r = 0; r < nl && same; r++) {
+                same = nat_vrow[(size_t)v * nl + r] == nat_vrow[(size_t)w * nl + r];
+                for (int j = 0; j < cf.max_nnz && same; j++)
+                    same = nat_ell[((size_t)j * W + v) * nl + r] == nat_ell[((size_t)j * W + w) * nl + r];
+            }
+            if (same) like = v;
+        }
+        if (like >= 0) {
+            perm = perms[(size_t)like];
+            apply(w, perm);
+            continue;
+        }
+        perm.resize((size_t)nl);
+        std::iota(perm.begin(), perm.end(), 0);
+        apply(w, perm);
+        long cur = warp_cost(cf, ell, vrow, w, S), best = cur;
+        std::vector<int> best_perm = perm;
+        const long iters = iters_per_row * nl;
+        for (long it = 0; it < iters; it++) {
+            const int a = (int)(next() % (uint32_t)nl), b = (int)(next() % (uint32_t)nl);
+            if (a == b) continue;
+            std::swap(perm[(size_t)a], perm[(size_t)b]);
+            apply(w, perm);
+            const long c = warp_cost(cf, ell, vrow, w, S);
+            const double T = 1.5 * (1.0 - (double)it / (double)iters) + 0.05;
+            if (c <= cur || (next() >> 8) * (1.0 / 16777216.0) < std::exp(-(double)(c - cur) / (T * cf.cpl))) {
+                cur = c;
+                if (c < best) {
+                    best = c;
+                    best_perm = perm;
+                }
+            } else
+                std::swap(perm[(size_t)a], perm[(size_t)b]);
+        }
+        perm = best_perm;
+        apply(w, perm);
+    }
+    cf.ell = ell;
+    cf.vrow = vrow;
+    for (int b = 0; b < cf.n_batches; b++) {
+        const std::vector<int> &pm = perms[(size_t)(b % W)];
+        for (int t = 0; t < nl; t++)
+            for (int q = 0; q < cf.cpl; q++) cf.vcol[((size_t)b * nl + pm[(size_t)t]) * cf.cpl + q] = nat_vcol[((size_t)b * nl + t) * cf.cpl + q];
+    }
+    resolve_padding(cf);
+}
+
+// Packs the units of a propagator into warps for a kernel shape of `rpl` rows x `cpl` columns per lane.
+//   resident: every unit gets its own place, at most max_team_warps warps (first-fit, largest components first);
+//   streamed: otherwise.  Components are bin-packed into CONFIGS (sets of components whose rows fit one warp
+//             together); a batch of a config integrates one unit of each of its components; the team's warps
+//             are dealt to the configs in proportion to their batch counts (a warp's rows are fixed for the whole
+//             kernel), warp w runs batches w, w + team_warps, ...
+// Returns false when the generator is connected (nothing to prune) or the form does not fit the shape.
+bool build_component_form(const Generator &g, int rpl, int cpl, int max_team_warps, ComponentForm &cf) {
+    const int n = g.n, cap = 32 * rpl;
+    std::vector<std::vector<int>> comps;
+    generator_components(g, cf.comp_of, comps);
+    cf.ok = false;
+    cf.n_comp = (int)comps.size();
+    if (comps.size() < 2) return false;
+    cf.rpl = rpl;
+    cf.cpl = cpl;
+    cf.max_nnz = g.max_nnz;
+    std::vector<int> order(comps.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return comps[(size_t)a].size() > comps[(size_t)b].size(); });
+    if ((int)comps[(size_t)order[0]].size() > cap) return false;
+    std::vector<int> index_in_comp((size_t)n, 0);
+    cf.nnz_cols = 0;
+    cf.entries = 0;
+    for (const auto &c : comps) {
+        for (size_t i = 0; i < c.size(); i++) index_in_comp[(size_t)c[i]] = (int)i;
+        int64_t nnz = 0;
+        for (int r : c)
+            for (int j = 0; j < g.max_nnz; j++) {
+                const uint32_t e = g.ell[(size_t)j * n + r];
+                if (e != 0xFFFFFFFFu && (e >> 16) != 0xFFFFu) nnz++;
+            }
+        cf.nnz_cols += nnz * (int64_t)c.size();
+        cf.entries += (int64_t)c.size() * (int64_t)c.size();
+    }
+    struct Place { int comp, first_col, base; };   // a unit inside a warp (resident) / a component inside a config (streamed)
+    std::vector<std::vector<Place>> warps;          // per warp: its units / its config's components
+    std::vector<int> used;
+    // ---- resident packing: all units at once ----
+    for (int k : order) {
+        const int nk = (int)comps[(size_t)k].size();
+        for (int c0 = 0; c0 < nk; c0 += cpl) {
+            size_t w = 0;
+            while (w < warps.size() && used[w] + nk > cap) w++;
+            if (w == warps.size()) {
+                warps.emplace_back();
+                used.push_back(0);
+            }
+            warps[w].push_back({k, c0, used[w]});
+            used[w] += nk;
+        }
+    }
+    std::vector<int> batch_warp;    // streamed: config of every warp
+    std::vector<std::vector<Place>> configs;
+    std::vector<int> rounds;
+    if ((int)warps.size() <= max_team_warps) {
+        cf.streamed = 0;
+        cf.team_warps = (int)warps.size();
+        cf.n_batches = cf.team_warps;
+    } else {
+        // ---- streamed packing: components into configs, warps dealt to configs ----
+        std::vector<int> cused;
+        for (int k : order) {
+            const int nk = (int)comps[(size_t)k].size();
+            size_t c = 0;
+            while (c < configs.size() && cused[c] + nk > cap) c++;
+            if (c == configs.size()) {
+                configs.emplace_back();
+                cused.push_back(0);
+            }
+            configs[c].push_back({k, 0, cused[c]});
+            cused[c] += nk;
+        }
+        const int nc = (int)configs.size();
+        if (nc > max_team_warps) return false;
+        rounds.assign((size_t)nc, 0);
+        for (int c = 0; c < nc; c++)
+            for (const auto &pl : configs[(size_t)c])
+                rounds[(size_t)c] = std::max(rounds[(size_t)c], ((int)comps[(size_t)pl.comp].size() + cpl - 1) / cpl);
+        // deal the warps: one each, then always to the config with the most batches per warp
+        std::vector<int> nw((size_t)nc, 1);
+        for (int left = max_team_warps - nc; left > 0; left--) {
+            int best = 0;
+            for (int c = 1; c < nc; c++)
+                if ((rounds[(size_t)c] + nw[(size_t)c] - 1) / nw[(size_t)c] > (rounds[(size_t)best] + nw[(size_t)best] - 1) / nw[(size_t)best]) best = c;
+            nw[(size_t)best]++;
+        }
+        cf.streamed = 1;
+        cf.team_warps = max_team_warps;
+        warps.clear();
+        used.clear();
+        int passes = 0;
+        for (int c = 0; c < nc; c++) {
+            passes = std::max(passes, (rounds[(size_t)c] + nw[(size_t)c] - 1) / nw[(size_t)c]);
+            for (int q = 0; q < nw[(size_t)c]; q++) {
+                warps.push_back(configs[(size_t)c]);
+                used.push_back(cused[(size_t)c]);
+                batch_warp.push_back(c);
+            }
+        }
+        cf.n_batches = passes * cf.team_warps;
+    }
+    const int W = cf.team_warps;
+    cf.n_loc = *std::max_element(used.begin(), used.end());
+    const int nl = cf.n_loc;
+    if (nl > cap) return false;
+    cf.vrow.assign((size_t)W * nl, -1);
+    cf.ell.assign((size_t)g.max_nnz * W * nl, 0);
+    for (int w = 0; w < W; w++) {
+        for (const auto &pl : warps[(size_t)w]) {
+            const auto &c = comps[(size_t)pl.comp];
+            for (size_t i = 0; i < c.size(); i++) {
+                const int lr = pl.base + (int)i, r = c[i];
+                cf.vrow[(size_t)w * nl + lr] = r;
+                for (int j = 0; j < g.max_nnz; j++) {
+                    const uint32_t e = g.ell[(size_t)j * n + r];
+                    uint32_t v;
+                    if (e == 0xFFFFFFFFu || (e >> 16) == 0xFFFFu)
+                        v = (uint32_t)lr | (0xFFFFu << 16);   // padding / zero entry: own row, zero slot
+                    else
+                        v = (uint32_t)(pl.base + index_in_comp[(size_t)(e & 0xFFFFu)]) | (e & 0xFFFF0000u);
+                    cf.ell[(size_t)j * W * nl + (size_t)w * nl + lr] = v;
+                }
+            }
+        }
+        // local rows past the warp's last one: the last row's position, zero slot (their loads coincide with its loads)
+        const int last = std::max(used[(size_t)w] - 1, 0);
+        for (int lr = used[(size_t)w]; lr < nl; lr++)
+            for (int j = 0; j < g.max_nnz; j++) cf.ell[(size_t)j * W * nl + (size_t)w * nl + lr] = (uint32_t)last | (0xFFFFu << 16);
+    }
+    cf.vcol.assign((size_t)cf.n_batches * nl * cpl, -1);
+    if (!cf.streamed) {
+        for (int w = 0; w < W; w++)
+            for (const auto &pl : warps[(size_t)w]) {
+                const auto &c = comps[(size_t)pl.comp];
+                for (size_t i = 0; i < c.size(); i++)
+                    for (int q = 0; q < cpl; q++)
+                        if (pl.first_col + q < (int)c.size())
+                            cf.vcol[((size_t)w * nl + pl.base + i) * cpl + q] = c[(size_t)(pl.first_col + q)];
+            }
+    } else {
+        // config c's warps share its rounds: the j-th warp of the config takes rounds j, j + nw, ... in its passes
+        std::vector<int> seen((size_t)configs.size(), 0), nwc((size_t)configs.size(), 0);
+        for (int w = 0; w < W; w++) nwc[(size_t)batch_warp[(size_t)w]]++;
+        for (int w = 0; w < W; w++) {
+            const int c = batch_warp[(size_t)w], j = seen[(size_t)c]++;
+            for (int pass = 0; pass * W + w < cf.n_batches; pass++) {
+                const int b = pass * W + w, round = pass * nwc[(size_t)c] + j;
+                for (const auto &pl : configs[(size_t)c]) {
+                    const auto &cc = comps[(size_t)pl.comp];
+                    for (size_t i = 0; i < cc.size(); i++)
+                        for (int q = 0; q < cpl; q++) {
+                            const int col = round * cpl + q;
+                            if (col < (int)cc.size()) cf.vcol[((size_t)b * nl + pl.base + i) * cpl + q] = cc[(size_t)col];
+                        }
+                }
+            }
+        }
+    }
+    optimize_component_layout(cf);
+    cf.zeros.clear();
+    for (int c = 0; c < n; c++)
+        for (int r = 0; r < n; r++)
+            if (cf.comp_of[(size_t)r] != cf.comp_of[(size_t)c]) cf.zeros.push_back(c * n + r);
+    cf.gv = g;
+    cf.gv.n = cf.n_loc;
+    cf.gv.ell = cf.ell;
+    cf.gv.row_len.assign((size_t)W * cf.n_loc, (uint8_t)g.max_nnz);
+    cf.ok = true;
+    return true;
+}
+
+}  // namespace qsim

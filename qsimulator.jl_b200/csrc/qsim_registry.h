@@ -30,6 +30,8 @@ QSIM_DECLARE(variants_colperlane)
 QSIM_DECLARE(variants_blocked)
 QSIM_DECLARE(variants_lean)
 QSIM_DECLARE(variants_lean_t256)
+QSIM_DECLARE(variants_r1c2_t128)
+QSIM_DECLARE(variants_lean_c2)
 
 #define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \
     {                                                                                                     \

@@ -132,6 +132,19 @@ struct LaunchArgs {
     // p = -beta1/2 (first) and p = +beta2/2 (second).  Filled on the host per call.
     double pow_coef[2][16][10];
     double pow_exp2[2][128];
+    // Component pruning (propagators, u0 = I).  Column c of a propagator is supported on the connected component of c
+    // in the generator's graph, so every entry (r, c) with r and c in different components is exactly zero at all
+    // times -- in the reference too: its dense products only ever add 0 * x there -- and contributes nothing to the
+    // error norms.  The kernel then integrates a VIRTUAL system built on the host: warp w of a team holds g.n local
+    // rows (g.ell has team_warps * g.n rows, sources are local row numbers) made of whole units (component, group of
+    // CPL of its columns); cf_vrow[w * g.n + r] is the state row of local row r (-1: none) and
+    // cf_vcol[(b * g.n + r) * CPL + c] the state column of entry (r, c) in batch b (-1: none; batch b runs on warp
+    // b mod team_warps).  Norm divisors and results refer to the n_out x out_cols state the caller sees; the
+    // structural zeros of every save point are written once per trajectory from zero_pos (positions col * n_out + row,
+    // or positions inside the selection when sel_index is set).
+    const int *cf_vrow, *cf_vcol, *zero_pos;
+    int n_zero;
+    int out_cols;         // columns of the state as the caller sees it (= ncols except under component pruning)
     int team_bytes;       // shared bytes per team
     int off_park;         // lean kernels: offset of the park area inside the team region (5 * E * 512 bytes per warp)
     double reltol, abstol, gamma, qmin, qmax, beta1, beta2, qoldinit, dtmax;
@@ -993,6 +1006,13 @@ struct Kern {
         }
     }
 
+    // state column of entry (row-slot i, c) of the batch starting at virtual column col0 (-1: none)
+    static __device__ __forceinline__ int out_col(const LaunchArgs &a, int col0, int row_word, int c) {
+        if (a.cf_vcol) return __ldg(a.cf_vcol + (size_t)col0 * a.g.n + (size_t)(row_word >> 16) * CPL + c);
+        return col0 + c < a.ncols ? col0 + c : -1;
+    }
+
+    // row_of[i]: state row in bits 0..15 (component pruning: the warp-local row in bits 16..)
     static __device__ __forceinline__ void write_out(const LaunchArgs &a, const Geo &g, long long traj, int ksave, int col0,
                                                      const int (&row_of)[RPL], const bool (&row_ok)[RPL], const Vec &x_in) {
         const int n = a.n_out;
@@ -1012,9 +1032,9 @@ struct Kern {
                 if (ok[i]) {
 #pragma unroll
                     for (int c = 0; c < CPL; c++) {
-                        const int col = col0 + c;
-                        if (col < a.ncols) {
-                            const int si = __ldg(a.sel_index + (size_t)col * n + row_of[i]);
+                        const int col = out_col(a, col0, row_of[i], c);
+                        if (col >= 0) {
+                            const int si = __ldg(a.sel_index + (size_t)col * n + (row_of[i] & 0xFFFF));
                             const double2 v = x[i * CPL + c];
                             if (si >= 0) {
                                 if (a.sel_abs2)
@@ -1027,16 +1047,38 @@ struct Kern {
                 }
             return;
         }
-        double2 *dst = a.out + ((size_t)traj * a.n_ts + ksave) * (size_t)a.ncols * n;
+        double2 *dst = a.out + ((size_t)traj * a.n_ts + ksave) * (size_t)a.out_cols * n;
 #pragma unroll
         for (int i = 0; i < RPL; i++)
             if (ok[i]) {
 #pragma unroll
                 for (int c = 0; c < CPL; c++) {
-                    const int col = col0 + c;
-                    if (col < a.ncols) dst[(size_t)col * n + row_of[i]] = x[i * CPL + c];
+                    const int col = out_col(a, col0, row_of[i], c);
+                    if (col >= 0) dst[(size_t)col * n + (row_of[i] & 0xFFFF)] = x[i * CPL + c];
                 }
             }
+    }
+
+    // Component pruning: the structurally zero entries of save points [k_lo, k_hi) (value 0, or NaN for the unreached
+    // save points of a failed trajectory).  Positions are disjoint from every entry the lanes write.
+    static __device__ __forceinline__ void fill_zeros(const LaunchArgs &a, const Geo &g, long long traj, int k_lo, int k_hi,
+                                                      double val) {
+        for (int ks = k_lo; ks < k_hi; ks++) {
+            if (a.sel_index) {
+                const size_t base = ((size_t)traj * a.n_ts + ks) * (size_t)a.n_sel;
+                for (int z = g.team_thread; z < a.n_zero; z += g.team_threads) {
+                    const int si = __ldg(a.zero_pos + z);
+                    if (a.sel_abs2)
+                        reinterpret_cast<double *>(a.out)[base + si] = val;
+                    else
+                        a.out[base + si] = make_double2(val, val);
+                }
+            } else {
+                double2 *dst = a.out + ((size_t)traj * a.n_ts + ks) * (size_t)a.out_cols * a.n_out;
+                for (int z = g.team_thread; z < a.n_zero; z += g.team_threads)
+                    dst[__ldg(a.zero_pos + z)] = make_double2(val, val);
+            }
+        }
     }
 
     static __device__ __forceinline__ void initial_state(const LaunchArgs &a, const Geo &g, long long traj, int col0,
@@ -1046,11 +1088,12 @@ struct Kern {
 #pragma unroll
             for (int c = 0; c < CPL; c++) {
                 double2 v = make_double2(0.0, 0.0);
-                if (row_ok[i] && col0 + c < a.ncols && !(AS && g.split_helper)) {   // (a helper part starts at zero)
+                const int col = out_col(a, col0, row_of[i], c);
+                if (row_ok[i] && col >= 0 && !(AS && g.split_helper)) {   // (a helper part starts at zero)
                     if (a.identity_init)
-                        v.x = (row_of[i] == col0 + c) ? 1.0 : 0.0;
+                        v.x = ((row_of[i] & 0xFFFF) == col) ? 1.0 : 0.0;
                     else
-                        v = a.init[(size_t)traj * a.init_stride + row_of[i]];
+                        v = a.init[(size_t)traj * a.init_stride + (row_of[i] & 0xFFFF)];
                 }
                 u[i * CPL + c] = v;
             }
@@ -1172,7 +1215,7 @@ struct Kern {
         const double *ts = a.ts + (size_t)tin * a.ts_stride;
         const double *prow = a.params + (size_t)tin * a.n_params;
         const double t0 = ts[0], tend = ts[a.n_ts - 1];
-        const double ntot = (double)a.n_out * (double)a.ncols;
+        const double ntot = (double)a.n_out * (double)a.out_cols;
         const uint32_t V0 = g.sm_V, V1 = V0 + g.v_stride, V2 = V1 + g.v_stride, V3 = V2 + g.v_stride, V4 = V3 + g.v_stride;
         const uint32_t yb0 = g.sm_y0, yb1 = g.sm_y1;
         const size_t sbuf = (size_t)a.n_batches * g.cpb * n;
@@ -1210,6 +1253,7 @@ struct Kern {
         st.n_rhs = 0;
         st.dt_init = 0.0;
 
+        if (a.n_zero > 0) fill_zeros(a, g, tout, 0, a.n_ts, 0.0);   // component pruning: structural zeros of every save point
         // resolve the drive descriptors against this trajectory's parameter row; constant channel
         {
             ResolvedEval *rev = const_cast<ResolvedEval *>(
@@ -1712,6 +1756,7 @@ struct Kern {
             for (int e = 0; e < E; e++) tmp[e] = make_double2(qnan, qnan);
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps)
                 for (int ks = nsave; ks < a.n_ts; ks++) write_out(a, g, tout, ks, b * g.cpb + g.colofs, row_of, row_ok, tmp);
+            if (a.n_zero > 0) fill_zeros(a, g, tout, nsave, a.n_ts, qnan);
         }
         st.t_final = t;
         if (g.team_thread == 0 && a.stats) a.stats[tout] = st;
@@ -1868,13 +1913,16 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         sidx[i] = 0;
         row_of[i] = (K::BLK || K::TR) ? g.blk_row * RPL + i : row0 + 32 * i;   // (tiered: the virtual row, until below)
         row_ok[i] = lane_active && row_of[i] < n;
+        // component pruning: warp w's local rows are rows [w * n, w * n + n) of the row table and of cf_vrow
+        const int vbase = a.cf_vrow ? g.warp_in_team * n : 0;
+        if (a.cf_vrow && row_ok[i]) row_ok[i] = __ldg(a.cf_vrow + vbase + row_of[i]) >= 0;
         sidx[i] = row_of[i];
         const int row_eff = row_of[i] < n ? row_of[i] : n - 1;
         my_off[i] = 16u * ((K::TR ? __ldg(a.row_pos + row_eff) : row_eff) * a.y_row_stride);
         // the row table may hold more rows than the state (helper lanes of split rows): those lanes gather too
-        const bool ell_ok = lane_active && row_of[i] < a.g.n_vrows;
+        const bool ell_ok = lane_active && row_of[i] < (a.cf_vrow ? n : a.g.n_vrows);
         // (tiered: lanes without a row repeat the last lane's table rows, zero slot: their loads coincide with its loads)
-        const int ell_row = (ell_ok || (K::TR && row_of[i] < n)) ? row_of[i] : n - 1;
+        const int ell_row = vbase + ((ell_ok || (K::TR && row_of[i] < n)) ? row_of[i] : n - 1);
 #pragma unroll
         for (int j = 0; j < K::NZ; j++) {
             // rows shorter than the variant's capacity: own row, zero slot
@@ -1889,6 +1937,8 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         }
         // tiered: stage buffer and row table are indexed by the virtual row, initial state and results by the state row
         if (K::TR || K::AS) row_of[i] = row_ok[i] ? __ldg(a.row_perm + row_of[i]) : 0;
+        // component pruning: state row for the initial state and the results, local row (bits 16..) for the column lookup
+        if (a.cf_vrow) row_of[i] = (row_ok[i] ? __ldg(a.cf_vrow + vbase + sidx[i]) : 0) | (sidx[i] << 16);
     }
     double2 *sc_base = nullptr;
     if (a.streamed)

@@ -68,6 +68,35 @@ struct Generator {
     bool imag_only = false;    // every value slot is purely imaginary (A = i B, B real): real H, no dissipator
 };
 
+// Component form of a propagator problem (u0 = I).  Column c of the propagator is supported on the connected
+// component of c in the generator's graph (union of the patterns at all times); the entries outside are exactly zero
+// in the reference as well (time_evolution.jl:31-37, 98-111: dense products that only add 0 * x there) and add
+// nothing to the error norms, so the kernels integrate only the component blocks: a UNIT is one component together
+// with `cpl` of its columns, units are packed into the warps of a team (whole units, never split), and every warp
+// sees a small virtual system over its local rows.  build_component_form() in qsim_components.cpp.
+struct ComponentForm {
+    bool ok = false;
+    int n_comp = 0;
+    int rpl = 1, cpl = 1;              // rows / columns per lane of the kernel shape the form was packed for
+    int n_loc = 0;                     // local rows per warp (the kernel's n): at most 32 * rpl
+    int team_warps = 1, n_batches = 1, streamed = 0;
+    int max_nnz = 0;
+    int stride = 1;                    // stage-buffer row stride in 16-byte units (chosen with the layout)
+    std::vector<uint32_t> ell;         // [max_nnz][team_warps * n_loc]: local source row | slot << 16
+    std::vector<int> vrow;             // [team_warps * n_loc]: state row of a local row, -1: none
+    std::vector<int> vcol;             // [n_batches * n_loc * cpl]: state column of (batch, local row, c), -1: none
+    std::vector<int> zeros;            // col * n + row of every structurally zero entry of the state
+    int64_t nnz_cols = 0;              // sum over components of (stored entries x columns): executed complex MACs per RHS
+    int64_t entries = 0;               // structurally non-zero entries of the state
+    std::vector<int> comp_of;          // [n] component of every row
+    Generator gv;                      // the generator as make_plan sees it: n = n_loc, ell = the per-warp table, slots and evaluators unchanged
+    int rs = 0;                        // row-split form (see RowSplitComponentForm in qsim_api.cu)
+};
+bool build_component_form(const Generator &g, int rpl, int cpl, int max_team_warps, ComponentForm &cf);
+void optimize_component_layout(ComponentForm &cf);
+long component_layout_cost(const ComponentForm &cf, int S);
+void generator_components(const Generator &g, std::vector<int> &comp_of, std::vector<std::vector<int>> &comps);
+
 }  // namespace qsim
 
 struct qsim_problem {
@@ -99,5 +128,7 @@ struct qsim_problem {
     // tiered form of each generator (qsim_api.cu, build_tiered): built on first use, under plan_mutex
     std::shared_ptr<struct TieredForm> tiered[2];
     std::shared_ptr<struct AddSplitForm> addsplit[2];   // additively split rows (build_addsplit)
+    std::shared_ptr<qsim::ComponentForm> cform[2];      // component form of the propagator problems (make_plan)
+    bool cform_tried[2] = {false, false};
     std::mutex plan_mutex;
 };

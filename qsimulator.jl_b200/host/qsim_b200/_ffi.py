@@ -256,7 +256,7 @@ class Problem:
         return v.value
 
     PLAN_KEYS = ("n", "ncols", "nnz", "max_row", "n_slots", "n_dyn_slots", "n_chan", "team_warps", "teams_per_cta",
-                 "block", "smem_bytes", "streamed", "scratch_bytes_per_team", "value_mode", "rowsplit", "_reserved")
+                 "block", "smem_bytes", "streamed", "scratch_bytes_per_team", "value_mode", "rowsplit", "components")
 
     def plan_info(self, which) -> dict:
         """Generator and launch-plan facts of one entry point (qsim_problem_plan_info)."""

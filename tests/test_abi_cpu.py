@@ -79,8 +79,9 @@ def test_compiled_generator_matches_oracle_assembly(builder):
 def test_kernel_dispatch_names_and_flops():
     cqs, _, _, _ = W.config("cfg2")
     P = Problem(cqs)
-    # one-warp resident teams run the lean (168-register, 12 warps per SM) kernels
-    assert P.kernel_name("unitary_propagator").startswith("tsit5_lean_r1c3")
+    # one-warp resident teams run the lean kernels; the propagator is integrated on its component form (two
+    # columns per lane, 128 registers, 16 warps per SM)
+    assert P.kernel_name("unitary_propagator").startswith("tsit5_lean_r1c2")
     assert "resident" in P.kernel_name("unitary_propagator")
     assert "streamed" in P.kernel_name("me_propagator")
     # executed flop never exceed the dense count 8 d^3

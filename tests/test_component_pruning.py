@@ -1,0 +1,175 @@
+"""Component pruning of propagators (csrc/qsim_components.cpp): when the generator's graph splits into connected
+components the library integrates only the component blocks; the entries that couple different components are
+exactly zero in the reference as well (/root/reference/src/time_evolution.jl:31-37, 98-111: dense products that
+only ever add 0 * x there) and are written as zeros.  Checked here: the plan, parity with the oracle (which
+integrates the full dense state) at 1e-8 with identical step counts, exact zeros, agreement with the un-pruned
+kernels of the same library, selected output, failed trajectories."""
+import os
+
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+from scipy.sparse.csgraph import connected_components
+
+from oracle import c_oracle as co
+from qsim_b200 import (CompositeQSystem, Cos, HermitianSpec, LiteralHermitian, Param, add_hamiltonian, add_lindblad,
+                       scaled_operator)
+from qsim_b200 import workloads as W
+from qsim_b200._ffi import Problem
+
+WHICH = {"unitary_propagator": 0, "unitary_state": 1, "me_propagator": 2, "me_state": 3}
+
+
+def _pattern_components(P, kind, row):
+    pat = None
+    for t in (0.13, 0.77, 3.3):
+        A = P.eval(kind, t, row) != 0
+        pat = A if pat is None else (pat | A)
+    nc, lab = connected_components(csr_matrix(pat | pat.T), directed=False)
+    return nc, lab
+
+
+@pytest.mark.parametrize("name,kernel,ncomp,ratio", [("cfg2", "r1c2", 2, 0.5), ("cfg3", "r1c4", 2, 0.5),
+                                                      ("cfg4", "r3c1", 2, 0.5)])
+def test_plan_of_benchmark_configs(name, kernel, ncomp, ratio):
+    """The transmon gates of benchmarks.jl conserve the parity of the total excitation number: two components,
+    half of the propagator's entries, half of the generator multiply-adds."""
+    cqs, params, _, which = W.config(name)
+    P = Problem(cqs)
+    info = P.plan_info(which)
+    assert info["components"] == ncomp
+    nc, _ = _pattern_components(P, 0 if which.startswith("unitary") else 1, params[len(params) // 3])
+    assert nc == ncomp
+    assert kernel in P.kernel_name(which)
+    vm = info["value_mode"]
+    full = (4.0 if vm >= 1 else 8.0) * info["nnz"] * info["n"]
+    assert abs(P.flops_per_rhs(which) / full - ratio) < 0.02
+    # state evolution takes an arbitrary initial state: never pruned
+    assert P.plan_info("unitary_state")["components"] == 0
+    os.environ["QSIM_NO_PRUNE"] = "1"
+    try:
+        assert Problem(cqs).plan_info(which)["components"] == 0
+    finally:
+        del os.environ["QSIM_NO_PRUNE"]
+
+
+def _block_system(sizes, rng, lindblad=False, permute=True):
+    """Levels in blocks that nothing couples (after a random permutation of the levels): banded Hermitian blocks, a
+    driven operator that is block-diagonal too, optionally collapse operators inside the blocks."""
+    d = int(sum(sizes))
+    h = np.diag(min(0.3, 6.0 / d) * np.arange(d) + 0.05 * rng.normal(size=d)).astype(complex)
+    x = np.zeros((d, d))
+    lo = 0
+    for s in sizes:
+        for k in (1, 2):
+            if s > k:
+                off = 0.02 * (rng.normal(size=s - k) + 1j * rng.normal(size=s - k))
+                idx = np.arange(lo, lo + s - k)
+                h[idx, idx + k] += off
+                h[idx + k, idx] += off.conj()
+        if s > 1:
+            idx = np.arange(lo, lo + s - 1)
+            x[idx, idx + 1] = np.sqrt(np.arange(1, s))
+        lo += s
+    perm = rng.permutation(d) if permute else np.arange(d)
+    pm = np.eye(d)[perm]
+    h = pm @ h @ pm.T
+    x = pm @ x @ pm.T
+    q = LiteralHermitian("q", HermitianSpec(h))
+    cqs = CompositeQSystem([q])
+    add_hamiltonian(cqs, q)
+    add_hamiltonian(cqs, scaled_operator(x + x.T, Cos(amp=Param(0), freq=0.31, phase=0.4)), q)
+    if lindblad:
+        add_lindblad(cqs, 0.05 * x, [q])
+        add_lindblad(cqs, 0.03 * (pm @ np.diag(np.arange(d)).astype(complex) @ pm.T), [q])
+    return cqs
+
+
+def _check(cqs, fn, ts, params, n_comp_min=2):
+    P = Problem(cqs)
+    info = P.plan_info(fn)
+    assert info["components"] >= n_comp_min, info
+    shape = P.state_shape(WHICH[fn])
+    buf = np.full((len(params), len(ts), int(np.prod(shape))), np.nan + 1j * np.nan)   # every entry must be written
+    got, st = P.solve(fn, ts, params=params, out=buf)
+    assert not np.any(np.isnan(got.real))
+    want, ost = co.OracleProblem(cqs).solve(WHICH[fn], ts, params, mode=co.STRUCTURED, n_threads=8)
+    assert np.all(st["retcode"] == 0)
+    assert np.array_equal(st["n_accept"], ost["n_accept"]) and np.array_equal(st["n_reject"], ost["n_reject"])
+    err = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)))
+    assert err <= 1e-8, err
+    # entries between components: exact zeros in the oracle and here
+    assert np.array_equal(got == 0, want == 0) or np.all(got[want == 0] == 0)
+    assert np.count_nonzero(want == 0) > 0
+    # the un-pruned kernels of the same library: same steps, same numbers up to the rounding of the error norms
+    os.environ["QSIM_NO_PRUNE"] = "1"
+    try:
+        full, fst = Problem(cqs).solve(fn, ts, params=params)
+    finally:
+        del os.environ["QSIM_NO_PRUNE"]
+    assert np.array_equal(st["n_accept"], fst["n_accept"]) and np.array_equal(st["n_reject"], fst["n_reject"])
+    assert float(np.max(np.abs(got - full))) < 1e-10
+    return P.kernel_name(fn)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sizes", [[5, 4], [1, 1], [2, 1, 3], [7, 7, 2], [14, 13], [16, 16], [20, 9, 3], [12, 11, 10, 9],
+                                   [30, 20, 10, 4], [32, 32, 32], [41, 40], [50, 30, 10, 5, 1], [64, 32], [90, 4, 2]])
+def test_unitary_block_systems(sizes):
+    rng = np.random.default_rng(5150 + 7 * len(sizes) + sum(sizes))
+    cqs = _block_system(sizes, rng)
+    params = np.array([[0.01], [0.03], [0.02]])
+    d = sum(sizes)
+    ts = np.linspace(0.0, 2.0 if d <= 40 else 1.0, 4)
+    name = _check(cqs, "unitary_propagator", ts, params, n_comp_min=len(sizes))
+    print(sizes, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sizes", [[2, 1], [2, 2], [3, 2, 1], [5, 4], [6, 3]])
+def test_lindblad_block_systems(sizes):
+    """Blocks of levels -> the superoperator couples rho_ij only within (block of i, block of j) classes."""
+    rng = np.random.default_rng(808 + sum(sizes) + len(sizes))
+    cqs = _block_system(sizes, rng, lindblad=True)
+    params = np.array([[0.01], [0.03]])
+    d = sum(sizes)
+    ts = np.linspace(0.0, 0.6 if d > 6 else 1.5, 3)
+    name = _check(cqs, "me_propagator", ts, params)
+    print(sizes, name)
+
+
+@pytest.mark.gpu
+def test_benchmark_gates_pruned_vs_full():
+    """cfg2 (two transmons, 20 ns with dense-output points inside steps) and cfg4 (its Lindblad form) against the
+    oracle and the un-pruned kernels."""
+    cqs, _, _, _ = W.config("cfg2")
+    params = W.amp_freq_grid(64, 64)[[0, 777, 4095]]
+    assert "r1c2" in _check(cqs, "unitary_propagator", np.linspace(0.0, 20.0, 47), params)
+    cqs4, p4, _, _ = W.config("cfg4")
+    _check(cqs4, "me_propagator", np.array([0.0, 0.7, 1.5]), p4[[0, 8191]])
+
+
+@pytest.mark.gpu
+def test_selected_output_and_failed_trajectories():
+    cqs, _, _, _ = W.config("cfg2")
+    params = W.amp_freq_grid(64, 64)[[5, 4000]]
+    ts = np.arange(0.0, 4.0)
+    P = Problem(cqs)
+    full, _ = P.solve("unitary_propagator", ts, params=params)
+    rows = np.array([0, 1, 3, 4, 4, 8, 2], dtype=np.int32)
+    cols = np.array([0, 1, 1, 4, 5, 8, 7], dtype=np.int32)
+    pairs = np.stack([rows, cols], axis=1)
+    sel, _ = P.solve("unitary_propagator", ts, params=params, select=pairs,
+                     out=np.full((2, len(ts), len(rows)), np.nan + 0j))
+    assert np.array_equal(sel, full[:, :, rows, cols])
+    assert np.any(sel == 0) and np.any(sel != 0)
+    p2, _ = P.solve("unitary_propagator", ts, params=params, select=pairs, abs2=True, out=np.full((2, len(ts), len(rows)), np.nan))
+    assert np.array_equal(p2, np.abs(full[:, :, rows, cols]) ** 2) or np.allclose(p2, np.abs(full[:, :, rows, cols]) ** 2, rtol=1e-15)
+    # a trajectory that runs out of steps: every entry of the unreached save points is NaN, structural zeros included
+    from qsim_b200 import _abi
+    o = _abi.default_opts()
+    o.maxiters = 50
+    bad, st = P.solve("unitary_propagator", ts, params=params, opts=o)
+    assert np.all(st["retcode"] != 0)
+    assert np.all(np.isnan(bad[:, -1].real))
+    assert np.array_equal(bad[:, 0], np.broadcast_to(np.eye(9), (2, 9, 9)))

@@ -367,11 +367,13 @@ def test_repeated_runs_are_bitwise_identical():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env,tag", [("QSIM_NO_LEAN", "tsit5_r1c3_nnz5_t128_vm2"), ("QSIM_TIERED", "lean_tiered_r3c1"),
+@pytest.mark.parametrize("env,tag", [("QSIM_NO_LEAN", "tsit5_r1c2_nnz5_t128_vm2"), ("QSIM_NO_PRUNE", "tsit5_lean_r1c3_nnz5_t128_vm2"),
+                                     ("QSIM_MAX_MINB", "tsit5_lean_r1c2_nnz5_t128b3_vm2"), ("QSIM_TIERED", "lean_tiered_r3c1"),
                                      ("QSIM_SPLIT", "lean_split_r1c3_nnz3"), ("QSIM_ADDSPLIT", "lean_addsplit_r1c3_nnz3")])
 def test_cfg2_kernel_variants(monkeypatch, env, tag):
-    """The default cfg2 kernel is the lean row-per-lane one (168 registers, 12 warps per SM).  The 255-register
-    kernel (QSIM_NO_LEAN=1) and the three opt-in mappings -- three rows of one column per lane sorted into tiers
+    """The default cfg2 kernel is the lean row-per-lane one on the component form (two blocks of 5 x 5 and 4 x 4 entries,
+    two columns per lane, 128 registers, 16 warps per SM).  Its 255-register form (QSIM_NO_LEAN=1), its 168-register
+    form (QSIM_MAX_MINB=3), the lean kernel on the full 9 x 9 state (QSIM_NO_PRUNE=1) and the three opt-in mappings -- three rows of one column per lane sorted into tiers
     (QSIM_TIERED=1), split rows with helper lanes (QSIM_SPLIT=1), additively split rows (QSIM_ADDSPLIT=1: the long row's
     state carried as two parts that add up to the physical entry) -- take the same step sequence and agree with it to
     rounding and with the oracle to 1e-8, including dense-output points inside steps (parked stage vectors)."""
@@ -381,9 +383,9 @@ def test_cfg2_kernel_variants(monkeypatch, env, tag):
     pr = np.ascontiguousarray(params[np.linspace(0, len(params) - 1, 40).astype(int)])
     ts = np.linspace(0.0, 5.0, 11)
     P = Problem(cqs)
-    assert "tsit5_lean_r1c3_nnz5_t128_vm2" in P.kernel_name(fn)
+    assert "tsit5_lean_r1c2_nnz5_t128b4_vm2" in P.kernel_name(fn)
     base, st0 = P.solve(fn, ts, params=pr)
-    monkeypatch.setenv(env, "1")
+    monkeypatch.setenv(env, "3" if env == "QSIM_MAX_MINB" else "1")
     P2 = Problem(cqs)
     assert tag in P2.kernel_name(fn)
     alt, st1 = P2.solve(fn, ts, params=pr)
