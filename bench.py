@@ -154,6 +154,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def pruning_info(prob, which, info):
+    """Component pruning (csrc/qsim_components.cpp): connected components of the generator graph, the fraction of the
+    generator multiply-adds (= of the propagator's entries, to within the blocks' density) that is integrated, and
+    the flop one RHS call of the un-pruned sparse form would execute."""
+    per = 4.0 if info["value_mode"] >= 1 else 8.0
+    full = per * info["nnz"] * (info["n"] if which in (0, 2, "unitary_propagator", "me_propagator") else 1)
+    f = prob.flops_per_rhs(which)
+    return {"components": info["components"], "integrated_fraction": f / full if full > 0 else 1.0,
+            "flops_per_rhs_full_state": full}
+
+
 def recorded_traffic(kernel, n_traj, n_ts):
     """Cross-check only: DRAM bytes per launch from the committed `ncu --set full` capture of this kernel on this
     workload (profiles/traffic.json), or None when no capture matches."""
@@ -254,10 +265,10 @@ def run_extra_config(name, ctx, world, rank, dev, dist, peak_tflops, deadline, r
     t0 = time.perf_counter()
     prob.solve(which, ts, params=probe, ctx=ctx, select=select)
     probe_s = reduce_max(time.perf_counter() - t0)
-    # N = 1 runs the shard one GPU of the smallest stated multi-GPU run gets (cfg5: 65536 / 2); the budget guard
-    # halves the shard further when the probe predicts that the call would not fit the time that is left
-    n_run = per_rank if name != "cfg5" else n_total // max(world, 2)
-    full = n_run == per_rank
+    # every rank runs its whole shard (N = 1: the whole config, cfg5's 65 536 points included); the budget guard halves
+    # the shard only when the probe predicts that the call would not fit the time that is left
+    n_run = per_rank
+    full = True
     budget = max(20.0, deadline - time.perf_counter())
     while n_run > n_probe and probe_s * n_run / n_probe * 0.9 > budget:
         n_run //= 2
@@ -301,12 +312,14 @@ def run_extra_config(name, ctx, world, rank, dev, dist, peak_tflops, deadline, r
         "roofline": {"bound": "fp64", "achieved": flops / (kernel_ms_max * 1e-3) / 1e12 / world, "peak": peak_tflops,
                      "unit": "TFLOP/s", "frac": flops / (kernel_ms_max * 1e-3) / 1e12 / world / peak_tflops,
                      "flops_per_rhs": prob.flops_per_rhs(which), "generator_nnz": info["nnz"],
+                     "pruning": pruning_info(prob, which, info),
+                     "full_state_equivalent_tflops": pruning_info(prob, which, info)["flops_per_rhs_full_state"]
+                                                     * (6.0 * attempts + 2.0 * n_done) / (kernel_ms_max * 1e-3) / 1e12 / world,
                      "scratch_stream_gbs": (info["scratch_bytes_per_team"] * attempts / max(kernel_ms_max * 1e-3, 1e-9) / 1e9
                                             if info["streamed"] else 0.0)},
     }
     if not res["full_config"]:
-        res["note"] = ("N=1 integrates the shard one GPU of the 2-GPU run gets" if name == "cfg5" and world == 1 and
-                       n_done == n_total // 2 else "reduced by the time-budget guard: value/e2e are rates per point")
+        res["note"] = "reduced by the time-budget guard: value/e2e are rates per point"
     if inv:
         res.update(inv)
     # parity against the oracle on two points, short span (elementwise, identical step counts)
@@ -523,6 +536,7 @@ def main():
         value = n_traj * world / (ms_per_step * 1e-3)
         achieved = flops_per_launch / (total_ms / args.steps * 1e-3) / 1e12
         xcheck, xsrc = recorded_traffic(prob.kernel_name(which), n_traj, len(ts))
+        prune = pruning_info(prob, which, prob.plan_info(which))
         out_bytes = n_traj * n_ts * d * d * 16
         line = {
             "metric": METRIC, "value": value, "unit": "propagators/s", "n_gpus": world, "steps": args.steps,
@@ -543,14 +557,21 @@ def main():
                          "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                         "nominal 37.2)",
                          "flop_counted": "executed sparse generator multiply-adds only (%d flop each: the generator is "
-                                         "%s); RK stage combinations, error norm and drive evaluation not counted"
+                                         "%s), on the component blocks of the propagator only (the entries between "
+                                         "components are exactly zero and are not integrated); RK stage combinations, "
+                                         "error norm and drive evaluation not counted"
                                          % ((4, "purely imaginary, 2 DFMA per entry") if "_vm0" not in prob.kernel_name(which)
                                             else (8, "complex, 4 DFMA per entry")),
+                         "pruning": prune,
+                         # the same launch time against the sparse generator applied to the full state (what the kernels
+                         # executed before component pruning) and against the reference's dense products
+                         "full_state_equivalent_tflops": prune["flops_per_rhs_full_state"] * (6.0 * attempts + 2.0 * n_traj)
+                                                         / (total_ms / args.steps * 1e-3) / 1e12,
                          "dense_equivalent_tflops": dense_flops_per_launch / (total_ms / args.steps * 1e-3) / 1e12,
                          # informational: + the Runge-Kutta vector arithmetic any Tsit5 must do per attempted step and
                          # complex state entry (21 stage-combination and 7 error-estimate real-by-complex multiply-adds
                          # at 4 flop, 6 stage arguments u + dt*(...) at 4 flop, ~10 flop of scaled error norm = 146 flop)
-                         "tsit5_total_tflops": (flops_per_launch + 146.0 * d * d * attempts)
+                         "tsit5_total_tflops": (flops_per_launch + 146.0 * d * d * prune["integrated_fraction"] * attempts)
                                                / (total_ms / args.steps * 1e-3) / 1e12,
                          "hbm_out_gbs": out_bytes / (total_ms / args.steps * 1e-3) / 1e9},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -99,9 +99,9 @@ struct qsim_problem::DeviceCopy {
     // (stage stride, team warps, value mode): me_propagator and me_state of one problem use different sets and may
     // run concurrently from different ctxs, so sets are never replaced, only added (freed with the problem).
     struct Packed {
-        int stride, warps, vm, cu = 0;
+        int stride, warps, vm, cu = 0, cf = 0;
         uint32_t *ell = nullptr;
-        int *perm = nullptr, *off = nullptr, *len = nullptr, *pos = nullptr;
+        int *perm = nullptr, *off = nullptr, *len = nullptr, *pos = nullptr, *pass = nullptr;
     };
     std::vector<Packed> packed;
     uint8_t *slot_imag = nullptr;    // value mode 4
@@ -124,6 +124,7 @@ struct qsim_problem::DeviceCopy {
             cudaFree(pk.off);
             cudaFree(pk.len);
             cudaFree(pk.pos);
+            cudaFree(pk.pass);
         }
         packed.clear();
         cudaFree(slot_imag);
@@ -1169,6 +1170,51 @@ static void build_rowsplit_table(const Generator &g, Plan &pl, bool full) {
 }
 
 // which: 0 unitary_propagator, 1 unitary_state, 2 me_propagator, 3 me_state
+// Row tables of a row-split component form: every component's own table (build_rowsplit_table on the component's
+// generator: rows sorted by length in chunks of 32, sources as positions inside the unit, annealed against bank
+// conflicts), concatenated; plus the empty chunk.  rs_perm holds state rows.
+static void build_rowsplit_component_tables(const ComponentForm &cf, Plan &pl, bool full) {
+    const uint32_t vb = pl.vm >= 1 ? 8u : 16u;
+    pl.rs_table.clear();
+    pl.rs_perm.clear();
+    pl.rs_pos.clear();
+    pl.rs_off.clear();
+    pl.rs_len.clear();
+    size_t total = 0;   // table entries so far
+    for (size_t k = 0; k < cf.subs.size(); k++) {
+        const Generator &sub = cf.subs[k];
+        Plan q;
+        q.rpl = 1;
+        q.team_warps = (sub.n + 31) / 32;
+        q.vm = pl.vm;
+        q.nvp = pl.nvp;
+        q.slot_imag = pl.slot_imag;
+        q.y_row_stride = pl.y_row_stride;
+        build_rowsplit_table(sub, q, full);
+        for (int c = 0; c < q.team_warps; c++) {
+            pl.rs_off.push_back(q.rs_off[(size_t)c] + (int)(total / 32));
+            pl.rs_len.push_back(q.rs_len[(size_t)c]);
+        }
+        if (full) {
+            pl.rs_table.insert(pl.rs_table.end(), q.rs_table.begin(), q.rs_table.end());
+            for (int v : q.rs_perm) pl.rs_perm.push_back(v >= 0 ? cf.comp_rows[k][(size_t)v] : -1);
+            pl.rs_pos.insert(pl.rs_pos.end(), q.rs_pos.begin(), q.rs_pos.end());
+        }
+        total += (size_t)q.ell_bytes / sizeof(uint32_t);
+    }
+    // the empty chunk: no rows, a zero diagonal and the two look-ahead rows
+    pl.rs_off.push_back((int)(total / 32));
+    pl.rs_len.push_back(1);
+    if (full) {
+        const uint32_t zero = (vb * (uint32_t)cf.gv.n_slots) << 16;   // position 0, zero slot
+        pl.rs_table.insert(pl.rs_table.end(), (size_t)32 * 3, zero);
+        pl.rs_perm.insert(pl.rs_perm.end(), 32, -1);
+        pl.rs_pos.insert(pl.rs_pos.end(), 32, 0);
+    }
+    total += 32 * 3;
+    pl.ell_bytes = (int)(total * sizeof(uint32_t));
+}
+
 // every off-diagonal entry of the generator is a per-trajectory constant (only diagonal slots depend on time)
 static bool offdiag_static(const Generator &g) {
     for (int j = 1; j < g.max_nnz; j++)
@@ -1251,11 +1297,17 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     // above and below run on the full state.
     if (pl.identity && !pl.af && !std::getenv("QSIM_NO_PRUNE") && !std::getenv("QSIM_BLOCKED") && !std::getenv("QSIM_TIERED") &&
         !std::getenv("QSIM_SPLIT") && !std::getenv("QSIM_SPLIT_ROWS") && !std::getenv("QSIM_COLPERLANE") && !std::getenv("QSIM_LEAN9") &&
-        gp.n <= 96 && gp.max_nnz <= 16) {
+        gp.n <= 9 * 96) {
         std::lock_guard<std::mutex> lk(p->plan_mutex);
         if (!p->cform_tried[pl.w]) {
             p->cform_tried[pl.w] = true;
-            choose_component_form(gp, p->cform[pl.w]);
+            if (gp.n <= 96 && gp.max_nnz <= 16)
+                choose_component_form(gp, p->cform[pl.w]);
+            else {
+                // row-split kernels: passes over several units at once, eight-warp teams
+                auto cf = std::make_shared<ComponentForm>();
+                if (build_rowsplit_component_form(gp, 8, *cf)) p->cform[pl.w] = cf;
+            }
         }
         if (p->cform[pl.w] && p->cform[pl.w]->ok) pl.cf = p->cform[pl.w].get();
     }
@@ -1267,6 +1319,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         rpl = pl.cf->rpl;
         cpl = pl.cf->cpl;
         pl.groups = 1;
+        pl.rowsplit = pl.cf->rs;
     } else if (n <= 16) {
         rpl = 1;
         pl.groups = std::min(32 / n, pl.ncols);
@@ -1498,7 +1551,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.y_row_stride = pl.cf->stride;   // chosen together with the rows' positions (optimize_component_layout)
         pl.y_grp_stride = cpl;
         if (16 * n * pl.y_row_stride > 65535) return fail(QSIM_ERR_UNSUPPORTED, "state too large for the packed 16-bit row offsets");
-        if (std::getenv("QSIM_DEBUG"))
+        if (std::getenv("QSIM_DEBUG") && !pl.cf->rs)
             std::fprintf(stderr, "[qsim] component form: %d components, r%dc%d, %d warps x %d local rows, %d batches%s: stage stride %d, "
                                  "%ld wavefronts per stage\n", pl.cf->n_comp, rpl, cpl, pl.team_warps, n, pl.n_batches,
                          pl.streamed ? " (streamed)" : "", pl.y_row_stride, component_layout_cost(*pl.cf, pl.y_row_stride));
@@ -1547,8 +1600,11 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
         pl.off_park = (pl.team_bytes + 15) & ~15;
         pl.team_bytes = pl.off_park + pl.team_warps * 5 * rpl * cpl * 512;
     }
-    const size_t smem_cap = 220 * 1024;
+    const size_t smem_cap = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100a
     if (pl.rowsplit) {
+        if (pl.cf)
+            build_rowsplit_component_tables(*pl.cf, pl, std::getenv("QSIM_DEBUG_LAYOUT") != nullptr);
+        else
         build_rowsplit_table(g, pl, std::getenv("QSIM_DEBUG_LAYOUT") != nullptr);   // (debug: run the annealer without a GPU)
         // team region: + three mbarriers, + the two prefetch buffers (u, k1 of a column each) for streamed teams;
         // common region: + the row table.  Both are dropped (global-memory table, direct scratch loads) when the
@@ -1581,7 +1637,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
                      g.n_dyn_slots, g.n_chan, pl.common_bytes, pl.team_bytes, pl.teams_per_cta, pl.smem,
                      pl.ell_in_smem ? ", row table in smem" : "", pl.rs_prefetch ? ", bulk prefetch" : "");
     pl.scratch_per_team = pl.streamed ? (size_t)4 * pl.n_batches * cpb * n * sizeof(double2) : 0;
-    if (pl.smem > 220 * 1024) return fail(QSIM_ERR_UNSUPPORTED, "problem needs more shared memory than one SM has");
+    if (pl.smem > smem_cap) return fail(QSIM_ERR_UNSUPPORTED, "problem needs more shared memory than one SM has");
     return QSIM_OK;
 }
 
@@ -1771,7 +1827,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         if (pl.rowsplit) {
             bool have = false;
             for (const auto &q : dc->packed)
-                if (q.stride == pl.y_row_stride && q.warps == pl.team_warps && q.vm == pl.vm && q.cu == pl.cu) {
+                if (q.stride == pl.y_row_stride && q.warps == pl.team_warps && q.vm == pl.vm && q.cu == pl.cu && q.cf == (pl.cf ? 1 : 0)) {
                     pk = q;
                     have = true;
                 }
@@ -1780,6 +1836,11 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
                 pk.warps = pl.team_warps;
                 pk.vm = pl.vm;
                 pk.cu = pl.cu;
+                pk.cf = pl.cf ? 1 : 0;
+                if (pl.cf) {
+                    build_rowsplit_component_tables(*pl.cf, pl, true);
+                    CU(upload(&pk.pass, pl.cf->pass));
+                } else
                 build_rowsplit_table(g, pl, true);
                 CU(upload(&pk.ell, pl.rs_table));
                 CU(upload(&pk.pos, pl.rs_pos));
@@ -1799,10 +1860,12 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
             CU(upload(&dc->as_phys, pl.af->phys));
             CU(upload(&dc->as_info, pl.af->lane_info));
         }
-        if (pl.cf && !dc->cf_ell) {
-            CU(upload(&dc->cf_ell, pl.cf->ell));
-            CU(upload(&dc->cf_vrow, pl.cf->vrow));
-            CU(upload(&dc->cf_vcol, pl.cf->vcol));
+        if (pl.cf && !dc->cf_zeros) {
+            if (!pl.cf->rs) {
+                CU(upload(&dc->cf_ell, pl.cf->ell));
+                CU(upload(&dc->cf_vrow, pl.cf->vrow));
+                CU(upload(&dc->cf_vcol, pl.cf->vcol));
+            }
             CU(upload(&dc->cf_zeros, pl.cf->zeros));
         }
         if (pl.tiered && !dc->tr_ell) {
@@ -1972,9 +2035,13 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     if (pl.cf) {   // the kernel runs over each warp's local rows; results, norms and the initial state refer to the state
         a.g.n = pl.cf->n_loc;
         a.g.n_vrows = pl.cf->team_warps * pl.cf->n_loc;
-        a.g.ell = dc->cf_ell;
-        a.cf_vrow = dc->cf_vrow;
-        a.cf_vcol = dc->cf_vcol;
+        if (pl.cf->rs) {
+            a.rs_pass = reinterpret_cast<const int4 *>(pk.pass);
+        } else {
+            a.g.ell = dc->cf_ell;
+            a.cf_vrow = dc->cf_vrow;
+            a.cf_vcol = dc->cf_vcol;
+        }
         if (!sel) {
             a.zero_pos = dc->cf_zeros;
             a.n_zero = (int)pl.cf->zeros.size();

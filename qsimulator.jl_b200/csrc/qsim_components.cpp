@@ -12,7 +12,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <numeric>
 #include <vector>
 
@@ -91,26 +93,37 @@ long component_layout_cost(const ComponentForm &cf, int S) {
     return c;
 }
 
-// Padding entries and rows without a state row read the first address their quarter warp really reads at that entry
-// (a broadcast: no extra wavefront), or their own position when the quarter reads nothing there.
+// Padding entries (zero slot) and local rows without a state row read an address that is read or written anyway: the
+// first source their quarter warp really gathers at that entry (a broadcast: no extra wavefront), else the position
+// of a row of the quarter (of the warp, if the quarter has none).  They must not read a position nobody stores to:
+// the operand is multiplied by zero, but uninitialised shared memory may hold a NaN.
 static void resolve_padding(ComponentForm &cf) {
     const int W = cf.team_warps, nl = cf.n_loc;
-    for (int w = 0; w < W; w++)
-        for (int j = 1; j < cf.max_nnz; j++)
+    for (int w = 0; w < W; w++) {
+        int first_row = -1;
+        for (int r = 0; r < nl && first_row < 0; r++)
+            if (cf.vrow[(size_t)w * nl + r] >= 0) first_row = r;
+        if (first_row < 0) first_row = 0;
+        for (int j = 0; j < cf.max_nnz; j++)
             for (int r0 = 0; r0 < nl; r0 += 8) {
-                int real = -1;
-                for (int r = r0; r < std::min(nl, r0 + 8) && real < 0; r++) {
+                const int r1 = std::min(nl, r0 + 8);
+                int real = -1, anchor = first_row;
+                for (int r = r1 - 1; r >= r0; r--)
+                    if (cf.vrow[(size_t)w * nl + r] >= 0) anchor = r;
+                for (int r = r0; r < r1 && real < 0 && j > 0; r++) {
                     const uint32_t e = cf.ell[((size_t)j * W + w) * nl + r];
                     if (cf.vrow[(size_t)w * nl + r] >= 0 && (e >> 16) != 0xFFFFu) real = (int)(e & 0xFFFFu);
                 }
-                for (int r = r0; r < std::min(nl, r0 + 8); r++) {
+                for (int r = r0; r < r1; r++) {
                     uint32_t &e = cf.ell[((size_t)j * W + w) * nl + r];
-                    if (cf.vrow[(size_t)w * nl + r] < 0 || (e >> 16) == 0xFFFFu) e = (uint32_t)(real >= 0 ? real : r) | (0xFFFFu << 16);
+                    const bool hole = cf.vrow[(size_t)w * nl + r] < 0;
+                    if (j == 0) {
+                        if (hole) e = (uint32_t)anchor | (0xFFFFu << 16);   // (the diagonal operand comes from registers)
+                    } else if (hole || (e >> 16) == 0xFFFFu)
+                        e = (uint32_t)(real >= 0 ? real : anchor) | (0xFFFFu << 16);
                 }
             }
-    for (int w = 0; w < W; w++)   // the diagonal entry of a row without a state row: own position, zero slot
-        for (int r = 0; r < nl; r++)
-            if (cf.vrow[(size_t)w * nl + r] < 0) cf.ell[(size_t)w * nl + r] = (uint32_t)r | (0xFFFFu << 16);
+    }
 }
 
 // Chooses, per warp, which local row (= lane, = position in the stage buffer) every row of the warp's units takes, by
@@ -391,10 +404,139 @@ bool build_component_form(const Generator &g, int rpl, int cpl, int max_team_war
     for (int c = 0; c < n; c++)
         for (int r = 0; r < n; r++)
             if (cf.comp_of[(size_t)r] != cf.comp_of[(size_t)c]) cf.zeros.push_back(c * n + r);
+    if (std::getenv("QSIM_DEBUG")) {
+        // self-check: every entry inside a component block is held by exactly one (batch, local row, c)
+        std::vector<int> cover((size_t)n * n, 0);
+        const int nl2 = cf.n_loc;
+        long bad = 0;
+        for (int b = 0; b < cf.n_batches; b++)
+            for (int r = 0; r < nl2; r++)
+                for (int q = 0; q < cpl; q++) {
+                    const int col = cf.vcol[((size_t)b * nl2 + r) * cpl + q], row = cf.vrow[(size_t)(b % W) * nl2 + r];
+                    if (col >= 0 && row < 0) bad++;
+                    if (col >= 0 && row >= 0) cover[(size_t)col * n + row]++;
+                }
+        for (int c = 0; c < n; c++)
+            for (int r = 0; r < n; r++)
+                if (cover[(size_t)c * n + r] != (cf.comp_of[(size_t)r] == cf.comp_of[(size_t)c] ? 1 : 0)) bad++;
+        std::fprintf(stderr, "[qsim] component form r%dc%d self-check: %ld bad entries\n", rpl, cpl, bad);
+    }
     cf.gv = g;
     cf.gv.n = cf.n_loc;
     cf.gv.ell = cf.ell;
     cf.gv.row_len.assign((size_t)W * cf.n_loc, (uint8_t)g.max_nnz);
+    cf.ok = true;
+    return true;
+}
+
+// Row-split form: passes over several units at once (see ComponentForm).  Units are placed largest component first;
+// a pass is filled with as many units of the current component as fit its 3 * team_warps chunks, then topped up with
+// units of smaller components.  Within a pass the chunks are dealt to (row-slot, warp) longest rows first, so the
+// warps of the team carry about equal work.
+bool build_rowsplit_component_form(const Generator &g, int team_warps, ComponentForm &cf) {
+    const int n = g.n, W = team_warps, slots = 3 * W;
+    std::vector<std::vector<int>> comps;
+    generator_components(g, cf.comp_of, comps);
+    cf.ok = false;
+    cf.n_comp = (int)comps.size();
+    if (comps.size() < 2) return false;
+    std::vector<int> order(comps.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return comps[(size_t)a].size() > comps[(size_t)b].size(); });
+    if (((int)comps[(size_t)order[0]].size() + 31) / 32 > slots) return false;
+    cf.rs = 1;
+    cf.rpl = 3;
+    cf.cpl = 1;
+    cf.team_warps = W;
+    cf.n_loc = 96 * W;
+    cf.stride = 1;
+    cf.max_nnz = g.max_nnz;
+    // components in placement order, their generators and chunk lengths (rows sorted by length, as rowsplit_rows does)
+    const int nk_total = (int)comps.size();
+    cf.subs.assign((size_t)nk_total, Generator());
+    cf.comp_rows.assign((size_t)nk_total, {});
+    cf.cc_first.assign((size_t)nk_total, 0);
+    std::vector<std::vector<int>> chunk_len((size_t)nk_total);
+    std::vector<int> local((size_t)n, 0);
+    cf.nnz_cols = 0;
+    cf.entries = 0;
+    int n_cc = 0;
+    for (int ki = 0; ki < nk_total; ki++) {
+        const auto &rows = comps[(size_t)order[(size_t)ki]];
+        const int nk = (int)rows.size();
+        cf.comp_rows[(size_t)ki] = rows;
+        for (int i = 0; i < nk; i++) local[(size_t)rows[(size_t)i]] = i;
+        Generator &sub = cf.subs[(size_t)ki];
+        sub = g;
+        sub.n = nk;
+        sub.ell.assign((size_t)g.max_nnz * nk, 0);
+        sub.row_len.assign((size_t)nk, (uint8_t)g.max_nnz);
+        std::vector<int> len((size_t)nk, 1);
+        int64_t nnz = 0;
+        for (int i = 0; i < nk; i++)
+            for (int j = 0; j < g.max_nnz; j++) {
+                const uint32_t e = g.ell[(size_t)j * n + rows[(size_t)i]];
+                const bool pad = e == 0xFFFFFFFFu || (e >> 16) == 0xFFFFu;
+                sub.ell[(size_t)j * nk + i] = pad ? ((uint32_t)i | (0xFFFFu << 16)) : ((uint32_t)local[(size_t)(e & 0xFFFFu)] | (e & 0xFFFF0000u));
+                if (!pad) nnz++;
+                if (!pad && j > 0) len[(size_t)i]++;
+            }
+        sub.nnz = nnz;
+        cf.nnz_cols += nnz * nk;
+        cf.entries += (int64_t)nk * nk;
+        std::sort(len.begin(), len.end(), std::greater<int>());
+        cf.cc_first[(size_t)ki] = n_cc;
+        for (int c0 = 0; c0 < nk; c0 += 32) chunk_len[(size_t)ki].push_back(len[(size_t)c0]);
+        n_cc += (nk + 31) / 32;
+    }
+    cf.n_cc = n_cc;
+    // ---- passes ----
+    std::vector<int> next_col((size_t)nk_total, 0);
+    cf.pass.clear();
+    int n_pass = 0;
+    for (;;) {
+        struct Chunk { int cc, ubase, col, len; };
+        std::vector<Chunk> chunks;
+        int free_slots = slots, ubase = 0;
+        for (int ki = 0; ki < nk_total; ki++) {
+            const int nk = (int)cf.comp_rows[(size_t)ki].size(), ncc = (nk + 31) / 32;
+            while (next_col[(size_t)ki] < nk && ncc <= free_slots) {
+                const int col = cf.comp_rows[(size_t)ki][(size_t)next_col[(size_t)ki]++];
+                for (int t = 0; t < ncc; t++) chunks.push_back({cf.cc_first[(size_t)ki] + t, ubase, col, chunk_len[(size_t)ki][(size_t)t]});
+                free_slots -= ncc;
+                ubase += (nk + 7) & ~7;
+            }
+        }
+        if (chunks.empty()) break;
+        std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk &a, const Chunk &b) { return a.len > b.len; });
+        for (int c = 0; c < slots; c++) {
+            if (c < (int)chunks.size()) {
+                cf.pass.push_back(chunks[(size_t)c].cc);
+                cf.pass.push_back(chunks[(size_t)c].ubase);
+                cf.pass.push_back(chunks[(size_t)c].col);
+            } else {
+                cf.pass.push_back(n_cc);   // the empty chunk
+                cf.pass.push_back(0);
+                cf.pass.push_back(0);
+            }
+            cf.pass.push_back(0);
+        }
+        n_pass++;
+    }
+    cf.n_batches = n_pass;
+    cf.streamed = n_pass > 1 ? 1 : 0;
+    cf.zeros.clear();
+    for (int c = 0; c < n; c++)
+        for (int r = 0; r < n; r++)
+            if (cf.comp_of[(size_t)r] != cf.comp_of[(size_t)c]) cf.zeros.push_back(c * n + r);
+    if (std::getenv("QSIM_DEBUG")) {
+        long used = 0;
+        for (size_t i = 0; i < cf.pass.size(); i += 4) used += cf.pass[i] != n_cc ? 1 : 0;
+        std::fprintf(stderr, "[qsim] row-split component form: %d components (largest %zu rows), %d component chunks, %d passes of %d chunk "
+                             "slots (%ld filled) instead of %d columns\n", cf.n_comp, comps[(size_t)order[0]].size(), n_cc, n_pass, slots, used, n);
+    }
+    cf.gv = g;
+    cf.gv.n = cf.n_loc;
     cf.ok = true;
     return true;
 }

@@ -39,11 +39,11 @@ QSIM_DECLARE(variants_lean_c2)
             launch_solver<R, C, M, T, B, I, false>, occupancy_solver<R, C, M, T, B, I, false>               \
     }
 // row-split variants: rows spread over the team's warps, sparse rows from a table in shared (or global) memory;
-// the per-lane `ell` registers hold {table offset, row length} of each of the lane's three chunks
+// the per-lane `ell` registers hold {table offset, row length, unit position (component passes)} of each of the lane's three chunks
 #define QSIM_VARIANT_RS(T, I)                                                                             \
     {                                                                                                     \
-        3, 1, 2, T, 1, I, 1, "tsit5_rowsplit_r3c1_t" #T "_vm" #I, launch_solver<3, 1, 2, T, 1, I, true>,      \
-            occupancy_solver<3, 1, 2, T, 1, I, true>                                                      \
+        3, 1, 3, T, 1, I, 1, "tsit5_rowsplit_r3c1_t" #T "_vm" #I, launch_solver<3, 1, 3, T, 1, I, true>,      \
+            occupancy_solver<3, 1, 3, T, 1, I, true>                                                      \
     }
 // column-per-lane variants (propagators with 17..32 rows): four whole rows per warp, lane = column
 #define QSIM_VARIANT_CU(T, I)                                                                             \

@@ -143,6 +143,11 @@ struct LaunchArgs {
     // structural zeros of every save point are written once per trajectory from zero_pos (positions col * n_out + row,
     // or positions inside the selection when sel_index is set).
     const int *cf_vrow, *cf_vcol, *zero_pos;
+    // Component pruning in the row-split kernels: a batch is a PASS over up to 3 * team_warps chunks of 32 rows taken from
+    // several units (component, one of its columns) at once.  rs_pass[b * 3 * team_warps + chunk] = {component chunk
+    // (index into rs_off / rs_len / rs_perm / rs_pos), position of the unit inside the stage buffer, state column, -};
+    // the row tables hold sources relative to the unit's position.  g.n = 96 * team_warps local rows per pass.
+    const int4 *rs_pass;
     int n_zero;
     int out_cols;         // columns of the state as the caller sees it (= ncols except under component pruning)
     int team_bytes;       // shared bytes per team
@@ -908,6 +913,8 @@ struct Kern {
                 // (padded on the host to 1 + an even count, plus one spare pair), so the off-diagonal entries are
                 // taken two at a time with the next pair's table words requested ahead of the multiply-adds.
                 const int nnz = (int)ell[i][MAXNNZ > 1 ? 1 : 0];
+                const uint32_t yb_full = yb;
+                const uint32_t yb = yb_full + (MAXNNZ > 2 ? ell[i][MAXNNZ > 2 ? 2 : 0] : 0u);   // + the unit's position (component passes)
                 if (g.sm_ell) {
                     const uint32_t tb = g.sm_ell + ell[i][0];
                     uint32_t ea = ldsu(tb + 128u), eb = ldsu(tb + 256u);
@@ -1008,6 +1015,7 @@ struct Kern {
 
     // state column of entry (row-slot i, c) of the batch starting at virtual column col0 (-1: none)
     static __device__ __forceinline__ int out_col(const LaunchArgs &a, int col0, int row_word, int c) {
+        if (RS && a.rs_pass) return row_word >> 16;   // (row-split passes: the chunk's column rides in the row word)
         if (a.cf_vcol) return __ldg(a.cf_vcol + (size_t)col0 * a.g.n + (size_t)(row_word >> 16) * CPL + c);
         return col0 + c < a.ncols ? col0 + c : -1;
     }
@@ -1247,6 +1255,27 @@ struct Kern {
             }
         };
 
+        // Component passes of the row-split kernels: batch b brings its own rows -- per chunk (row-slot i, this warp) the
+        // component chunk, the unit's position in the stage buffer and its state column (LaunchArgs::rs_pass).  The
+        // per-lane tables are the kernel's own local arrays (never const objects), rewritten here.
+        auto load_pass = [&](int b) {
+            if (!(RS && MAXNNZ > 2) || !a.rs_pass) return;
+#pragma unroll
+            for (int i = 0; i < RPL; i++) {
+                const int chunk = i * a.team_warps + g.warp_in_team;
+                const int4 d = __ldg(a.rs_pass + (size_t)b * (size_t)(RPL * a.team_warps) + chunk);
+                const int q = d.x * 32 + g.lane;
+                const int rr = __ldg(a.rs_perm + q);
+                const_cast<bool &>(row_ok[i]) = rr >= 0;
+                const_cast<int &>(row_of[i]) = rr >= 0 ? (rr | (d.z << 16)) : 0;
+                const_cast<int &>(sidx[i]) = chunk * 32 + g.lane;
+                const_cast<uint32_t &>(my_off[i]) = 16u * (uint32_t)((d.y + __ldg(a.rs_pos + q)) * a.y_row_stride);
+                const_cast<uint32_t &>(ell[i][0]) = 4u * (32u * (uint32_t)__ldg(a.rs_off + d.x) + (uint32_t)g.lane);
+                const_cast<uint32_t &>(ell[i][MAXNNZ > 1 ? 1 : 0]) = (uint32_t)__ldg(a.rs_len + d.x);
+                const_cast<uint32_t &>(ell[i][MAXNNZ > 2 ? 2 : 0]) = 16u * (uint32_t)(d.y * a.y_row_stride);
+            }
+        };
+
         qsim_traj_stats st;
         st.retcode = QSIM_RET_SUCCESS;
         st.n_accept = st.n_reject = 0;
@@ -1294,6 +1323,7 @@ struct Kern {
             // ---- initial step (DiffEqBase ode_determine_initdt) ----
             double acc2[2] = {0.0, 0.0};
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
+                load_pass(b);
                 const int col0 = b * g.cpb + g.colofs;
                 initial_state(a, g, tin, col0, row_of, row_ok, u);
                 for (int ks = 0; ks < nsave; ks++) write_out(a, g, tout, ks, col0, row_of, row_ok, u);
@@ -1328,6 +1358,7 @@ struct Kern {
                 if (g.team_thread == 0) pf_issue(0, sc_u0, sc_k0);
             }
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
+                load_pass(b);
                 const int col0 = b * g.cpb + g.colofs;
                 if (a.streamed) fetch_uk(b, col0, sc_u0, sc_k0, u, k1);
 #pragma unroll
@@ -1439,6 +1470,7 @@ struct Kern {
                     if (g.team_thread == 0) pf_issue(0, sc_u0 + (size_t)(2 * cur) * sbuf, sc_k0 + (size_t)(2 * cur) * sbuf);
                 }
                 for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
+                    load_pass(b);
                     const int col0 = b * g.cpb + g.colofs;
                     if (a.streamed)
                         fetch_uk(b, col0, sc_u0 + (size_t)(2 * cur) * sbuf, sc_k0 + (size_t)(2 * cur) * sbuf, u, k1);
@@ -1744,6 +1776,7 @@ struct Kern {
         } else {
             // zero-length span: only the start saves
             for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
+                load_pass(b);
                 const int col0 = b * g.cpb + g.colofs;
                 initial_state(a, g, tin, col0, row_of, row_ok, u);
                 for (int ks = 0; ks < nsave; ks++) write_out(a, g, tout, ks, col0, row_of, row_ok, u);
@@ -1754,8 +1787,10 @@ struct Kern {
             const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
             for (int e = 0; e < E; e++) tmp[e] = make_double2(qnan, qnan);
-            for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps)
+            for (int b = RS ? 0 : g.warp_in_team; b < a.n_batches; b += RS ? 1 : a.team_warps) {
+                load_pass(b);
                 for (int ks = nsave; ks < a.n_ts; ks++) write_out(a, g, tout, ks, b * g.cpb + g.colofs, row_of, row_ok, tmp);
+            }
             if (a.n_zero > 0) fill_zeros(a, g, tout, nsave, a.n_ts, qnan);
         }
         st.t_final = t;
@@ -1899,6 +1934,15 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
             // the table's zero-slot padding (the host fills the whole chunk).
             // (rs_perm / rs_pos hold 32 entries per chunk; -1 marks a lane without a row.  With the column-per-lane
             // mapping all lanes of a chunk name the same row and the lane selects the column instead.)
+            if (MAXNNZ > 2) ell[i][MAXNNZ > 2 ? 2 : 0] = 0u;
+            if (a.rs_pass) {   // component passes: every batch loads its own rows (Kern::run, load_pass)
+                row_ok[i] = false;
+                row_of[i] = sidx[i] = 0;
+                my_off[i] = 0u;
+                ell[i][0] = 0u;
+                ell[i][MAXNNZ > 1 ? 1 : 0] = 1u;
+                continue;
+            }
             const int chunk = i * a.team_warps + g.warp_in_team;
             const int q = chunk * 32 + g.lane;
             const int rr = __ldg(a.rs_perm + q);
@@ -1907,7 +1951,7 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
             sidx[i] = row_ok[i] ? q : 0;
             my_off[i] = 16u * (uint32_t)(__ldg(a.rs_pos + q) * a.y_row_stride);
             ell[i][0] = 4u * (32u * (uint32_t)__ldg(a.rs_off + chunk) + (uint32_t)g.lane);  // byte offset of entry 0
-            ell[i][MAXNNZ - 1] = (uint32_t)__ldg(a.rs_len + chunk);                          // entries per row (0: no rows)
+            ell[i][MAXNNZ > 1 ? 1 : 0] = (uint32_t)__ldg(a.rs_len + chunk);                  // entries per row (0: no rows)
             continue;
         }
         sidx[i] = 0;
@@ -1927,6 +1971,9 @@ __global__ void __launch_bounds__(MAXT, MINB) solve_kernel(const __grid_constant
         for (int j = 0; j < K::NZ; j++) {
             // rows shorter than the variant's capacity: own row, zero slot
             uint32_t e = (uint32_t)row_eff | (0xFFFFu << 16);
+            // (component forms: a local row without a state row is never stored to the stage buffer; the host pointed its
+            // diagonal entry at a position that is, and the padding beyond the table's row length follows it)
+            if (a.cf_vrow) e = (a.g.ell[ell_row] & 0xFFFFu) | (0xFFFFu << 16);
             if (!RS && j < a.g.max_nnz) e = a.g.ell[(size_t)j * a.g.n_vrows + ell_row];
             // slot 0xFFFF marks a zero entry (padding, or a row without a stored diagonal)
             const uint32_t sl = (!ell_ok || (e >> 16) == 0xFFFFu) ? (uint32_t)a.g.n_slots : (e >> 16);

@@ -90,9 +90,20 @@ struct ComponentForm {
     int64_t entries = 0;               // structurally non-zero entries of the state
     std::vector<int> comp_of;          // [n] component of every row
     Generator gv;                      // the generator as make_plan sees it: n = n_loc, ell = the per-warp table, slots and evaluators unchanged
-    int rs = 0;                        // row-split form (see RowSplitComponentForm in qsim_api.cu)
+    // Row-split form (rs = 1: state vectors longer than 96 entries or rows longer than 16 entries).  A batch is a PASS:
+    // up to 3 * team_warps chunks of 32 rows taken from several units (component, ONE of its columns) at once.  Every
+    // component keeps its rows sorted by length in chunks of 32 (`subs[k]`: the component's own generator, local row
+    // numbers; the row tables are built from it by qsim_api.cu once the value mode is known); pass[4 * (b * 3 *
+    // team_warps + c)] = {component chunk, position of the unit in the stage buffer, state column, 0}; component chunk
+    // `n_cc` is the empty chunk.
+    int rs = 0, n_cc = 0;
+    std::vector<Generator> subs;       // per component: generator restricted to it
+    std::vector<std::vector<int>> comp_rows;   // per component: its state rows (local row -> state row)
+    std::vector<int> cc_first;         // per component: its first component chunk
+    std::vector<int> pass;
 };
 bool build_component_form(const Generator &g, int rpl, int cpl, int max_team_warps, ComponentForm &cf);
+bool build_rowsplit_component_form(const Generator &g, int team_warps, ComponentForm &cf);
 void optimize_component_layout(ComponentForm &cf);
 long component_layout_cost(const ComponentForm &cf, int S);
 void generator_components(const Generator &g, std::vector<int> &comp_of, std::vector<std::vector<int>> &comps);

@@ -53,7 +53,7 @@ def test_plan_of_benchmark_configs(name, kernel, ncomp, ratio):
         del os.environ["QSIM_NO_PRUNE"]
 
 
-def _block_system(sizes, rng, lindblad=False, permute=True):
+def _block_system(sizes, rng, lindblad=False, permute=True, band=2):
     """Levels in blocks that nothing couples (after a random permutation of the levels): banded Hermitian blocks, a
     driven operator that is block-diagonal too, optionally collapse operators inside the blocks."""
     d = int(sum(sizes))
@@ -61,7 +61,7 @@ def _block_system(sizes, rng, lindblad=False, permute=True):
     x = np.zeros((d, d))
     lo = 0
     for s in sizes:
-        for k in (1, 2):
+        for k in range(1, band + 1):
             if s > k:
                 off = 0.02 * (rng.normal(size=s - k) + 1j * rng.normal(size=s - k))
                 idx = np.arange(lo, lo + s - k)
@@ -173,3 +173,18 @@ def test_selected_output_and_failed_trajectories():
     assert np.all(st["retcode"] != 0)
     assert np.all(np.isnan(bad[:, -1].real))
     assert np.array_equal(bad[:, 0], np.broadcast_to(np.eye(9), (2, 9, 9)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sizes,band", [([70, 60], 2), ([100, 50, 30, 20], 2), ([120, 40, 5, 3, 1, 1], 2), ([20, 20], 19),
+                                        ([30, 25, 18], 24)])
+def test_row_split_block_systems(sizes, band):
+    """State vectors longer than 96 entries, or rows longer than 16 entries: the row-split kernels integrate several
+    units (component, column) per pass."""
+    rng = np.random.default_rng(31337 + sum(sizes) + band)
+    cqs = _block_system(sizes, rng, band=band)
+    params = np.array([[0.02], [0.01]])
+    ts = np.array([0.0, 0.4, 0.8])
+    name = _check(cqs, "unitary_propagator", ts, params, n_comp_min=len(sizes))
+    assert "rowsplit" in name
+    print(sizes, name)
