@@ -551,6 +551,7 @@ struct Plan {
     // row-split teams: compact row table (see LaunchArgs::rs_off), row permutation, chunk offsets / lengths
     std::vector<uint32_t> rs_table;
     std::vector<int> rs_perm, rs_off, rs_len, rs_pos;
+    std::vector<int> rs_lane;          // component passes: {row | col << 16, stage offset, table offset, len | unit offset << 8} per (pass, chunk, lane)
     int ell_in_smem = 0, off_ell = 0, ell_bytes = 0, rs_prefetch = 0, off_pf = 0;
     // split rows (LaunchArgs::split_info): virtual row table [split_nnz][split_nv], per-lane info
     int split_nv = 0, split_nnz = 0;
@@ -1025,7 +1026,7 @@ static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int bloc
                                               variants_r1c4_t256, variants_r2c1_t128,
                                               variants_r2c2_t256, variants_r3c1_t128, variants_r3c1_t256,
                                               variants_rowsplit, variants_colperlane, variants_blocked, variants_lean,
-                                              variants_lean_t256, variants_r1c2_t128, variants_lean_c2};
+                                              variants_lean_t256, variants_r1c2_t128, variants_lean_c2, variants_lean_c2_t256};
     // (development: QSIM_MAX_MINB caps the occupancy target of the chosen variant, e.g. 3 keeps the 168-register lean kernels)
     const int max_minb = std::getenv("QSIM_MAX_MINB") ? std::atoi(std::getenv("QSIM_MAX_MINB")) : 99;
     const KernelVariant *best = nullptr;
@@ -1213,6 +1214,21 @@ static void build_rowsplit_component_tables(const ComponentForm &cf, Plan &pl, b
     }
     total += 32 * 3;
     pl.ell_bytes = (int)(total * sizeof(uint32_t));
+    if (!full) return;
+    // per (pass, chunk, lane) records for the kernel (LaunchArgs::rs_pass)
+    const size_t n_rec = cf.pass.size() / 4;
+    pl.rs_lane.assign(n_rec * 32 * 4, 0);
+    for (size_t c = 0; c < n_rec; c++) {
+        const int cc = cf.pass[4 * c], ubase = cf.pass[4 * c + 1], col = cf.pass[4 * c + 2];
+        for (int l = 0; l < 32; l++) {
+            const int q = cc * 32 + l, row = pl.rs_perm[(size_t)q];
+            int *rec = &pl.rs_lane[(c * 32 + (size_t)l) * 4];
+            rec[0] = row >= 0 ? (row | (col << 16)) : -1;
+            rec[1] = 16 * (ubase + pl.rs_pos[(size_t)q]) * pl.y_row_stride;
+            rec[2] = 4 * (32 * pl.rs_off[(size_t)cc] + l);
+            rec[3] = pl.rs_len[(size_t)cc] | ((16 * ubase * pl.y_row_stride) << 8);
+        }
+    }
 }
 
 // every off-diagonal entry of the generator is a per-trajectory constant (only diagonal slots depend on time)
@@ -1227,9 +1243,11 @@ static bool offdiag_static(const Generator &g) {
 
 // Component pruning of a propagator problem: the kernel shape (rows x columns per lane), the packing and the kernel
 // variant with the best estimated throughput, or nothing when the generator is connected.  The estimate: a Tsit5 step
-// of a warp costs about 2200 + 650 E cycles (E = entries per lane; measured on cfg2); one-warp
-// teams run 12 per SM in the lean kernels (E <= 3) and 8 otherwise, multi-warp resident teams floor(8 / warps) per
-// SM, streamed teams one per SM with their batches in sequence.
+// of a warp costs about 2200 + 650 E cycles (E = entries per lane; measured on cfg2) plus 340 per
+// further warp of the team (barriers; fitted to cfg3: five warps x three columns 441 ms, four x four 470 ms, seven x two
+// 484 ms per 1184 x 50 ns); one-warp teams run four per CTA and as many CTAs per SM as the variant's register target
+// allows, multi-warp resident teams share a CTA of up to eight warps (two CTAs per SM where the variant asks for it),
+// streamed teams run one per SM with their batches in sequence.
 static void choose_component_form(const Generator &gp, std::shared_ptr<ComponentForm> &out) {
     const bool no_lean = std::getenv("QSIM_NO_LEAN") != nullptr;
     const bool stat = gp.imag_only && offdiag_static(gp);
@@ -1257,8 +1275,12 @@ static void choose_component_form(const Generator &gp, std::shared_ptr<Component
             if (cf->streamed)
                 score = 1.0 / (2200.0 + (double)(cf->n_batches / W) * (650.0 * E + 400.0));
             else {
-                const int warps_per_sm = (W == 1 && lv && E <= 3) ? 12 : 8;
-                score = (double)(warps_per_sm / W) / (2200.0 + 650.0 * E);
+                // teams per SM: one-warp teams, four per CTA, as many CTAs as the variant's register target allows;
+                // multi-warp teams share a CTA of up to eight warps, two CTAs per SM where the variant asks for it
+                const int teams_per_sm = W == 1 ? 4 * kv->minb : kv->minb * tpc;
+                score = (double)teams_per_sm / (2200.0 + 650.0 * E + 340.0 * (W - 1));   // (+ team barriers; measured on cfg3)
+                if (const char *force = std::getenv("QSIM_CF_SHAPE"))   // development: "r1c4" forces a shape
+                    if (std::string(force) == "r" + std::to_string(rpl) + "c" + std::to_string(cpl)) score = 1e9;
             }
             if (std::getenv("QSIM_DEBUG"))
                 std::fprintf(stderr, "[qsim] component form r%dc%d: %d components, %d warps%s, %d batches, %d local rows, %s: score %.3g\n",
@@ -1839,7 +1861,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
                 pk.cf = pl.cf ? 1 : 0;
                 if (pl.cf) {
                     build_rowsplit_component_tables(*pl.cf, pl, true);
-                    CU(upload(&pk.pass, pl.cf->pass));
+                    CU(upload(&pk.pass, pl.rs_lane));
                 } else
                 build_rowsplit_table(g, pl, true);
                 CU(upload(&pk.ell, pl.rs_table));

@@ -144,9 +144,11 @@ struct LaunchArgs {
     // or positions inside the selection when sel_index is set).
     const int *cf_vrow, *cf_vcol, *zero_pos;
     // Component pruning in the row-split kernels: a batch is a PASS over up to 3 * team_warps chunks of 32 rows taken from
-    // several units (component, one of its columns) at once.  rs_pass[b * 3 * team_warps + chunk] = {component chunk
-    // (index into rs_off / rs_len / rs_perm / rs_pos), position of the unit inside the stage buffer, state column, -};
-    // the row tables hold sources relative to the unit's position.  g.n = 96 * team_warps local rows per pass.
+    // several units (component, one of its columns) at once.  The host expands the pass list into one 16-byte record
+    // per (pass, chunk, lane): rs_pass[(b * 3 * team_warps + chunk) * 32 + lane] = {state row | state column << 16
+    // (-1: no row), byte offset of the lane's entry in the stage buffer, byte offset of its first row-table entry,
+    // entries per row | byte offset of the unit in the stage buffer << 8}.  The row tables hold sources relative to the
+    // unit's position.  g.n = 96 * team_warps local rows per pass.
     const int4 *rs_pass;
     int n_zero;
     int out_cols;         // columns of the state as the caller sees it (= ncols except under component pruning)
@@ -1255,24 +1257,21 @@ struct Kern {
             }
         };
 
-        // Component passes of the row-split kernels: batch b brings its own rows -- per chunk (row-slot i, this warp) the
-        // component chunk, the unit's position in the stage buffer and its state column (LaunchArgs::rs_pass).  The
-        // per-lane tables are the kernel's own local arrays (never const objects), rewritten here.
+        // Component passes of the row-split kernels: batch b brings its own rows (one record per lane and row-slot,
+        // LaunchArgs::rs_pass).  The per-lane tables are the kernel's own local arrays (never const objects), rewritten here.
         auto load_pass = [&](int b) {
             if (!(RS && MAXNNZ > 2) || !a.rs_pass) return;
 #pragma unroll
             for (int i = 0; i < RPL; i++) {
                 const int chunk = i * a.team_warps + g.warp_in_team;
-                const int4 d = __ldg(a.rs_pass + (size_t)b * (size_t)(RPL * a.team_warps) + chunk);
-                const int q = d.x * 32 + g.lane;
-                const int rr = __ldg(a.rs_perm + q);
-                const_cast<bool &>(row_ok[i]) = rr >= 0;
-                const_cast<int &>(row_of[i]) = rr >= 0 ? (rr | (d.z << 16)) : 0;
+                const int4 d = __ldg(a.rs_pass + ((size_t)b * (size_t)(RPL * a.team_warps) + chunk) * 32 + g.lane);
+                const_cast<bool &>(row_ok[i]) = d.x >= 0;
+                const_cast<int &>(row_of[i]) = d.x >= 0 ? d.x : 0;
                 const_cast<int &>(sidx[i]) = chunk * 32 + g.lane;
-                const_cast<uint32_t &>(my_off[i]) = 16u * (uint32_t)((d.y + __ldg(a.rs_pos + q)) * a.y_row_stride);
-                const_cast<uint32_t &>(ell[i][0]) = 4u * (32u * (uint32_t)__ldg(a.rs_off + d.x) + (uint32_t)g.lane);
-                const_cast<uint32_t &>(ell[i][MAXNNZ > 1 ? 1 : 0]) = (uint32_t)__ldg(a.rs_len + d.x);
-                const_cast<uint32_t &>(ell[i][MAXNNZ > 2 ? 2 : 0]) = 16u * (uint32_t)(d.y * a.y_row_stride);
+                const_cast<uint32_t &>(my_off[i]) = (uint32_t)d.y;
+                const_cast<uint32_t &>(ell[i][0]) = (uint32_t)d.z;
+                const_cast<uint32_t &>(ell[i][MAXNNZ > 1 ? 1 : 0]) = (uint32_t)d.w & 0xFFu;
+                const_cast<uint32_t &>(ell[i][MAXNNZ > 2 ? 2 : 0]) = (uint32_t)d.w >> 8;
             }
         };
 
@@ -1282,7 +1281,6 @@ struct Kern {
         st.n_rhs = 0;
         st.dt_init = 0.0;
 
-        if (a.n_zero > 0) fill_zeros(a, g, tout, 0, a.n_ts, 0.0);   // component pruning: structural zeros of every save point
         // resolve the drive descriptors against this trajectory's parameter row; constant channel
         {
             ResolvedEval *rev = const_cast<ResolvedEval *>(
@@ -1314,6 +1312,9 @@ struct Kern {
         int cur = 0;
         int nsave = 0;
         while (nsave < a.n_ts && ts[nsave] <= t0) nsave++;  // save_start: every ts[k] == t0
+        // component pruning: the structural zeros of a save point are written when the save point is (spread over the
+        // trajectory: a burst of them at the start of every trajectory backs up the write path of page-locked results)
+        if (a.n_zero > 0) fill_zeros(a, g, tout, 0, nsave, 0.0);
         const double inf = __longlong_as_double(0x7ff0000000000000LL);
         double ts_next = nsave < a.n_ts ? ts[nsave] : inf;
 
@@ -1753,6 +1754,7 @@ struct Kern {
                         cur ^= 1;
                     }
                     if (nsave_hi > nsave) {
+                        if (a.n_zero > 0) fill_zeros(a, g, tout, nsave, nsave_hi, 0.0);
                         nsave = nsave_hi;
                         CTL_ST(C_TSNEXT, nsave < a.n_ts ? ts[nsave] : inf);
                     }

@@ -29,7 +29,7 @@ def _pattern_components(P, kind, row):
     return nc, lab
 
 
-@pytest.mark.parametrize("name,kernel,ncomp,ratio", [("cfg2", "r1c2", 2, 0.5), ("cfg3", "r1c4", 2, 0.5),
+@pytest.mark.parametrize("name,kernel,ncomp,ratio", [("cfg2", "r1c2", 2, 0.5), ("cfg3", "r1c3", 2, 0.5),
                                                       ("cfg4", "r3c1", 2, 0.5)])
 def test_plan_of_benchmark_configs(name, kernel, ncomp, ratio):
     """The transmon gates of benchmarks.jl conserve the parity of the total excitation number: two components,
