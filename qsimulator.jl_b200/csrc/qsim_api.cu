@@ -99,7 +99,8 @@ struct qsim_problem::DeviceCopy {
     // (stage stride, team warps, value mode): me_propagator and me_state of one problem use different sets and may
     // run concurrently from different ctxs, so sets are never replaced, only added (freed with the problem).
     struct Packed {
-        int stride, warps, vm, cu = 0, cf = 0;
+        int stride, warps, vm, cu = 0;
+        const ComponentForm *cf = nullptr;
         uint32_t *ell = nullptr;
         int *perm = nullptr, *off = nullptr, *len = nullptr, *pos = nullptr, *pass = nullptr;
     };
@@ -114,8 +115,14 @@ struct qsim_problem::DeviceCopy {
     uint32_t *as_ell = nullptr;      // additively split rows: row table over the table rows, table row -> state row, lane info
     int *as_phys = nullptr;
     uint8_t *as_info = nullptr;
-    uint32_t *cf_ell = nullptr;      // component form: per-warp row table, local row -> state row, (batch, local row, c) -> state
-    int *cf_vrow = nullptr, *cf_vcol = nullptr, *cf_zeros = nullptr;   // column, structurally zero entries
+    // component forms (the propagator's, and one per support pattern of the initial states seen): per-warp row table,
+    // local row -> state row, (batch, local row, c) -> state column, structurally zero entries
+    struct CfDev {
+        const ComponentForm *form = nullptr;
+        uint32_t *ell = nullptr;
+        int *vrow = nullptr, *vcol = nullptr, *zeros = nullptr;
+    };
+    std::vector<CfDev> cf_sets;
     ~DeviceCopy() { free_all(); }  // the owning device must be current
     void free_all() {
         for (auto &pk : packed) {
@@ -148,12 +155,13 @@ struct qsim_problem::DeviceCopy {
         as_ell = nullptr;
         as_phys = nullptr;
         as_info = nullptr;
-        cudaFree(cf_ell);
-        cudaFree(cf_vrow);
-        cudaFree(cf_vcol);
-        cudaFree(cf_zeros);
-        cf_ell = nullptr;
-        cf_vrow = cf_vcol = cf_zeros = nullptr;
+        for (auto &q : cf_sets) {
+            cudaFree(q.ell);
+            cudaFree(q.vrow);
+            cudaFree(q.vcol);
+            cudaFree(q.zeros);
+        }
+        cf_sets.clear();
         cudaFree(dyn_rec);
         dyn_rec = nullptr;
         cudaFree(tables);
@@ -1292,7 +1300,7 @@ static void choose_component_form(const Generator &gp, std::shared_ptr<Component
         }
 }
 
-static int make_plan(qsim_problem *p, int which, Plan &pl) {
+static int make_plan(qsim_problem *p, int which, Plan &pl, const ComponentForm *state_cf = nullptr) {
     pl.w = which >= 2 ? 1 : 0;
     if (int rc = ensure_generator(p, pl.w)) return rc;
     const Generator &gp = p->gen[pl.w];
@@ -1317,7 +1325,9 @@ static int make_plan(qsim_problem *p, int which, Plan &pl) {
     // Component pruning (propagators): integrate only the blocks of the connected components of the generator's graph
     // (qsim_components.cpp).  QSIM_NO_PRUNE=1 keeps the full state (development A/B switch); the opt-in experiments
     // above and below run on the full state.
-    if (pl.identity && !pl.af && !std::getenv("QSIM_NO_PRUNE") && !std::getenv("QSIM_BLOCKED") && !std::getenv("QSIM_TIERED") &&
+    if (state_cf) {
+        pl.cf = state_cf;   // state evolution on the components the initial state touches (solve_common, state_form_for)
+    } else if (pl.identity && !pl.af && !std::getenv("QSIM_NO_PRUNE") && !std::getenv("QSIM_BLOCKED") && !std::getenv("QSIM_TIERED") &&
         !std::getenv("QSIM_SPLIT") && !std::getenv("QSIM_SPLIT_ROWS") && !std::getenv("QSIM_COLPERLANE") && !std::getenv("QSIM_LEAN9") &&
         gp.n <= 9 * 96) {
         std::lock_guard<std::mutex> lk(p->plan_mutex);
@@ -1793,6 +1803,49 @@ static bool host_pointer_is_pinned(const void *ptr, void **dev_alias) {
     return true;
 }
 
+// State evolution (unitary_state / me_state) with host-side initial states: the components of the generator graph that
+// the initial states touch (any of them, when every trajectory brings its own).  Entries of the other components stay
+// exactly zero, in the reference too, so only the touched ones are integrated (csrc/qsim_components.cpp, state forms);
+// forms are cached in the problem by the set of touched components.  *out stays nullptr when nothing can be pruned.
+static int state_form_for(qsim_problem *p, int which, const double *init, int64_t init_stride, int64_t n_points,
+                          const ComponentForm **out) {
+    *out = nullptr;
+    if (std::getenv("QSIM_NO_PRUNE")) return QSIM_OK;
+    const int w = which >= 2 ? 1 : 0;
+    if (int rc = ensure_generator(p, w)) return rc;
+    const Generator &g = p->gen[w];
+    if (g.n > 9 * 96) return QSIM_OK;
+    std::lock_guard<std::mutex> lk(p->plan_mutex);
+    if (p->n_comp[w] < 0) {
+        std::vector<std::vector<int>> comps;
+        generator_components(g, p->comp_of[w], comps);
+        p->n_comp[w] = (int)comps.size();
+    }
+    if (p->n_comp[w] < 2) return QSIM_OK;
+    std::vector<char> touched((size_t)p->n_comp[w], 0);
+    int n_touched = 0;
+    const int64_t n_init = init_stride ? n_points : 1;
+    for (int64_t t = 0; t < n_init && n_touched < p->n_comp[w]; t++) {
+        const double *v = init + 2 * (size_t)t * (size_t)init_stride;
+        for (int r = 0; r < g.n; r++)
+            if ((v[2 * r] != 0.0 || v[2 * r + 1] != 0.0) && !touched[(size_t)p->comp_of[w][(size_t)r]]) {
+                touched[(size_t)p->comp_of[w][(size_t)r]] = 1;
+                n_touched++;
+            }
+    }
+    if (n_touched == 0 || n_touched == p->n_comp[w]) return QSIM_OK;
+    for (const auto &q : p->sforms[w])
+        if (q.first == touched) {
+            if (q.second && q.second->ok) *out = q.second.get();
+            return QSIM_OK;
+        }
+    auto cf = std::make_shared<ComponentForm>();
+    const bool ok = build_state_form(g, touched, *cf);
+    p->sforms[w].emplace_back(touched, ok ? cf : nullptr);
+    if (ok) *out = cf.get();
+    return QSIM_OK;
+}
+
 static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj, const double *params,
                         const double *ts, int n_ts, int64_t ts_stride, const double *init, int64_t init_stride,
                         const qsim_solver_opts *opts_in, double *out, qsim_traj_stats *stats,
@@ -1831,8 +1884,11 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
                     return fail(QSIM_ERR_ARG, "ts must be sorted");
     }
     if (n_traj == 0) return QSIM_OK;
+    const ComponentForm *state_cf = nullptr;
+    if ((which == 1 || which == 3) && !dev_ptrs && init)
+        if (int rc = state_form_for(p, which, init, init_stride, sh.total, &state_cf)) return rc;
     Plan pl;
-    if (int rc = make_plan(p, which, pl)) return rc;
+    if (int rc = make_plan(p, which, pl, state_cf)) return rc;
     CU(cudaSetDevice(c->device));
     qsim_problem::DeviceCopy *dc = nullptr;
     if (int rc = ensure_device_copy(c, p, pl.w, &dc)) return rc;
@@ -1844,12 +1900,13 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
     const uint32_t *d_blk_ell = nullptr;
     const uint16_t *d_blk_slot = nullptr;
     const int *d_tr_perm = nullptr, *d_tr_pos = nullptr;
+    qsim_problem::DeviceCopy::CfDev cfd;
     {
         std::lock_guard<std::mutex> packed_lock(p->dev_mutex);
         if (pl.rowsplit) {
             bool have = false;
             for (const auto &q : dc->packed)
-                if (q.stride == pl.y_row_stride && q.warps == pl.team_warps && q.vm == pl.vm && q.cu == pl.cu && q.cf == (pl.cf ? 1 : 0)) {
+                if (q.stride == pl.y_row_stride && q.warps == pl.team_warps && q.vm == pl.vm && q.cu == pl.cu && q.cf == pl.cf) {
                     pk = q;
                     have = true;
                 }
@@ -1858,7 +1915,7 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
                 pk.warps = pl.team_warps;
                 pk.vm = pl.vm;
                 pk.cu = pl.cu;
-                pk.cf = pl.cf ? 1 : 0;
+                pk.cf = pl.cf;
                 if (pl.cf) {
                     build_rowsplit_component_tables(*pl.cf, pl, true);
                     CU(upload(&pk.pass, pl.rs_lane));
@@ -1882,13 +1939,19 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
             CU(upload(&dc->as_phys, pl.af->phys));
             CU(upload(&dc->as_info, pl.af->lane_info));
         }
-        if (pl.cf && !dc->cf_zeros) {
-            if (!pl.cf->rs) {
-                CU(upload(&dc->cf_ell, pl.cf->ell));
-                CU(upload(&dc->cf_vrow, pl.cf->vrow));
-                CU(upload(&dc->cf_vcol, pl.cf->vcol));
+        if (pl.cf) {
+            for (const auto &q : dc->cf_sets)
+                if (q.form == pl.cf) cfd = q;
+            if (!cfd.form) {
+                cfd.form = pl.cf;
+                if (!pl.cf->rs) {
+                    CU(upload(&cfd.ell, pl.cf->ell));
+                    CU(upload(&cfd.vrow, pl.cf->vrow));
+                    CU(upload(&cfd.vcol, pl.cf->vcol));
+                }
+                CU(upload(&cfd.zeros, pl.cf->zeros));
+                dc->cf_sets.push_back(cfd);
             }
-            CU(upload(&dc->cf_zeros, pl.cf->zeros));
         }
         if (pl.tiered && !dc->tr_ell) {
             CU(upload(&dc->tr_ell, pl.tf->ell));
@@ -1934,7 +1997,8 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         size_t n_sel_zero = 0;
         if (pl.cf)
             for (int i = 0; i < sel->n_sel; i++)
-                if (pl.cf->comp_of[(size_t)sel->rows[i]] != pl.cf->comp_of[(size_t)(sel->cols ? sel->cols[i] : 0)]) {
+                if (pl.cf->state ? !pl.cf->live[(size_t)sel->rows[i]]
+                                 : pl.cf->comp_of[(size_t)sel->rows[i]] != pl.cf->comp_of[(size_t)(sel->cols ? sel->cols[i] : 0)]) {
                     index.push_back(i);
                     n_sel_zero++;
                 }
@@ -2060,12 +2124,12 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
         if (pl.cf->rs) {
             a.rs_pass = reinterpret_cast<const int4 *>(pk.pass);
         } else {
-            a.g.ell = dc->cf_ell;
-            a.cf_vrow = dc->cf_vrow;
-            a.cf_vcol = dc->cf_vcol;
+            a.g.ell = cfd.ell;
+            a.cf_vrow = cfd.vrow;
+            a.cf_vcol = cfd.vcol;
         }
         if (!sel) {
-            a.zero_pos = dc->cf_zeros;
+            a.zero_pos = cfd.zeros;
             a.n_zero = (int)pl.cf->zeros.size();
         }
     }

@@ -433,7 +433,7 @@ bool build_component_form(const Generator &g, int rpl, int cpl, int max_team_war
 // a pass is filled with as many units of the current component as fit its 3 * team_warps chunks, then topped up with
 // units of smaller components.  Within a pass the chunks are dealt to (row-slot, warp) longest rows first, so the
 // warps of the team carry about equal work.
-bool build_rowsplit_component_form(const Generator &g, int team_warps, ComponentForm &cf) {
+bool build_rowsplit_component_form(const Generator &g, int team_warps, ComponentForm &cf, const std::vector<char> *touched) {
     const int n = g.n, W = team_warps, slots = 3 * W;
     std::vector<std::vector<int>> comps;
     generator_components(g, cf.comp_of, comps);
@@ -445,6 +445,11 @@ bool build_rowsplit_component_form(const Generator &g, int team_warps, Component
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return comps[(size_t)a].size() > comps[(size_t)b].size(); });
     if (((int)comps[(size_t)order[0]].size() + 31) / 32 > slots) return false;
     cf.rs = 1;
+    cf.state = touched ? 1 : 0;
+    if (touched) {
+        cf.live.assign((size_t)n, 0);
+        for (int r = 0; r < n; r++) cf.live[(size_t)r] = (*touched)[(size_t)cf.comp_of[(size_t)r]];
+    }
     cf.rpl = 3;
     cf.cpl = 1;
     cf.team_warps = W;
@@ -482,8 +487,9 @@ bool build_rowsplit_component_form(const Generator &g, int team_warps, Component
                 if (!pad && j > 0) len[(size_t)i]++;
             }
         sub.nnz = nnz;
-        cf.nnz_cols += nnz * nk;
-        cf.entries += (int64_t)nk * nk;
+        const bool live_k = !touched || (*touched)[(size_t)order[(size_t)ki]];
+        cf.nnz_cols += touched ? (live_k ? nnz : 0) : nnz * nk;
+        cf.entries += touched ? (live_k ? nk : 0) : (int64_t)nk * nk;
         std::sort(len.begin(), len.end(), std::greater<int>());
         cf.cc_first[(size_t)ki] = n_cc;
         for (int c0 = 0; c0 < nk; c0 += 32) chunk_len[(size_t)ki].push_back(len[(size_t)c0]);
@@ -491,7 +497,10 @@ bool build_rowsplit_component_form(const Generator &g, int team_warps, Component
     }
     cf.n_cc = n_cc;
     // ---- passes ----
-    std::vector<int> next_col((size_t)nk_total, 0);
+    // units still to place per component: all its columns (propagators), or the one state column if the state touches it
+    std::vector<int> next_col((size_t)nk_total, 0), n_units((size_t)nk_total, 0);
+    for (int ki = 0; ki < nk_total; ki++)
+        n_units[(size_t)ki] = touched ? ((*touched)[(size_t)order[(size_t)ki]] ? 1 : 0) : (int)cf.comp_rows[(size_t)ki].size();
     cf.pass.clear();
     int n_pass = 0;
     for (;;) {
@@ -500,8 +509,9 @@ bool build_rowsplit_component_form(const Generator &g, int team_warps, Component
         int free_slots = slots, ubase = 0;
         for (int ki = 0; ki < nk_total; ki++) {
             const int nk = (int)cf.comp_rows[(size_t)ki].size(), ncc = (nk + 31) / 32;
-            while (next_col[(size_t)ki] < nk && ncc <= free_slots) {
-                const int col = cf.comp_rows[(size_t)ki][(size_t)next_col[(size_t)ki]++];
+            while (next_col[(size_t)ki] < n_units[(size_t)ki] && ncc <= free_slots) {
+                const int col = touched ? 0 : cf.comp_rows[(size_t)ki][(size_t)next_col[(size_t)ki]];
+                next_col[(size_t)ki]++;
                 for (int t = 0; t < ncc; t++) chunks.push_back({cf.cc_first[(size_t)ki] + t, ubase, col, chunk_len[(size_t)ki][(size_t)t]});
                 free_slots -= ncc;
                 ubase += (nk + 7) & ~7;
@@ -523,9 +533,14 @@ bool build_rowsplit_component_form(const Generator &g, int team_warps, Component
         }
         n_pass++;
     }
+    if (n_pass == 0) return false;
     cf.n_batches = n_pass;
     cf.streamed = n_pass > 1 ? 1 : 0;
     cf.zeros.clear();
+    if (touched) {
+        for (int r = 0; r < n; r++)
+            if (!cf.live[(size_t)r]) cf.zeros.push_back(r);
+    } else
     for (int c = 0; c < n; c++)
         for (int r = 0; r < n; r++)
             if (cf.comp_of[(size_t)r] != cf.comp_of[(size_t)c]) cf.zeros.push_back(c * n + r);
@@ -538,6 +553,69 @@ bool build_rowsplit_component_form(const Generator &g, int team_warps, Component
     cf.gv = g;
     cf.gv.n = cf.n_loc;
     cf.ok = true;
+    return true;
+}
+
+// State form: the rows of the components the initial state touches, one column.  Small live sets (at most 96 rows, rows
+// of at most 16 entries) run as ONE warp of the row-per-lane kernels whatever the size of the full state; larger ones as
+// passes of the row-split kernels (usually one).
+bool build_state_form(const Generator &g, const std::vector<char> &touched, ComponentForm &cf) {
+    const int n = g.n;
+    std::vector<std::vector<int>> comps;
+    generator_components(g, cf.comp_of, comps);
+    cf.ok = false;
+    cf.n_comp = (int)comps.size();
+    if (comps.size() < 2 || touched.size() != comps.size()) return false;
+    std::vector<int> rows;
+    for (size_t k = 0; k < comps.size(); k++)
+        if (touched[k]) rows.insert(rows.end(), comps[k].begin(), comps[k].end());
+    const int nl = (int)rows.size();
+    if (nl == 0 || nl == n) return false;
+    if (nl > 96 || g.max_nnz > 16) {
+        if (!build_rowsplit_component_form(g, 8, cf, &touched)) return false;
+        if (std::getenv("QSIM_DEBUG"))
+            std::fprintf(stderr, "[qsim] state form: %d of %d rows live (%d components), row-split, %d pass(es)\n", nl, n, cf.n_comp, cf.n_batches);
+        return true;
+    }
+    std::sort(rows.begin(), rows.end());
+    cf.state = 1;
+    cf.rs = 0;
+    cf.rpl = (nl + 31) / 32;
+    cf.cpl = 1;
+    cf.team_warps = 1;
+    cf.n_batches = 1;
+    cf.streamed = 0;
+    cf.max_nnz = g.max_nnz;
+    cf.n_loc = nl;
+    cf.live.assign((size_t)n, 0);
+    std::vector<int> local((size_t)n, -1);
+    for (int i = 0; i < nl; i++) {
+        cf.live[(size_t)rows[(size_t)i]] = 1;
+        local[(size_t)rows[(size_t)i]] = i;
+    }
+    cf.vrow = rows;
+    cf.vcol.assign((size_t)nl, 0);
+    cf.ell.assign((size_t)g.max_nnz * nl, 0);
+    cf.nnz_cols = 0;
+    for (int i = 0; i < nl; i++)
+        for (int j = 0; j < g.max_nnz; j++) {
+            const uint32_t e = g.ell[(size_t)j * n + rows[(size_t)i]];
+            const bool pad = e == 0xFFFFFFFFu || (e >> 16) == 0xFFFFu;
+            cf.ell[(size_t)j * nl + i] = pad ? ((uint32_t)i | (0xFFFFu << 16)) : ((uint32_t)local[(size_t)(e & 0xFFFFu)] | (e & 0xFFFF0000u));
+            if (!pad) cf.nnz_cols++;
+        }
+    cf.entries = nl;
+    optimize_component_layout(cf);
+    cf.zeros.clear();
+    for (int r = 0; r < n; r++)
+        if (!cf.live[(size_t)r]) cf.zeros.push_back(r);
+    cf.gv = g;
+    cf.gv.n = cf.n_loc;
+    cf.gv.ell = cf.ell;
+    cf.gv.row_len.assign((size_t)cf.n_loc, (uint8_t)g.max_nnz);
+    cf.ok = true;
+    if (std::getenv("QSIM_DEBUG"))
+        std::fprintf(stderr, "[qsim] state form: %d of %d rows live (%d components), one warp, %d row(s) per lane\n", nl, n, cf.n_comp, cf.rpl);
     return true;
 }
 

@@ -97,13 +97,19 @@ struct ComponentForm {
     // team_warps + c)] = {component chunk, position of the unit in the stage buffer, state column, 0}; component chunk
     // `n_cc` is the empty chunk.
     int rs = 0, n_cc = 0;
+    // State form (state = 1; unitary_state / me_state): the single column is the initial state, supported on the
+    // components it touches (live[r] = 1 for their rows); everything else stays exactly zero.  Same tables, one unit per
+    // touched component with column 0.
+    int state = 0;
+    std::vector<char> live;
     std::vector<Generator> subs;       // per component: generator restricted to it
     std::vector<std::vector<int>> comp_rows;   // per component: its state rows (local row -> state row)
     std::vector<int> cc_first;         // per component: its first component chunk
     std::vector<int> pass;
 };
 bool build_component_form(const Generator &g, int rpl, int cpl, int max_team_warps, ComponentForm &cf);
-bool build_rowsplit_component_form(const Generator &g, int team_warps, ComponentForm &cf);
+bool build_rowsplit_component_form(const Generator &g, int team_warps, ComponentForm &cf, const std::vector<char> *touched = nullptr);
+bool build_state_form(const Generator &g, const std::vector<char> &touched, ComponentForm &cf);
 void optimize_component_layout(ComponentForm &cf);
 long component_layout_cost(const ComponentForm &cf, int S);
 void generator_components(const Generator &g, std::vector<int> &comp_of, std::vector<std::vector<int>> &comps);
@@ -141,5 +147,9 @@ struct qsim_problem {
     std::shared_ptr<struct AddSplitForm> addsplit[2];   // additively split rows (build_addsplit)
     std::shared_ptr<qsim::ComponentForm> cform[2];      // component form of the propagator problems (make_plan)
     bool cform_tried[2] = {false, false};
+    // state forms by the set of components the initial state touches (solve_common), and the components themselves
+    std::vector<std::pair<std::vector<char>, std::shared_ptr<qsim::ComponentForm>>> sforms[2];
+    std::vector<int> comp_of[2];
+    int n_comp[2] = {-1, -1};
     std::mutex plan_mutex;
 };

@@ -188,3 +188,80 @@ def test_row_split_block_systems(sizes, band):
     name = _check(cqs, "unitary_propagator", ts, params, n_comp_min=len(sizes))
     assert "rowsplit" in name
     print(sizes, name)
+
+
+def _check_state(cqs, fn, ts, params, init, expect_pruned, capfd):
+    P = Problem(cqs)
+    n = int(np.prod(P.state_shape(WHICH[fn])))
+    buf = np.full((len(params), len(ts), n), np.nan + 1j * np.nan)
+    os.environ["QSIM_DEBUG"] = "1"
+    try:
+        got, st = P.solve(fn, ts, params=params, init=init, out=buf)
+    finally:
+        del os.environ["QSIM_DEBUG"]
+    err_text = capfd.readouterr().err
+    assert ("state form:" in err_text) == expect_pruned, err_text[-400:]
+    assert not np.any(np.isnan(got.real))
+    want, ost = co.OracleProblem(cqs).solve(WHICH[fn], ts, params, init=init, mode=co.STRUCTURED, n_threads=8)
+    assert np.all(st["retcode"] == 0)
+    assert np.array_equal(st["n_accept"], ost["n_accept"]) and np.array_equal(st["n_reject"], ost["n_reject"])
+    err = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)))
+    assert err <= 1e-8, err
+    assert np.all(got[want == 0] == 0)
+    os.environ["QSIM_NO_PRUNE"] = "1"
+    try:
+        full, fst = Problem(cqs).solve(fn, ts, params=params, init=init)
+    finally:
+        del os.environ["QSIM_NO_PRUNE"]
+    assert np.array_equal(st["n_accept"], fst["n_accept"]) and np.array_equal(st["n_reject"], fst["n_reject"])
+    assert float(np.max(np.abs(got - full))) < 1e-10
+    return got
+
+
+@pytest.mark.gpu
+def test_state_evolution_on_touched_components(capfd):
+    """unitary_state / me_state: only the components the initial state touches are integrated (state forms); an initial
+    state that touches every component runs on the full state."""
+    # cfg2 system: |01> lies in the odd-parity block (4 of 9 levels); a superposition of |00> and |01> touches both
+    cqs, _, _, _ = W.config("cfg2")
+    params = W.amp_freq_grid(64, 64)[[0, 2017, 4095]]
+    ts = np.linspace(0.0, 6.0, 7)
+    psi = np.zeros(9, dtype=complex)
+    psi[1] = 1.0
+    got = _check_state(cqs, "unitary_state", ts, params, psi, True, capfd)
+    assert np.all(got[:, :, [0, 2, 4, 6, 8]] == 0)
+    both = np.zeros(9, dtype=complex)
+    both[0] = both[1] = np.sqrt(0.5)
+    _check_state(cqs, "unitary_state", ts, params, both, False, capfd)
+    # per-trajectory initial states in different blocks: the union is integrated (here: everything)
+    per = np.zeros((3, 9), dtype=complex)
+    per[0, 1] = per[1, 0] = per[2, 3] = 1.0
+    _check_state(cqs, "unitary_state", ts, params, per, False, capfd)
+    per[1, 0], per[1, 5] = 0.0, 1.0
+    _check_state(cqs, "unitary_state", ts, params, per, True, capfd)
+    # cfg4 system (Lindblad, d^2 = 81): rho0 = |01><01| lies in the (odd, odd) + (even, even) class: 41 of 81 entries
+    cqs4, p4, _, _ = W.config("cfg4")
+    rho = np.zeros((9, 9), dtype=complex)
+    rho[1, 1] = 1.0
+    _check_state(cqs4, "me_state", np.array([0.0, 0.8, 1.6]), p4[[0, 8191]], rho, True, capfd)
+    # cfg5 system (d^2 = 729, 13 components): rho0 = |010><010| touches the 141-row component only (row-split, one pass)
+    cqs5, p5, _, _ = W.config("cfg5")
+    rho5 = np.zeros((27, 27), dtype=complex)
+    rho5[3, 3] = 1.0
+    _check_state(cqs5, "me_state", np.array([0.0, 0.1, 0.2]), p5[[0, 65535]], rho5, True, capfd)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sizes", [[5, 4], [20, 9, 3], [50, 30, 10, 5, 1], [100, 50, 30, 20], [120, 110]])
+def test_state_block_systems(sizes, capfd):
+    rng = np.random.default_rng(99 + sum(sizes))
+    cqs = _block_system(sizes, rng)
+    d = sum(sizes)
+    params = np.array([[0.02], [0.01]])
+    ts = np.array([0.0, 0.5, 1.0])
+    # an initial state inside the component of level 0 (whatever the permutation made of it)
+    P = Problem(cqs)
+    _, lab = _pattern_components(P, 0, params[0])
+    psi = np.where(lab == lab[0], rng.normal(size=d) + 1j * rng.normal(size=d), 0.0)
+    psi /= np.linalg.norm(psi)
+    _check_state(cqs, "unitary_state", ts, params, psi, True, capfd)
