@@ -1,11 +1,9 @@
 #!/bin/bash
-# Round 2, component pruning: follow-up checks (one B200).
+# Round 2: operand chunk sizes of the cfg2 component-form kernel (alternate builds of qsim_inst_lean_c2.cu).
 mkdir -p gpurun_out
 {
-timeout 900 python -m pytest tests/test_component_pruning.py -q -m gpu -k "state" 2>&1 | tail -30
-python scripts/state_probe.py cfg2 4096 20 2>&1 | tail -2
-QSIM_NO_PRUNE=1 python scripts/state_probe.py cfg2 4096 20 2>&1 | tail -2
-python scripts/state_probe.py cfg3 2048 20 2>&1 | tail -2
-QSIM_NO_PRUNE=1 python scripts/state_probe.py cfg3 2048 20 2>&1 | tail -2
-} > gpurun_out/prune_check6.log 2>&1
-tail -60 gpurun_out/prune_check6.log | cut -c1-400
+for tag in b200 ch422 ch444 ch111; do
+  echo "--- $tag"; QSIM_B200_LIB=$PWD/qsimulator.jl_b200/lib/libqsim_$tag.so python scripts/perf_probe.py cfg2:4096:200 2>&1 | tail -1
+done
+} > gpurun_out/prune_check8.log 2>&1
+cat gpurun_out/prune_check8.log | cut -c1-300
