@@ -430,11 +430,11 @@ bool build_component_form(const Generator &g, int rpl, int cpl, int max_team_war
 }
 
 // Row-split form: passes over several units at once (see ComponentForm).  Units are placed largest component first;
-// a pass is filled with as many units of the current component as fit its 3 * team_warps chunks, then topped up with
+// a pass is filled with as many units of the current component as fit its rpl * team_warps chunks, then topped up with
 // units of smaller components.  Within a pass the chunks are dealt to (row-slot, warp) longest rows first, so the
 // warps of the team carry about equal work.
-bool build_rowsplit_component_form(const Generator &g, int team_warps, ComponentForm &cf, const std::vector<char> *touched) {
-    const int n = g.n, W = team_warps, slots = 3 * W;
+bool build_rowsplit_component_form(const Generator &g, int team_warps, ComponentForm &cf, const std::vector<char> *touched, int rpl) {
+    const int n = g.n, W = team_warps, slots = rpl * W;
     std::vector<std::vector<int>> comps;
     generator_components(g, cf.comp_of, comps);
     cf.ok = false;
@@ -450,10 +450,10 @@ bool build_rowsplit_component_form(const Generator &g, int team_warps, Component
         cf.live.assign((size_t)n, 0);
         for (int r = 0; r < n; r++) cf.live[(size_t)r] = (*touched)[(size_t)cf.comp_of[(size_t)r]];
     }
-    cf.rpl = 3;
+    cf.rpl = rpl;
     cf.cpl = 1;
     cf.team_warps = W;
-    cf.n_loc = 96 * W;
+    cf.n_loc = 32 * rpl * W;
     cf.stride = 1;
     cf.max_nnz = g.max_nnz;
     // components in placement order, their generators and chunk lengths (rows sorted by length, as rowsplit_rows does)

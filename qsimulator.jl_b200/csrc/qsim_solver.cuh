@@ -1272,6 +1272,10 @@ struct Kern {
                 const_cast<uint32_t &>(ell[i][0]) = (uint32_t)d.z;
                 const_cast<uint32_t &>(ell[i][MAXNNZ > 1 ? 1 : 0]) = (uint32_t)d.w & 0xFFu;
                 const_cast<uint32_t &>(ell[i][MAXNNZ > 2 ? 2 : 0]) = (uint32_t)d.w >> 8;
+                // the next pass's record (pass 0 of the next stage loop after the last one) on its way into L1: a pass
+                // otherwise begins with an exposed L2 round trip on every lane
+                const int bn = b + 1 < a.n_batches ? b + 1 : 0;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rs_pass + ((size_t)bn * (size_t)(RPL * a.team_warps) + chunk) * 32 + g.lane));
             }
         };
 

@@ -108,7 +108,8 @@ struct ComponentForm {
     std::vector<int> pass;
 };
 bool build_component_form(const Generator &g, int rpl, int cpl, int max_team_warps, ComponentForm &cf);
-bool build_rowsplit_component_form(const Generator &g, int team_warps, ComponentForm &cf, const std::vector<char> *touched = nullptr);
+bool build_rowsplit_component_form(const Generator &g, int team_warps, ComponentForm &cf, const std::vector<char> *touched = nullptr,
+                                      int rpl = 3);
 bool build_state_form(const Generator &g, const std::vector<char> &touched, ComponentForm &cf);
 void optimize_component_layout(ComponentForm &cf);
 long component_layout_cost(const ComponentForm &cf, int S);
