@@ -1300,7 +1300,7 @@ static void choose_component_form(const Generator &gp, std::shared_ptr<Component
         }
 }
 
-static int make_plan(qsim_problem *p, int which, Plan &pl, const ComponentForm *state_cf = nullptr) {
+static int make_plan(qsim_problem *p, int which, Plan &pl, const ComponentForm *state_cf = nullptr, bool allow_prune = true) {
     pl.w = which >= 2 ? 1 : 0;
     if (int rc = ensure_generator(p, pl.w)) return rc;
     const Generator &gp = p->gen[pl.w];
@@ -1327,7 +1327,7 @@ static int make_plan(qsim_problem *p, int which, Plan &pl, const ComponentForm *
     // above and below run on the full state.
     if (state_cf) {
         pl.cf = state_cf;   // state evolution on the components the initial state touches (solve_common, state_form_for)
-    } else if (pl.identity && !pl.af && !std::getenv("QSIM_NO_PRUNE") && !std::getenv("QSIM_BLOCKED") && !std::getenv("QSIM_TIERED") &&
+    } else if (pl.identity && allow_prune && !pl.af && !std::getenv("QSIM_NO_PRUNE") && !std::getenv("QSIM_BLOCKED") && !std::getenv("QSIM_TIERED") &&
         !std::getenv("QSIM_SPLIT") && !std::getenv("QSIM_SPLIT_ROWS") && !std::getenv("QSIM_COLPERLANE") && !std::getenv("QSIM_LEAN9") &&
         gp.n <= 9 * 96) {
         std::lock_guard<std::mutex> lk(p->plan_mutex);
@@ -1893,11 +1893,14 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
                     return fail(QSIM_ERR_ARG, "ts must be sorted");
     }
     if (n_traj == 0) return QSIM_OK;
+    // (abstol = 0: the reference's error norm divides 0 by 0 on entries that are exactly zero; the full state is
+    // integrated then, so that the library fails the same way instead of succeeding on the component blocks)
+    const bool allow_prune = o.abstol > 0.0;
     const ComponentForm *state_cf = nullptr;
-    if ((which == 1 || which == 3) && !dev_ptrs && init)
+    if ((which == 1 || which == 3) && !dev_ptrs && init && allow_prune)
         if (int rc = state_form_for(p, which, init, init_stride, sh.total, &state_cf)) return rc;
     Plan pl;
-    if (int rc = make_plan(p, which, pl, state_cf)) return rc;
+    if (int rc = make_plan(p, which, pl, state_cf, allow_prune)) return rc;
     CU(cudaSetDevice(c->device));
     qsim_problem::DeviceCopy *dc = nullptr;
     if (int rc = ensure_device_copy(c, p, pl.w, &dc)) return rc;

@@ -265,3 +265,23 @@ def test_state_block_systems(sizes, capfd):
     psi = np.where(lab == lab[0], rng.normal(size=d) + 1j * rng.normal(size=d), 0.0)
     psi /= np.linalg.norm(psi)
     _check_state(cqs, "unitary_state", ts, params, psi, True, capfd)
+
+
+@pytest.mark.gpu
+def test_abstol_zero_integrates_the_full_state():
+    """abstol = 0 makes the reference's error norm 0/0 on exactly-zero entries; the library then integrates the full
+    state (no pruning), so it behaves exactly like its un-pruned kernels."""
+    from qsim_b200 import _abi
+    cqs, _, _, _ = W.config("cfg2")
+    params = W.amp_freq_grid(64, 64)[[7, 3000]]
+    ts = np.arange(0.0, 3.0)
+    o = _abi.default_opts()
+    o.abstol = 0.0
+    a, sa = Problem(cqs).solve("unitary_propagator", ts, params=params, opts=o)
+    os.environ["QSIM_NO_PRUNE"] = "1"
+    try:
+        b, sb = Problem(cqs).solve("unitary_propagator", ts, params=params, opts=o)
+    finally:
+        del os.environ["QSIM_NO_PRUNE"]
+    assert np.array_equal(sa, sb)
+    assert np.array_equal(a, b, equal_nan=True)
