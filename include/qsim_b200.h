@@ -250,6 +250,14 @@ int qsim_problem_eval(qsim_problem *prob, int kind, double t,
  *   me_propagator:      out[traj][k][d^2*d^2]
  *   me_state:           out[traj][k][d*d]      rho0[d*d]
  * stats may be NULL.
+ *
+ * Every entry of every result is written.  When the generator's graph splits into
+ * connected components (e.g. a conserved excitation-number parity), the entries
+ * that couple different components are exactly zero -- in the reference as well:
+ * its dense products (time_evolution.jl:31-37, 98-111) only ever add 0 * x there --
+ * and the library writes them as zeros without integrating them; step sequences
+ * and norms are those of the full state.  The same holds for state solvers whose
+ * (host-side) initial states touch only some components.
  */
 int qsim_unitary_propagator(qsim_ctx *ctx, qsim_problem *prob, int64_t n_traj,
                             const double *params, const double *ts, int n_ts,
