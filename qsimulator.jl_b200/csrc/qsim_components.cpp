@@ -545,6 +545,27 @@ bool build_rowsplit_component_form(const Generator &g, int team_warps, Component
         for (int r = 0; r < n; r++)
             if (cf.comp_of[(size_t)r] != cf.comp_of[(size_t)c]) cf.zeros.push_back(c * n + r);
     if (std::getenv("QSIM_DEBUG")) {
+        // self-check: every (component, column) unit -- all of the component's chunks -- is placed exactly once
+        // (state forms: column 0 of the touched components only)
+        long bad = 0;
+        std::vector<int> comp_of_cc((size_t)n_cc, 0);
+        for (int ki = 0; ki < nk_total; ki++)
+            for (int t = 0; t < ((int)cf.comp_rows[(size_t)ki].size() + 31) / 32; t++) comp_of_cc[(size_t)(cf.cc_first[(size_t)ki] + t)] = ki;
+        std::vector<int> seen((size_t)n_cc * n, 0);
+        for (size_t i = 0; i < cf.pass.size(); i += 4)
+            if (cf.pass[i] != n_cc) seen[(size_t)cf.pass[i] * n + (size_t)cf.pass[i + 2]]++;
+        for (int cc = 0; cc < n_cc; cc++) {
+            const int ki = comp_of_cc[(size_t)cc];
+            for (int c = 0; c < n; c++) {
+                bool want;
+                if (touched)
+                    want = c == 0 && (*touched)[(size_t)order[(size_t)ki]];
+                else
+                    want = std::find(cf.comp_rows[(size_t)ki].begin(), cf.comp_rows[(size_t)ki].end(), c) != cf.comp_rows[(size_t)ki].end();
+                if (seen[(size_t)cc * n + c] != (want ? 1 : 0)) bad++;
+            }
+        }
+        std::fprintf(stderr, "[qsim] component form row-split self-check: %ld bad entries\n", bad);
         long used = 0;
         for (size_t i = 0; i < cf.pass.size(); i += 4) used += cf.pass[i] != n_cc ? 1 : 0;
         std::fprintf(stderr, "[qsim] row-split component form: %d components (largest %zu rows), %d component chunks, %d passes of %d chunk "

@@ -285,3 +285,38 @@ def test_abstol_zero_integrates_the_full_state():
         del os.environ["QSIM_NO_PRUNE"]
     assert np.array_equal(sa, sb)
     assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("sizes,lindblad,band", [([5, 4], False, 2), ([1, 1], False, 2), ([7, 7, 2], False, 2), ([14, 13], False, 2),
+                                                 ([12, 11, 10, 9], False, 2), ([32, 32, 32], False, 2), ([41, 40], False, 2),
+                                                 ([50, 30, 10, 5, 1], False, 2), ([90, 4, 2], False, 2), ([3, 2, 1], True, 2),
+                                                 ([6, 3], True, 2), ([70, 60], False, 2), ([120, 40, 5, 3, 1, 1], False, 2),
+                                                 ([20, 20], False, 19), ([30, 25, 18], False, 24)])
+def test_component_form_tables_cover_the_blocks(sizes, lindblad, band, capfd):
+    """No GPU needed: the packing of (component, column) units into warps / row-split passes is checked by the builder's
+    own self-check (QSIM_DEBUG): every entry inside a component block is held by exactly one (batch, local row, column
+    slot), nothing outside is, for every kernel shape the chooser tries."""
+    rng = np.random.default_rng(424242 + sum(sizes) + band)
+    cqs = _block_system(sizes, rng, lindblad=lindblad, band=band)
+    fn = "me_propagator" if lindblad else "unitary_propagator"
+    os.environ["QSIM_DEBUG"] = "1"
+    try:
+        P = Problem(cqs)
+        info = P.plan_info(fn)
+        name = P.kernel_name(fn)
+    finally:
+        del os.environ["QSIM_DEBUG"]
+    err = capfd.readouterr().err
+    checks = [ln for ln in err.splitlines() if "self-check" in ln]
+    assert checks, err[-500:]
+    assert all(ln.rstrip().endswith(" 0 bad entries") for ln in checks), checks
+    assert info["components"] >= len(sizes)
+    n_state = info["n"]
+    kind = 1 if lindblad else 0
+    nc, lab = _pattern_components(P, kind, np.array([0.02]))
+    assert nc == info["components"]
+    # executed multiply-adds: the blocks' share of the generator's
+    sizes_c = np.bincount(lab)
+    assert P.flops_per_rhs(fn) < (4.0 if info["value_mode"] >= 1 else 8.0) * info["nnz"] * n_state
+    assert ("rowsplit" in name) == (n_state > 96 or info["max_row"] > 16)
+    assert sizes_c.max() <= n_state
