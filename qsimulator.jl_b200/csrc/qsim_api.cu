@@ -1287,9 +1287,9 @@ static void choose_component_form(const Generator &gp, std::shared_ptr<Component
                 // multi-warp teams share a CTA of up to eight warps, two CTAs per SM where the variant asks for it
                 const int teams_per_sm = W == 1 ? 4 * kv->minb : kv->minb * tpc;
                 score = (double)teams_per_sm / (2200.0 + 650.0 * E + 340.0 * (W - 1));   // (+ team barriers; measured on cfg3)
-                if (const char *force = std::getenv("QSIM_CF_SHAPE"))   // development: "r1c4" forces a shape
-                    if (std::string(force) == "r" + std::to_string(rpl) + "c" + std::to_string(cpl)) score = 1e9;
             }
+            if (const char *force = std::getenv("QSIM_CF_SHAPE"))   // development: "r1c4" forces a shape
+                if (std::string(force) == "r" + std::to_string(rpl) + "c" + std::to_string(cpl)) score = 1e9;
             if (std::getenv("QSIM_DEBUG"))
                 std::fprintf(stderr, "[qsim] component form r%dc%d: %d components, %d warps%s, %d batches, %d local rows, %s: score %.3g\n",
                              rpl, cpl, cf->n_comp, W, cf->streamed ? " (streamed)" : "", cf->n_batches, cf->n_loc, kv->name, score * 1e3);
