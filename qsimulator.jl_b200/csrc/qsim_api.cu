@@ -1034,7 +1034,7 @@ static const KernelVariant *find_variant(int rpl, int cpl, int max_nnz, int bloc
                                               variants_r1c4_t256, variants_r2c1_t128,
                                               variants_r2c2_t256, variants_r3c1_t128, variants_r3c1_t256,
                                               variants_rowsplit, variants_colperlane, variants_blocked, variants_lean,
-                                              variants_lean_t256, variants_r1c2_t128, variants_lean_c2, variants_lean_c2_t256, variants_rowsplit_r1};
+                                              variants_lean_t256, variants_lean_c2, variants_lean_c2_t256};
     // (development: QSIM_MAX_MINB caps the occupancy target of the chosen variant, e.g. 3 keeps the 168-register lean kernels)
     const int max_minb = std::getenv("QSIM_MAX_MINB") ? std::atoi(std::getenv("QSIM_MAX_MINB")) : 99;
     const KernelVariant *best = nullptr;
@@ -1337,16 +1337,12 @@ static int make_plan(qsim_problem *p, int which, Plan &pl, const ComponentForm *
                 choose_component_form(gp, p->cform[pl.w]);
             else {
                 // row-split kernels: passes over several units at once, eight-warp teams with three rows per lane.
-                // Opt-in (QSIM_RS_R1=1): sixteen-warp teams with one row per lane at 128 registers (16 chunks per pass
-                // instead of 24, twice the warps per SM) -- parity-green and 2.5 % slower on cfg5 (115.1 ms against 112.2 ms
-                // per 592 x 2 ns): a pass costs about 1500 cycles per stage whatever a warp's share of the rows is.
+                // (Sixteen-warp teams with one row per lane at 128 registers -- 16 chunks per pass instead of 24, twice
+                // the warps per SM -- were measured parity-green and 2.5 % slower on cfg5, 115.1 ms against 112.2 ms per
+                // 592 x 2 ns: a pass costs about 1500 cycles per stage whatever a warp's share of the rows is.  Their
+                // instantiations were dropped again; build_rowsplit_component_form still takes the rows per lane.)
                 auto cf = std::make_shared<ComponentForm>();
-                bool ok = false;
-                if (std::getenv("QSIM_RS_R1") && find_variant(1, 1, 1, 512, 0, 1)) ok = build_rowsplit_component_form(gp, 16, *cf, nullptr, 1);
-                if (!ok) {
-                    cf = std::make_shared<ComponentForm>();
-                    ok = build_rowsplit_component_form(gp, 8, *cf);
-                }
+                const bool ok = build_rowsplit_component_form(gp, 8, *cf);
                 if (ok) p->cform[pl.w] = cf;
             }
         }

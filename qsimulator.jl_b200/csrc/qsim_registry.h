@@ -30,10 +30,8 @@ QSIM_DECLARE(variants_colperlane)
 QSIM_DECLARE(variants_blocked)
 QSIM_DECLARE(variants_lean)
 QSIM_DECLARE(variants_lean_t256)
-QSIM_DECLARE(variants_r1c2_t128)
 QSIM_DECLARE(variants_lean_c2)
 QSIM_DECLARE(variants_lean_c2_t256)
-QSIM_DECLARE(variants_rowsplit_r1)
 
 #define QSIM_VARIANT(R, C, M, T, B, I)                                                                    \
     {                                                                                                     \

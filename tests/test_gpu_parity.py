@@ -367,12 +367,13 @@ def test_repeated_runs_are_bitwise_identical():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env,tag", [("QSIM_NO_LEAN", "tsit5_r1c2_nnz5_t128_vm2"), ("QSIM_NO_PRUNE", "tsit5_lean_r1c3_nnz5_t128_vm2"),
+@pytest.mark.parametrize("env,tag", [("QSIM_NO_LEAN", "tsit5_r2c1_nnz5_t128_vm2"), ("QSIM_NO_PRUNE", "tsit5_lean_r1c3_nnz5_t128_vm2"),
                                      ("QSIM_MAX_MINB", "tsit5_lean_r1c2_nnz5_t128b3_vm2"), ("QSIM_TIERED", "lean_tiered_r3c1"),
                                      ("QSIM_SPLIT", "lean_split_r1c3_nnz3"), ("QSIM_ADDSPLIT", "lean_addsplit_r1c3_nnz3")])
 def test_cfg2_kernel_variants(monkeypatch, env, tag):
     """The default cfg2 kernel is the lean row-per-lane one on the component form (two blocks of 5 x 5 and 4 x 4 entries,
-    two columns per lane, 128 registers, 16 warps per SM).  Its 255-register form (QSIM_NO_LEAN=1), its 168-register
+    two columns per lane, 128 registers, 16 warps per SM).  The 255-register kernels (QSIM_NO_LEAN=1: two rows of one column per lane
+    on the component form), its 168-register
     form (QSIM_MAX_MINB=3), the lean kernel on the full 9 x 9 state (QSIM_NO_PRUNE=1) and the three opt-in mappings -- three rows of one column per lane sorted into tiers
     (QSIM_TIERED=1), split rows with helper lanes (QSIM_SPLIT=1), additively split rows (QSIM_ADDSPLIT=1: the long row's
     state carried as two parts that add up to the physical entry) -- take the same step sequence and agree with it to
