@@ -2055,7 +2055,10 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
             CU(c->out.reserve(traj_bytes * (size_t)per_chunk));
             if (n_chunks > 1) CU(c->out2.reserve(traj_bytes * (size_t)per_chunk));
         }
-        if (!stats_direct) CU(c->stats.reserve(sizeof(qsim_traj_stats) * (size_t)n_traj));
+        // the kernel writes a trajectory's stats where it writes its results: at the sweep point's own position when the
+        // results go out in place (zero-copy), so a shard's device stats buffer spans the shard's positions
+        if (!stats_direct)
+            CU(c->stats.reserve(sizeof(qsim_traj_stats) * (size_t)(zero_copy ? sh.first + (n_traj - 1) * sh.step + 1 : n_traj)));
         if (params && p->n_params > 0) CU(cudaMemcpyAsync(c->params.p, params, b_params, cudaMemcpyHostToDevice, stream));
         CU(cudaMemcpyAsync(c->ts.p, ts, b_ts, cudaMemcpyHostToDevice, stream));
         if (init) {
@@ -2214,9 +2217,15 @@ static int solve_common(qsim_ctx *c, qsim_problem *p, int which, int64_t n_traj,
             if (!zero_copy)
                 CU(cudaMemcpy2DAsync((char *)out + traj_bytes * (size_t)sh.first, traj_bytes * (size_t)sh.step, c->out.p, traj_bytes,
                                      traj_bytes, (size_t)n_traj, cudaMemcpyDeviceToHost, stream));
-            if (stats && !stats_direct)
-                CU(cudaMemcpy2DAsync(stats + sh.first, sizeof(qsim_traj_stats) * (size_t)sh.step, c->stats.p, sizeof(qsim_traj_stats),
-                                     sizeof(qsim_traj_stats), (size_t)n_traj, cudaMemcpyDeviceToHost, stream));
+            if (stats && !stats_direct) {
+                if (zero_copy)   // device stats at the points' own positions (see above)
+                    CU(cudaMemcpy2DAsync(stats + sh.first, sizeof(qsim_traj_stats) * (size_t)sh.step,
+                                         (const qsim_traj_stats *)c->stats.p + sh.first, sizeof(qsim_traj_stats) * (size_t)sh.step,
+                                         sizeof(qsim_traj_stats), (size_t)n_traj, cudaMemcpyDeviceToHost, stream));
+                else
+                    CU(cudaMemcpy2DAsync(stats + sh.first, sizeof(qsim_traj_stats) * (size_t)sh.step, c->stats.p, sizeof(qsim_traj_stats),
+                                         sizeof(qsim_traj_stats), (size_t)n_traj, cudaMemcpyDeviceToHost, stream));
+            }
             CU(cudaStreamSynchronize(stream));
         }
         return QSIM_OK;

@@ -68,9 +68,12 @@ def test_block_cyclic_fanout_two_contexts_one_device():
     assert np.array_equal(got, ref) and np.array_equal(st, st_ref)
     pin = PinnedArray((len(params), len(ts), 81), np.complex128)
     pin.array[...] = np.nan   # every entry must be delivered
-    got2, _ = prob.solve("unitary_propagator", ts, params=params, ctx=ctxs, out=pin.array)
-    bad = np.argwhere(~((got2 == ref) | (np.isnan(got2.real) & np.isnan(ref.real))))
-    assert len(bad) == 0, (len(bad), bad[:8].tolist(), got2[tuple(bad[0])], ref[tuple(bad[0])])
+    for _ in range(6):   # (a shard's device stats buffer once overflowed here and corrupted a neighbour's inputs now and then)
+        pin.array[...] = np.nan
+        got2, st2 = prob.solve("unitary_propagator", ts, params=params, ctx=ctxs, out=pin.array)
+        bad = np.argwhere(~((got2 == ref) | (np.isnan(got2.real) & np.isnan(ref.real))))
+        assert len(bad) == 0, (len(bad), bad[:8].tolist(), got2[tuple(bad[0])], ref[tuple(bad[0])])
+        assert np.array_equal(st2, st_ref)
     # states with per-trajectory initial vectors and save grids
     rng = np.random.default_rng(5)
     psi = rng.normal(size=(len(params), 9)) + 1j * rng.normal(size=(len(params), 9))
