@@ -30,10 +30,11 @@ def _pattern_components(P, kind, row):
 
 
 @pytest.mark.parametrize("name,kernel,ncomp,ratio", [("cfg2", "r1c2", 2, 0.5), ("cfg3", "r1c3", 2, 0.5),
-                                                      ("cfg4", "r3c1", 2, 0.5)])
+                                                      ("cfg4", "r3c1", 2, 0.5), ("cfg5", "rowsplit", 13, 0.1452)])
 def test_plan_of_benchmark_configs(name, kernel, ncomp, ratio):
-    """The transmon gates of benchmarks.jl conserve the parity of the total excitation number: two components,
-    half of the propagator's entries, half of the generator multiply-adds."""
+    """The lab-frame transmon gates of benchmarks.jl conserve the parity of the total excitation number: two
+    components, half of the propagator's entries, half of the generator multiply-adds; the rotating-frame exchange form
+    with decay and dephasing (cfg5) conserves the excitation-number difference of |i><j|: 13 components, 14.5 %."""
     cqs, params, _, which = W.config(name)
     P = Problem(cqs)
     info = P.plan_info(which)
