@@ -16,8 +16,8 @@ e2e    = propagators/s through the public host-buffer API: H2D of the parameter 
 roofline: FP64 pipe.  achieved = executed algorithmic flop of the sparse generator application (4 or 8 flop x
          stored entries x columns per RHS, 6 RHS per attempted step + 2, from the solver's own step counts) /
          kernel time; peak = DFMA peak measured in the same run (MEASURED_PEAKS.json has no FP64 entry).
-         traffic: not measured in this run (null); the algorithmic bytes are stated, and profiles/traffic.json keeps
-         the ncu cross-check.
+         traffic: DRAM bytes of one launch, measured in this run by an ncu child process (measure_traffic); the
+         algorithmic bytes are stated beside it and profiles/traffic.json keeps the committed capture as a cross-check.
 cpu_baseline / --impl reference: the C oracle in reference-faithful mode on the host cores (threads over the
          sweep, the analogue of Threads.@threads) -- a C restatement of the reference algorithm, not Julia.
 
@@ -163,6 +163,41 @@ def pruning_info(prob, which, info):
     f = prob.flops_per_rhs(which)
     return {"components": info["components"], "integrated_fraction": f / full if full > 0 else 1.0,
             "flops_per_rhs_full_state": full}
+
+
+def measure_traffic(args):
+    """roofline.traffic, measured in this run: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of
+    the benchmark kernel on the benchmark workload, from a child process of this script under ncu (two metrics, one
+    replay pass; the child repeats the device-resident launch of the timed region and ncu profiles its second launch).
+    Nothing timed runs under the profiler.  Returns (bytes or None, note)."""
+    import shutil
+    ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.exists("/usr/local/cuda/bin/ncu") else None)
+    if ncu is None:
+        return None, "ncu not found on this box"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
+           "-k", "regex:solve_kernel", "-s", "1", "-c", "1", "--csv", sys.executable, os.path.abspath(__file__), "--traffic-child"]
+    if args.small:
+        cmd.append("--small")
+    if args.points:
+        cmd += ["--points", str(args.points)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    except (OSError, subprocess.TimeoutExpired) as e:
+        return None, f"ncu child failed: {type(e).__name__}"
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, seen = 0.0, 0
+    import csv as _csv
+    for row in _csv.reader(r.stdout.splitlines()):
+        if len(row) >= 3 and row[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and row[-2] in unit:
+            try:
+                total += float(row[-1].replace(",", "")) * unit[row[-2]]
+                seen += 1
+            except ValueError:
+                pass
+    if seen != 2:
+        return None, f"ncu child gave no DRAM counters (exit {r.returncode}): {(r.stderr or r.stdout)[-160:]!r}"
+    return total, ("dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, measured by an "
+                   "ncu child process of this run (second of two device-resident launches, L2 flushed before it)")
 
 
 def recorded_traffic(kernel, n_traj, n_ts):
@@ -382,6 +417,8 @@ def main():
     ap.add_argument("--budget-s", type=float, default=400.0, help="time budget for the --configs block")
     ap.add_argument("--small", action="store_true", help="reduced sweep (1776 points, 20 ns) for ncu captures")
     ap.add_argument("--points", type=int, default=0, help="development: override the number of sweep points")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child process that measures roofline.traffic")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     global SMALL, POINTS
     SMALL = args.small
@@ -429,6 +466,14 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.traffic_child:
+        # child of measure_traffic(): the same device-resident launch twice (L2 flushed before each); ncu profiles the second
+        for _ in range(2):
+            flush.zero_()
+            launch()
+        torch.cuda.synchronize()
+        return
 
     peak_tflops = ctx.peak_fp64(300.0)
     for _ in range(max(args.warmup, 3)):
@@ -496,6 +541,10 @@ def main():
                     "sample": f"{n_sample} of the 4096 sweep points (evenly spaced), full ts=0:200, {secs:.1f} s; "
                               "C restatement of the reference algorithm (dense per-RHS assembly + zgemm), not Julia"}
 
+    traffic, traffic_note = None, "not measured (multi-rank run or --no-traffic)"
+    if rank == 0 and world == 1 and not args.no_traffic:
+        traffic, traffic_note = measure_traffic(args)
+
     # ---- the other BASELINE configs (strong-sharded over the ranks) ----
     extra = {}
     names = [] if (args.configs in ("", "none") or SMALL or POINTS) else [c for c in args.configs.split(",") if c in EXTRA]
@@ -550,8 +599,7 @@ def main():
                        "unitarity_err_final": unit_err},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / peak_tflops if peak_tflops > 0 else None,
-                         "traffic": None, "traffic_note": "not measured inside this run; algorithmic_bytes is the result "
-                         "stream + parameters one launch must move",
+                         "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_note": traffic_note,
                          "algorithmic_bytes": int(out_bytes + params.nbytes + n_traj * 32),
                          "traffic_crosscheck": xcheck, "traffic_crosscheck_source": xsrc,
                          "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure; "
